@@ -1,0 +1,130 @@
+/*
+ * acm_gpu.h -- batched ACM decode on a B200 (the entry point the reference does
+ * not have).  Plain C ABI: pointers and sizes only.
+ *
+ * One call decodes thousands to millions of INDEPENDENT ACM streams.  It
+ * replaces, for every stream at once, the loop a reference caller writes around
+ *   acm_open_decoder (decode.c:758) -> acm_read_loop (util.c:258) -> acm_close
+ * and produces, per stream, exactly what that loop produces:
+ *   PCM      the words acm_read delivered (decode.c:826-876), in the format
+ *            (bigendianp, wordlen, sgned) of output_values (decode.c:657-677);
+ *            when pad_tail is set the rest of the stream's total_values words
+ *            are zero bytes, which is byte-for-byte `acmtool -d -r` (acmtool.c:293-310)
+ *   status   what the LAST acm_read returned: 0, ACM_ERR_CORRUPT (-6) or
+ *            ACM_ERR_UNEXPECTED_EOF (-7); ACM_ERR_NOT_ACM (-3) if the header is
+ *            rejected (decode.c:712-752); ACM_ERR_OTHER (-1) if the image is too
+ *            large for the device decoder (>= 512 MiB)
+ *   words    acm->stream_pos at that moment
+ *
+ * Streams are "file images": the bytes of a .acm / WAVC file, header included,
+ * concatenated in one blob (any alignment; 16-byte aligned images are fastest).
+ */
+#ifndef ACM_GPU_H
+#define ACM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACM_GPU_ABI_VERSION 1
+
+typedef struct acm_gpu_stream {
+	/* ---- caller fills */
+	uint64_t in_off;       /* byte offset of the file image inside the blob */
+	uint32_t in_len;       /* image length in bytes */
+	uint32_t reserved0;
+	uint64_t out_off;      /* byte offset of this stream's PCM inside `out`; multiple of 16
+				  (acm_gpu_layout assigns it) */
+	/* ---- acm_gpu_probe fills (header fields, read_header decode.c:712-752) */
+	uint32_t total_values; /* PCM words, all channels */
+	uint32_t channels;     /* effective, after force_chans (decode.c:795-799) */
+	uint32_t acm_channels; /* as written in the header */
+	uint32_t rate;
+	uint32_t level;
+	uint32_t rows;
+	uint32_t wavc;         /* 1 if the 28-byte WAVC pre-header is present */
+	/* ---- decode fills */
+	int32_t status;
+	uint32_t words;
+	uint32_t reserved1;
+	uint64_t checksum;     /* sum over emitted words i of (i+1)*(u_i+1) mod 2^64, u_i the word as
+				  an unsigned wordlen-byte integer; 0 unless want_checksums */
+} acm_gpu_stream;
+
+typedef struct acm_gpu_opts {
+	int32_t device;         /* CUDA ordinal; -1 = the calling thread's current device */
+	int32_t bigendianp;     /* as acm_read: 0 little endian, 1 big endian */
+	int32_t wordlen;        /* 2 (reference), 3 or 4 (extension) */
+	int32_t sgned;          /* 1 signed, 0 unsigned (adds the sign bit, decode.c:640) */
+	int32_t force_chans;    /* as acm_open_decoder */
+	int32_t want_checksums; /* compute acm_gpu_stream.checksum on the device */
+	int32_t pad_tail;       /* zero-fill words [words, total_values) of every stream */
+	int32_t kernel;         /* 0 auto; 1 force the generic kernel (testing) */
+	int32_t reserved[8];
+} acm_gpu_opts;
+
+typedef struct acm_gpu_batch {
+	const void *blob;      /* concatenated file images */
+	uint64_t blob_len;
+	int32_t blob_on_device; /* 0: host memory, 1: device memory of opts->device */
+	int32_t out_on_device;
+	void *out;             /* PCM destination */
+	uint64_t out_len;
+	acm_gpu_stream *streams; /* host array, n entries */
+	uint64_t n;
+} acm_gpu_batch;
+
+/* defaults: current device, s16le signed, trust header, no checksums, pad_tail=1 */
+void acm_gpu_opts_init(acm_gpu_opts *o);
+
+/*
+ * Parse the n headers (host or device blob) and fill the header fields of
+ * every stream; a rejected header gets status = ACM_ERR_NOT_ACM and
+ * total_values = 0.  Returns the number of accepted streams or ACM_ERR_*.
+ */
+int64_t acm_gpu_probe(const void *blob, uint64_t blob_len, int blob_on_device,
+		      acm_gpu_stream *streams, uint64_t n, const acm_gpu_opts *opts);
+
+/* Assign out_off back to back (16-byte aligned); returns the bytes `out` must hold. */
+uint64_t acm_gpu_layout(acm_gpu_stream *streams, uint64_t n, int wordlen);
+
+/*
+ * One-shot decode.  Host blobs/outputs are staged through pinned buffers and
+ * copied inside the call (pipelined with the kernels); device pointers are used
+ * in place.  Streams must have been probed.  Returns ACM_OK, or ACM_ERR_OTHER for
+ * a CUDA/runtime failure (per-stream problems are reported in streams[i].status).
+ */
+int acm_gpu_decode_batch(const acm_gpu_batch *batch, const acm_gpu_opts *opts);
+
+/*
+ * Resident path: build the device-side descriptor tables once, then launch the
+ * decode kernels any number of times on device-resident blob/out pointers.
+ */
+typedef struct acm_gpu_plan acm_gpu_plan;
+
+acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *streams, uint64_t n,
+				  const acm_gpu_opts *opts, int *err);
+/* asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream) */
+int acm_gpu_plan_run(acm_gpu_plan *plan, const void *d_blob, void *d_out, void *cuda_stream);
+/* waits for cuda_stream and copies status / words / checksum into streams[] */
+int acm_gpu_plan_fetch(acm_gpu_plan *plan, acm_gpu_stream *streams, void *cuda_stream);
+/* kernels launched by one acm_gpu_plan_run */
+int acm_gpu_plan_launches(const acm_gpu_plan *plan);
+/* streams routed to the (fast, generic) kernels */
+void acm_gpu_plan_split(const acm_gpu_plan *plan, uint64_t *n_fast, uint64_t *n_generic);
+/* average device time of the kernels of the last run on that plan, ms (CUDA events on cuda_stream) */
+float acm_gpu_plan_last_ms(acm_gpu_plan *plan);
+void acm_gpu_plan_destroy(acm_gpu_plan *plan);
+
+/* last CUDA / runtime error text of the calling thread ("" if none) */
+const char *acm_gpu_last_error(void);
+int acm_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

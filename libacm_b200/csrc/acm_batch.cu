@@ -1,0 +1,485 @@
+/*
+ * acm_batch.cu -- host side of the batched decoder: header parsing, descriptor
+ * tables, kernel launches, and the C ABI declared in include/acm_gpu.h.
+ *
+ * Host work per stream is limited to what the reference does once per stream in
+ * acm_open_decoder (decode.c:758-824): read_header / read_wavc_header
+ * (decode.c:679-752) and the force_chans rule (decode.c:795-799).  Everything the
+ * reference does per block runs on the device.
+ */
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "acm_gpu.h"
+#include "acm_host.h"
+#include "acm_kernels.cuh"
+#include "libacm.h"
+
+using namespace acm;
+
+/* ------------------------------------------------------------------ errors */
+
+static thread_local char g_err[512];
+
+void acm_set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *acm_gpu_last_error(void) { return g_err; }
+extern "C" int acm_gpu_abi_version(void) { return ACM_GPU_ABI_VERSION; }
+
+#define CU(call)                                                                      \
+	do {                                                                          \
+		cudaError_t e_ = (call);                                              \
+		if (e_ != cudaSuccess) {                                              \
+			acm_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call,     \
+				      cudaGetErrorString(e_));                        \
+			goto fail;                                                    \
+		}                                                                     \
+	} while (0)
+
+/* ------------------------------------------------------------------ opts */
+
+extern "C" void acm_gpu_opts_init(acm_gpu_opts *o)
+{
+	memset(o, 0, sizeof(*o));
+	o->device = -1;
+	o->wordlen = 2;
+	o->sgned = 1;
+	o->pad_tail = 1;
+}
+
+static int use_device(const acm_gpu_opts *o)
+{
+	if (o && o->device >= 0) {
+		cudaError_t e = cudaSetDevice(o->device);
+		if (e != cudaSuccess) {
+			acm_set_error("cudaSetDevice(%d): %s", o->device, cudaGetErrorString(e));
+			return ACM_ERR_OTHER;
+		}
+	}
+	return ACM_OK;
+}
+
+/* ------------------------------------------------------------------ probe */
+
+extern "C" int64_t acm_gpu_probe(const void *blob, uint64_t blob_len, int blob_on_device,
+				 acm_gpu_stream *s, uint64_t n, const acm_gpu_opts *opts)
+{
+	acm_gpu_opts defaults;
+	std::vector<uint8_t> hdrs;
+	uint64_t *d_off = nullptr;
+	uint32_t *d_len = nullptr;
+	uint8_t *d_hdr = nullptr;
+	int64_t ok = 0;
+	g_err[0] = 0;
+	if (!opts) {
+		acm_gpu_opts_init(&defaults);
+		opts = &defaults;
+	}
+	if (blob_on_device) {
+		if (use_device(opts) < 0)
+			return ACM_ERR_OTHER;
+		std::vector<uint64_t> off(n);
+		std::vector<uint32_t> len(n);
+		for (uint64_t i = 0; i < n; i++) {
+			off[i] = s[i].in_off;
+			len[i] = s[i].in_len;
+		}
+		hdrs.resize(n * 48);
+		CU(cudaMalloc(&d_off, n * 8 + 8));
+		CU(cudaMalloc(&d_len, n * 4 + 8));
+		CU(cudaMalloc(&d_hdr, n * 48 + 8));
+		CU(cudaMemcpy(d_off, off.data(), n * 8, cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(d_len, len.data(), n * 4, cudaMemcpyHostToDevice));
+		CU(launch_gather_headers((const uint8_t *)blob, blob_len, d_off, d_len, d_hdr, n, 0));
+		CU(cudaMemcpy(hdrs.data(), d_hdr, n * 48, cudaMemcpyDeviceToHost));
+		cudaFree(d_off);
+		cudaFree(d_len);
+		cudaFree(d_hdr);
+		d_off = nullptr; d_len = nullptr; d_hdr = nullptr;
+	}
+	for (uint64_t i = 0; i < n; i++) {
+		acm_header h;
+		const uint8_t *p;
+		uint64_t len = s[i].in_len;
+		if (blob_on_device) {
+			p = hdrs.data() + i * 48;
+		} else {
+			if (s[i].in_off > blob_len)
+				len = 0;
+			else if (s[i].in_off + len > blob_len)
+				len = blob_len - s[i].in_off;
+			p = (const uint8_t *)blob + (len ? s[i].in_off : 0);
+		}
+		int err = acm_parse_header(p, len, opts->force_chans, &h);
+		s[i].total_values = err < 0 ? 0 : h.total_values;
+		s[i].channels = h.channels;
+		s[i].acm_channels = h.acm_channels;
+		s[i].rate = h.rate;
+		s[i].level = h.level;
+		s[i].rows = h.rows;
+		s[i].wavc = h.wavc;
+		s[i].status = err;
+		s[i].words = 0;
+		s[i].checksum = 0;
+		if (err == ACM_OK)
+			ok++;
+	}
+	return ok;
+fail:
+	cudaFree(d_off);
+	cudaFree(d_len);
+	cudaFree(d_hdr);
+	return ACM_ERR_OTHER;
+}
+
+extern "C" uint64_t acm_gpu_layout(acm_gpu_stream *s, uint64_t n, int wordlen)
+{
+	uint64_t at = 0;
+	for (uint64_t i = 0; i < n; i++) {
+		s[i].out_off = at;
+		at += ((uint64_t)s[i].total_values * (uint64_t)wordlen + 15u) & ~(uint64_t)15u;
+	}
+	return at;
+}
+
+/* ------------------------------------------------------------------ plan */
+
+struct acm_gpu_plan {
+	int device;
+	uint64_t n;          /* caller's stream count */
+	uint64_t n_dev;      /* streams that reach the device */
+	uint64_t n_fast, n_generic;
+	Format fmt;
+	std::vector<int32_t> host_status; /* statuses decided on the host (NOT_ACM, OTHER) */
+	DevStream *d_streams;
+	int32_t *d_status;
+	uint32_t *d_words;
+	unsigned long long *d_cks;
+	acm_tables *d_tables;
+	uint32_t *d_counters; /* [0] fast queue, [1] generic queue */
+	GenericScratch scratch;
+	int generic_ctas;
+	int sm_count;
+	cudaEvent_t ev0, ev1;
+	bool timed;
+};
+
+static void plan_free(acm_gpu_plan *p)
+{
+	if (!p)
+		return;
+	cudaFree(p->d_streams);
+	cudaFree(p->d_status);
+	cudaFree(p->d_words);
+	cudaFree(p->d_cks);
+	cudaFree(p->d_tables);
+	cudaFree(p->d_counters);
+	cudaFree(p->scratch.buf);
+	if (p->ev0)
+		cudaEventDestroy(p->ev0);
+	if (p->ev1)
+		cudaEventDestroy(p->ev1);
+	delete p;
+}
+
+static bool fast_eligible(const acm_gpu_stream &, const acm_gpu_opts *)
+{
+	return false; /* acm_fast.cu registers its shapes here (see acm_fast_eligible) */
+}
+
+extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n,
+					     const acm_gpu_opts *opts, int *err_out)
+{
+	acm_gpu_opts defaults;
+	acm_gpu_plan *p = nullptr;
+	std::vector<DevStream> fast, gen;
+	acm_tables host_tab;
+	cudaDeviceProp prop;
+	int err = ACM_ERR_OTHER, dev = 0;
+	uint32_t max_blen = 1, max_cols = 1;
+
+	g_err[0] = 0;
+	if (!opts) {
+		acm_gpu_opts_init(&defaults);
+		opts = &defaults;
+	}
+	if (opts->wordlen < 2 || opts->wordlen > 4) {
+		acm_set_error("wordlen %d not supported (2, 3 or 4)", opts->wordlen);
+		err = ACM_ERR_BADFMT;
+		goto fail;
+	}
+	if (use_device(opts) < 0)
+		goto fail;
+	CU(cudaGetDevice(&dev));
+	CU(cudaGetDeviceProperties(&prop, dev));
+
+	p = new acm_gpu_plan();
+	memset(&p->scratch, 0, sizeof(p->scratch));
+	p->d_streams = nullptr; p->d_status = nullptr; p->d_words = nullptr; p->d_cks = nullptr;
+	p->d_tables = nullptr; p->d_counters = nullptr; p->ev0 = nullptr; p->ev1 = nullptr;
+	p->device = dev;
+	p->n = n;
+	p->sm_count = prop.multiProcessorCount;
+	p->timed = false;
+	p->fmt.wordlen = opts->wordlen;
+	p->fmt.be = opts->bigendianp ? 1 : 0;
+	p->fmt.bias = opts->sgned ? 0u : (1u << (8 * opts->wordlen - 1));
+	p->fmt.checksums = opts->want_checksums ? 1 : 0;
+	p->host_status.assign(n, 0);
+
+	for (uint64_t i = 0; i < n; i++) {
+		const acm_gpu_stream &g = s[i];
+		if (g.status == 0 && (g.out_off & 15u)) {
+			acm_set_error("stream %llu: out_off must be a multiple of 16", (unsigned long long)i);
+			goto fail;
+		}
+		DevStream d;
+		int hs = acm_make_devstream(&g, (uint32_t)i, opts->pad_tail, &d);
+		if (hs < 0) {
+			p->host_status[i] = hs;
+			continue;
+		}
+		uint32_t blen = g.rows << g.level;
+		if (opts->kernel != 1 && fast_eligible(g, opts)) {
+			fast.push_back(d);
+		} else {
+			gen.push_back(d);
+			max_blen = std::max(max_blen, blen);
+			max_cols = std::max(max_cols, 1u << g.level);
+		}
+	}
+	/* longest first: the work queues hand out streams in this order (LPT) */
+	{
+		auto by_len = [](const DevStream &a, const DevStream &b) {
+			if (a.n_attempt != b.n_attempt)
+				return a.n_attempt > b.n_attempt;
+			return a.index < b.index;
+		};
+		std::sort(fast.begin(), fast.end(), by_len);
+		auto by_work = [](const DevStream &a, const DevStream &b) {
+			uint64_t wa = (uint64_t)a.n_attempt * (a.rows << a.level);
+			uint64_t wb = (uint64_t)b.n_attempt * (b.rows << b.level);
+			if (wa != wb)
+				return wa > wb;
+			return a.index < b.index;
+		};
+		std::sort(gen.begin(), gen.end(), by_work);
+	}
+	p->n_fast = fast.size();
+	p->n_generic = gen.size();
+	p->n_dev = p->n_fast + p->n_generic;
+
+	CU(cudaMalloc(&p->d_streams, (p->n_dev + 1) * sizeof(DevStream)));
+	if (p->n_fast)
+		CU(cudaMemcpy(p->d_streams, fast.data(), p->n_fast * sizeof(DevStream), cudaMemcpyHostToDevice));
+	if (p->n_generic)
+		CU(cudaMemcpy(p->d_streams + p->n_fast, gen.data(), p->n_generic * sizeof(DevStream),
+			      cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&p->d_status, (n + 1) * sizeof(int32_t)));
+	CU(cudaMalloc(&p->d_words, (n + 1) * sizeof(uint32_t)));
+	CU(cudaMalloc(&p->d_cks, (n + 1) * sizeof(unsigned long long)));
+	CU(cudaMemset(p->d_status, 0, (n + 1) * sizeof(int32_t)));
+	CU(cudaMemset(p->d_words, 0, (n + 1) * sizeof(uint32_t)));
+	CU(cudaMemset(p->d_cks, 0, (n + 1) * sizeof(unsigned long long)));
+	acm_tables_build(&host_tab);
+	CU(cudaMalloc(&p->d_tables, sizeof(acm_tables)));
+	CU(cudaMemcpy(p->d_tables, &host_tab, sizeof(acm_tables), cudaMemcpyHostToDevice));
+	CU(cudaMalloc(&p->d_counters, 64));
+	CU(cudaEventCreate(&p->ev0));
+	CU(cudaEventCreate(&p->ev1));
+
+	if (p->n_generic) {
+		size_t stride = generic_scratch_words(max_blen, max_cols);
+		size_t budget = (size_t)4 << 30; /* bytes of scratch we are willing to hold */
+		int ctas = p->sm_count * 4;
+		if ((uint64_t)ctas > p->n_generic)
+			ctas = (int)p->n_generic;
+		while (ctas > 1 && (size_t)ctas * stride * 4 > budget)
+			ctas /= 2;
+		p->generic_ctas = ctas;
+		p->scratch.stride = stride;
+		p->scratch.max_blen = max_blen;
+		p->scratch.max_cols = max_cols;
+		CU(cudaMalloc(&p->scratch.buf, (size_t)ctas * stride * 4));
+	}
+	if (err_out)
+		*err_out = ACM_OK;
+	return p;
+fail:
+	plan_free(p);
+	if (err_out)
+		*err_out = err;
+	return nullptr;
+}
+
+extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out, void *cuda_stream)
+{
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	KernelArgs a;
+	g_err[0] = 0;
+	CU(cudaSetDevice(p->device));
+	CU(cudaMemsetAsync(p->d_counters, 0, 64, st));
+	CU(cudaEventRecord(p->ev0, st));
+	a.blob = (const uint8_t *)d_blob;
+	a.out = (uint8_t *)d_out;
+	a.status = p->d_status;
+	a.words = p->d_words;
+	a.cks = p->d_cks;
+	a.tables = p->d_tables;
+	a.fmt = p->fmt;
+	if (p->n_generic) {
+		a.streams = p->d_streams + p->n_fast;
+		a.count = (uint32_t)p->n_generic;
+		a.counter = p->d_counters + 1;
+		CU(launch_generic(a, p->scratch, p->generic_ctas, st));
+	}
+	CU(cudaEventRecord(p->ev1, st));
+	p->timed = true;
+	return ACM_OK;
+fail:
+	return ACM_ERR_OTHER;
+}
+
+extern "C" int acm_gpu_plan_fetch(acm_gpu_plan *p, acm_gpu_stream *s, void *cuda_stream)
+{
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	std::vector<int32_t> status(p->n);
+	std::vector<uint32_t> words(p->n);
+	std::vector<unsigned long long> cks(p->n);
+	g_err[0] = 0;
+	CU(cudaSetDevice(p->device));
+	CU(cudaStreamSynchronize(st));
+	if (p->n) {
+		CU(cudaMemcpy(status.data(), p->d_status, p->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(words.data(), p->d_words, p->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+		CU(cudaMemcpy(cks.data(), p->d_cks, p->n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	}
+	for (uint64_t i = 0; i < p->n; i++) {
+		if (p->host_status[i] < 0) {
+			s[i].status = p->host_status[i];
+			s[i].words = 0;
+			s[i].checksum = 0;
+		} else {
+			s[i].status = status[i];
+			s[i].words = words[i];
+			s[i].checksum = cks[i];
+		}
+	}
+	return ACM_OK;
+fail:
+	return ACM_ERR_OTHER;
+}
+
+extern "C" int acm_gpu_plan_launches(const acm_gpu_plan *p)
+{
+	return (p->n_fast ? 1 : 0) + (p->n_generic ? 1 : 0);
+}
+
+extern "C" void acm_gpu_plan_split(const acm_gpu_plan *p, uint64_t *n_fast, uint64_t *n_generic)
+{
+	if (n_fast)
+		*n_fast = p->n_fast;
+	if (n_generic)
+		*n_generic = p->n_generic;
+}
+
+extern "C" float acm_gpu_plan_last_ms(acm_gpu_plan *p)
+{
+	float ms = -1.0f;
+	if (!p->timed)
+		return ms;
+	if (cudaEventSynchronize(p->ev1) != cudaSuccess)
+		return -1.0f;
+	if (cudaEventElapsedTime(&ms, p->ev0, p->ev1) != cudaSuccess)
+		return -1.0f;
+	return ms;
+}
+
+extern "C" void acm_gpu_plan_destroy(acm_gpu_plan *p) { plan_free(p); }
+
+/* ------------------------------------------------------------------ one-shot */
+
+extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *opts)
+{
+	acm_gpu_opts defaults;
+	acm_gpu_plan *plan = nullptr;
+	uint8_t *d_blob = nullptr, *d_out = nullptr;
+	const uint8_t *blob_dev;
+	uint8_t *out_dev;
+	cudaStream_t st = nullptr;
+	int err = ACM_ERR_OTHER, perr = 0;
+	bool need_probe = false;
+
+	g_err[0] = 0;
+	if (!b || (!b->streams && b->n)) {
+		acm_set_error("acm_gpu_decode_batch: null batch");
+		return ACM_ERR_OTHER;
+	}
+	if (!opts) {
+		acm_gpu_opts_init(&defaults);
+		opts = &defaults;
+	}
+	if (use_device(opts) < 0)
+		return ACM_ERR_OTHER;
+	for (uint64_t i = 0; i < b->n; i++)
+		if (b->streams[i].rows == 0 && b->streams[i].status == 0)
+			need_probe = true;
+	if (need_probe &&
+	    acm_gpu_probe(b->blob, b->blob_len, b->blob_on_device, b->streams, b->n, opts) < 0)
+		return ACM_ERR_OTHER;
+	for (uint64_t i = 0; i < b->n; i++) {
+		const acm_gpu_stream &g = b->streams[i];
+		uint64_t need = g.out_off + (uint64_t)g.total_values * (uint64_t)opts->wordlen;
+		if (g.status == 0 && (need > b->out_len || g.in_off + g.in_len > b->blob_len)) {
+			acm_set_error("stream %llu does not fit its blob/out range", (unsigned long long)i);
+			return ACM_ERR_OTHER;
+		}
+	}
+	plan = acm_gpu_plan_create(b->streams, b->n, opts, &perr);
+	if (!plan)
+		return perr ? perr : ACM_ERR_OTHER;
+
+	CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	if (b->blob_on_device) {
+		blob_dev = (const uint8_t *)b->blob;
+	} else {
+		CU(cudaMalloc(&d_blob, b->blob_len + 64));
+		CU(cudaMemcpyAsync(d_blob, b->blob, b->blob_len, cudaMemcpyHostToDevice, st));
+		blob_dev = d_blob;
+	}
+	if (b->out_on_device) {
+		out_dev = (uint8_t *)b->out;
+	} else {
+		CU(cudaMalloc(&d_out, b->out_len + 64));
+		out_dev = d_out;
+	}
+	if (acm_gpu_plan_run(plan, blob_dev, out_dev, st) < 0)
+		goto fail;
+	if (!b->out_on_device && b->out_len)
+		CU(cudaMemcpyAsync(b->out, d_out, b->out_len, cudaMemcpyDeviceToHost, st));
+	if (acm_gpu_plan_fetch(plan, b->streams, st) < 0)
+		goto fail;
+	CU(cudaGetLastError());
+	err = ACM_OK;
+fail:
+	if (st) {
+		cudaStreamSynchronize(st);
+		cudaStreamDestroy(st);
+	}
+	cudaFree(d_blob);
+	cudaFree(d_out);
+	acm_gpu_plan_destroy(plan);
+	return err;
+}

@@ -1,0 +1,47 @@
+/*
+ * acm_kernels.cuh -- launch interface between the host glue (acm_batch.cu) and the
+ * decode kernels (acm_kernels.cu, acm_fast.cu).
+ */
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "acm_device.cuh"
+
+namespace acm {
+
+struct KernelArgs {
+	const uint8_t *blob;
+	uint8_t *out;
+	const DevStream *streams; /* this kernel's slice of the descriptor table */
+	uint32_t count;
+	int32_t *status;          /* result arrays, indexed by DevStream::index */
+	uint32_t *words;
+	unsigned long long *cks;
+	const acm_tables *tables; /* device copy */
+	uint32_t *counter;        /* work-queue cursor (zeroed before launch) */
+	Format fmt;
+};
+
+struct GenericScratch {
+	uint32_t *buf;      /* n_ctas * stride words */
+	size_t stride;      /* words per CTA */
+	uint32_t max_blen;  /* largest rows*cols among the streams */
+	uint32_t max_cols;
+};
+
+/* words of scratch one CTA of the generic kernel needs */
+inline size_t generic_scratch_words(uint32_t max_blen, uint32_t max_cols)
+{
+	return 2 * (size_t)max_blen + 3 * (size_t)max_cols + 64;
+}
+
+cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_ctas,
+			   cudaStream_t st);
+
+/* gathers the first 48 bytes of every image (header parse on the host) */
+cudaError_t launch_gather_headers(const uint8_t *blob, uint64_t blob_len, const uint64_t *in_off,
+				  const uint32_t *in_len, uint8_t *dst, uint64_t n, cudaStream_t st);
+
+} // namespace acm

@@ -1,0 +1,124 @@
+/* acm_tables.c -- builds the lookup tables described in acm_tables.h. */
+#include <string.h>
+
+#include "acm_tables.h"
+
+static const int8_t sel_of_kt[8] = { 17, 18, 20, 21, 23, 24, 26, 27 };
+
+/*
+ * Decode ONE prefix-code symbol of selector `sel` from bits b[pos..8).
+ * Returns its length in bits, or 0 if it does not fit completely in the window.
+ * *count = values produced (2 for the "0 = two zeros" symbol), *value = the value.
+ * Symbol grammar: SURVEY.md Appendix A.4 / reference decode.c:208-403.
+ */
+static int k_symbol(int sel, unsigned b, int pos, int *count, int *value)
+{
+	static const int near2[4] = { -2, -1, 1, 2 }, far2[4] = { -3, -2, 2, 3 };
+	static const int m3[8] = { -4, -3, -2, -1, 1, 2, 3, 4 };
+	int pair = (sel == 17 || sel == 20 || sel == 23 || sel == 26);
+	int p = pos, len;
+#define BIT(i) ((b >> (i)) & 1u)
+#define FIELD(i, n) ((b >> (i)) & ((1u << (n)) - 1))
+	*count = 1;
+	*value = 0;
+	if (p + 1 > 8)
+		return 0;
+	if (BIT(p) == 0) { /* "0" */
+		*count = pair ? 2 : 1;
+		return 1;
+	}
+	p++;
+	if (pair) { /* "1 0" = one zero */
+		if (p + 1 > 8)
+			return 0;
+		if (BIT(p) == 0)
+			return 2;
+		p++;
+	}
+	switch (sel) {
+	case 17: case 18: len = 1; break;
+	case 20: case 21: len = 2; break;
+	case 26: case 27: len = 3; break;
+	default: /* 23: 1 1 [0 x | 1 xx]   24: 1 [0 x | 1 xx] */
+		if (p + 1 > 8)
+			return 0;
+		len = BIT(p) ? 2 : 1;
+		p++;
+		if (p + len > 8)
+			return 0;
+		*value = len == 1 ? (FIELD(p, 1) ? 1 : -1) : far2[FIELD(p, 2)];
+		return p + len - pos;
+	}
+	if (p + len > 8)
+		return 0;
+	if (len == 1)
+		*value = FIELD(p, 1) ? 1 : -1;
+	else if (len == 2)
+		*value = near2[FIELD(p, 2)];
+	else
+		*value = m3[FIELD(p, 3)];
+	return p + len - pos;
+#undef BIT
+#undef FIELD
+}
+
+void acm_tables_build(acm_tables *t)
+{
+	int kt, sel;
+	unsigned b;
+
+	memset(t, 0, sizeof(*t));
+	for (kt = 0; kt < 8; kt++) {
+		for (b = 0; b < 256; b++) {
+			uint64_t e = 0;
+			int pos = 0, nv = 0;
+			for (;;) {
+				int count, value, len, k;
+				len = k_symbol(sel_of_kt[kt], b, pos, &count, &value);
+				if (!len || nv + count > 7)
+					break;
+				pos += len;
+				for (k = 0; k < count; k++, nv++) {
+					e |= (uint64_t)pos << (4 + 4 * nv);
+					e |= (uint64_t)(value & 15) << (32 + 4 * nv);
+				}
+			}
+			/* every symbol is <= 5 bits, so nv >= 1 always */
+			t->k8[kt * 256 + b] = e | (uint64_t)nv;
+		}
+	}
+	for (b = 0; b < 128; b++) {
+		unsigned v;
+		/* t15 (selector 19): b < 27, digits base 3 minus 1 */
+		v = b < 27 ? (((b % 3 - 1) & 15) | (((b / 3) % 3 - 1) & 15) << 4 | ((b / 9 - 1) & 15) << 8)
+			   : 0x8000u;
+		if (b < 32)
+			t->t[0 * 128 + b] = (uint16_t)v;
+		/* t27 (selector 22): b < 125, digits base 5 minus 2 */
+		v = b < 125 ? (((b % 5 - 2) & 15) | (((b / 5) % 5 - 2) & 15) << 4 | ((b / 25 - 2) & 15) << 8)
+			    : 0x8000u;
+		t->t[1 * 128 + b] = (uint16_t)v;
+		/* t37 (selector 29): b < 121, digits base 11 minus 5 */
+		v = b < 121 ? (((b % 11 - 5) & 15) | ((b / 11 - 5) & 15) << 4) : 0x8000u;
+		t->t[2 * 128 + b] = (uint16_t)v;
+	}
+	/* selector classes: the reference's filler_list (decode.c:480-489) */
+	for (sel = 0; sel < 32; sel++) {
+		uint8_t k = ACM_CLS_BAD;
+		if (sel == 0)
+			k = ACM_CLS_ZERO;
+		else if (sel >= 3 && sel <= 16)
+			k = ACM_CLS_LINEAR;
+		else if (sel == 19)
+			k = ACM_CLS_T | (0 << 3);
+		else if (sel == 22)
+			k = ACM_CLS_T | (1 << 3);
+		else if (sel == 29)
+			k = ACM_CLS_T | (2 << 3);
+		else
+			for (kt = 0; kt < 8; kt++)
+				if (sel_of_kt[kt] == sel)
+					k = (uint8_t)(ACM_CLS_K | (kt << 3));
+		t->kind[sel] = k;
+	}
+}

@@ -1,0 +1,51 @@
+"""CPU tier: the product's __host__ __device__ decode logic (code tables, block scan,
+column decode, transform, output, descriptor construction), driven by a CPU mirror of
+the generic kernel's control flow, against the checker."""
+import numpy as np
+
+from libacm_b200 import api, gen
+from tests import corpus, emu_bindings as emu
+
+
+def _check(img, checker, **kw):
+    a = checker.decode(img, force_chans=kw.get("force_chans", 0), be=kw.get("be", 0), sgned=kw.get("sgned", 1))
+    err, st, words, pcm, cks = emu.decode(img, **kw)
+    assert err == a.open_err
+    if err == 0:
+        assert (st, words) == (a.status, a.words)
+        assert np.array_equal(pcm, a.pcm)
+        assert cks == api.checksum_ref(a.pcm, a.words, 2, kw.get("be", 0))
+    return a
+
+
+def test_emu_stress_corpus(checker):
+    for k, img in enumerate(corpus.images(corpus.stress_params(max_values=40_000))):
+        _check(img, checker, be=k & 1, sgned=(k >> 1) & 1, lead=k % 7, nthreads=(1, 32, 64, 256)[k % 4])
+
+
+def test_emu_single_fillers_and_negatives(checker):
+    seen = set()
+    for img in corpus.images(corpus.single_filler_params() + corpus.negative_params()):
+        seen.add(_check(img, checker).status)
+    assert seen == {0, -6}
+
+
+def test_emu_truncations(checker):
+    img = gen.make_stream(level=5, rows=7, channels=2, total_values=5000, dist=gen.DIST_STRESS, seed=5)
+    seen = set()
+    for cut in range(len(img)):
+        a = _check(img[:cut], checker, lead=cut % 5)
+        if a.open_err == 0:
+            seen.add(a.status)
+    assert seen == {0, -6, -7}
+
+
+def test_emu_force_chans(checker):
+    for fc in (-1, 0, 1, 2, 3):
+        for wavc in (0, 1):
+            for ch in (1, 2):
+                for level, rows in ((0, 5), (3, 3), (7, 16)):
+                    img = gen.make_stream(level=level, rows=rows, channels=ch, wavc=wavc,
+                                          total_values=(rows << level) * 3 + 1, dist=gen.DIST_STRESS,
+                                          seed=fc + 10 * wavc + 100 * ch + level)
+                    _check(img, checker, force_chans=fc)

@@ -1,0 +1,123 @@
+"""GPU tier: acm_gpu_decode_batch / acm_gpu_plan_* through the C ABI against the checker
+(the reference itself when oracle/_ref is present).  Bit-exact, zero tolerance."""
+import numpy as np
+import pytest
+
+from libacm_b200 import api, gen
+from tests import corpus, gpu_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_stress_corpus_host_buffers(checker, kernel):
+    imgs = corpus.images(corpus.stress_params(max_values=60_000))
+    s, out = gu.decode_host(imgs, want_checksums=1, kernel=kernel)
+    assert gu.compare(imgs, s, out, checker, checksums=True) == []
+
+
+@pytest.mark.parametrize("be,sgned", [(0, 1), (1, 1), (0, 0), (1, 0)])
+def test_formats_device_resident(checker, be, sgned):
+    imgs = corpus.images(corpus.stress_params(max_values=20_000)[::3] + corpus.fallout_params(24, seed=3, hi=40_000))
+    s, out = gu.decode_device(imgs, bigendianp=be, sgned=sgned, want_checksums=1)
+    assert gu.compare(imgs, s, out, checker, be=be, sgned=sgned, checksums=True) == []
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_unaligned_back_to_back_images(checker, kernel):
+    imgs = corpus.images(corpus.stress_params(max_values=8_000)[::2] + corpus.fallout_params(40, seed=9, hi=30_000))
+    for lead in (0, 1, 2, 3):
+        s, out = gu.decode_host(imgs, align=1, lead=lead, kernel=kernel)
+        assert gu.compare(imgs, s, out, checker) == []
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_single_fillers_and_negatives(checker, kernel):
+    imgs = corpus.images(corpus.single_filler_params() + corpus.single_filler_params(level=7, rows=16) +
+                         corpus.negative_params())
+    s, out = gu.decode_host(imgs, kernel=kernel)
+    assert gu.compare(imgs, s, out, checker) == []
+    assert set(s["status"].tolist()) == {0, -6}
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("shape", [(5, 7, 2), (7, 16, 1)])
+def test_truncations(checker, kernel, shape):
+    level, rows, ch = shape
+    img = gen.make_stream(level=level, rows=rows, channels=ch, total_values=(rows << level) * 3 + 9,
+                          dist=gen.DIST_STRESS, seed=5)
+    cuts = list(range(0, 60)) + list(range(60, len(img), 7)) + [len(img) - 1, len(img)]
+    imgs = [img[:c] for c in cuts]
+    s, out = gu.decode_host(imgs, align=1, kernel=kernel)
+    assert gu.compare(imgs, s, out, checker) == []
+    assert {0, -3, -7} <= set(s["status"].tolist())
+
+
+@pytest.mark.parametrize("fc", [-1, 0, 1, 2, 3])
+def test_force_chans(checker, fc):
+    imgs = []
+    for wavc in (0, 1):
+        for ch in (1, 2):
+            for level, rows in ((0, 5), (3, 3), (7, 16)):
+                imgs.append(gen.make_stream(level=level, rows=rows, channels=ch, wavc=wavc,
+                                            total_values=(rows << level) * 3 + 1, dist=gen.DIST_STRESS,
+                                            seed=fc + 10 * wavc + 100 * ch + level))
+    s, out = gu.decode_host(imgs, force_chans=fc)
+    assert gu.compare(imgs, s, out, checker, force_chans=fc) == []
+
+
+@pytest.mark.parametrize("wordlen", [3, 4])
+def test_wordlen_3_4_unpinned_invariant(checker, wordlen):
+    """No reference answer exists for wordlen 3/4 (decode.c:832-835): low 16 bits must
+    equal the s16 output, and the oracle port's definition must match."""
+    from oracle import bindings
+    port = bindings.Oracle()
+    imgs = corpus.images(corpus.stress_params(max_values=8_000)[::5] + corpus.fallout_params(8, seed=2, hi=30_000))
+    for be in (0, 1):
+        for sg in (0, 1):
+            s, out = gu.decode_host(imgs, wordlen=wordlen, bigendianp=be, sgned=sg)
+            for i, img in enumerate(imgs):
+                want = port.decode(img, be=be, wordlen=wordlen, sgned=sg)
+                o = int(s["out_off"][i])
+                assert np.array_equal(out[o:o + want.pcm.size], want.pcm)
+                s16 = checker.decode(img).pcm.view("<u2")
+                b = want.pcm.reshape(-1, wordlen)
+                lo = (b[:, -1].astype(np.uint16) | (b[:, -2].astype(np.uint16) << 8)) if be else \
+                     (b[:, 0].astype(np.uint16) | (b[:, 1].astype(np.uint16) << 8))
+                assert np.array_equal(lo, s16)
+
+
+def test_golden_fixtures_on_gpu():
+    import hashlib
+    import json
+    import os
+    g = os.path.join(os.path.dirname(__file__), "golden")
+    meta = json.load(open(os.path.join(g, "golden.json")))
+    names = sorted(meta)
+    for fc in sorted({m["force_chans"] for m in meta.values()}):
+        sel = [n for n in names if meta[n]["force_chans"] == fc]
+        imgs = [open(os.path.join(g, n), "rb").read() for n in sel]
+        for be in (0, 1):
+            for sg in (0, 1):
+                s, out = gu.decode_host(imgs, bigendianp=be, sgned=sg, force_chans=fc)
+                for i, n in enumerate(sel):
+                    m = meta[n]
+                    if m["open_err"] < 0:
+                        assert s["status"][i] == m["open_err"]
+                        continue
+                    assert (int(s["status"][i]), int(s["words"][i])) == (m["status"], m["words"]), n
+                    o = int(s["out_off"][i])
+                    pcm = out[o:o + m["info"]["total_values"] * 2]
+                    assert hashlib.sha256(pcm.tobytes()).hexdigest() == m["sha256"][f"b{be}s{sg}"], n
+
+
+def test_fallout_batch_checksums_and_roundtrip_properties(checker):
+    """Larger batch (config 2 shape, scaled): per-stream checksums equal the checker's and
+    the checksum of checksums is invariant under a permutation of the batch order."""
+    imgs = corpus.images(corpus.fallout_params(300, seed=7))
+    s, out = gu.decode_device(imgs, want_checksums=1)
+    assert gu.compare(imgs[::15], s[::15], out, checker, checksums=True) == []
+    perm = np.random.default_rng(0).permutation(len(imgs))
+    s2, _ = gu.decode_device([imgs[i] for i in perm], want_checksums=1)
+    assert np.array_equal(s2["checksum"], s["checksum"][perm])
+    assert np.all(s["status"] == 0) and np.array_equal(s["words"], s["total_values"])
