@@ -102,6 +102,17 @@ def build_all(force=False, verbose=False):
     build_oracle()
 
 
+def ensure_built():
+    """Build only what is missing (no mtime checks: safe when several ranks start at once
+    on a box that received prebuilt .so files)."""
+    if not os.path.exists(os.path.join(LIBDIR, "libacmgen.so")):
+        build_generator()
+    if not os.path.exists(os.path.join(LIBDIR, "libacm_b200.so")):
+        build_cuda()
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libacm_oracle.so")):
+        build_oracle()
+
+
 if __name__ == "__main__":
     build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print("ok")

@@ -194,9 +194,11 @@ static void plan_free(acm_gpu_plan *p)
 	delete p;
 }
 
-static bool fast_eligible(const acm_gpu_stream &, const acm_gpu_opts *)
+static bool fast_eligible(const acm_gpu_stream &g, const acm_gpu_opts *o)
 {
-	return false; /* acm_fast.cu registers its shapes here (see acm_fast_eligible) */
+	/* the register/shared-memory kernel covers the common block shape and the
+	 * reference's own 16-bit formats; everything else takes the generic kernel */
+	return o->wordlen == 2 && fast_shape(g.level, g.rows);
 }
 
 extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n,
@@ -339,6 +341,16 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 	a.cks = p->d_cks;
 	a.tables = p->d_tables;
 	a.fmt = p->fmt;
+	if (p->n_fast) {
+		int ctas = p->sm_count;
+		uint64_t groups = (p->n_fast + 29) / 30;
+		if ((uint64_t)ctas > groups)
+			ctas = (int)groups;
+		a.streams = p->d_streams;
+		a.count = (uint32_t)p->n_fast;
+		a.counter = p->d_counters;
+		CU(launch_fast(a, ctas, st));
+	}
 	if (p->n_generic) {
 		a.streams = p->d_streams + p->n_fast;
 		a.count = (uint32_t)p->n_generic;

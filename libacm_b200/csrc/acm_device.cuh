@@ -208,7 +208,7 @@ struct ScanResult {
 template <typename OFF>
 ACM_HD ScanResult scan_block(BitReader &br, uint32_t P, uint32_t limit, uint32_t cols,
 			     uint32_t rows, OFF *coloff, uint32_t off_base, const uint8_t *kind,
-			     const uint64_t *k8)
+			     const uint64_t *k8, uint32_t pitch = 1)
 {
 	ScanResult s;
 	s.status = SCAN_OK;
@@ -228,7 +228,7 @@ ACM_HD ScanResult scan_block(BitReader &br, uint32_t P, uint32_t limit, uint32_t
 			break;
 		}
 		uint32_t ind = br.peek(P) & 31u, k = kind[ind];
-		coloff[c] = (OFF)(P - off_base);
+		coloff[c * pitch] = (OFF)(P - off_base);
 		if ((k & 7u) == ACM_CLS_BAD) {
 			s.status = -6;
 			break;

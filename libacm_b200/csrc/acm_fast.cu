@@ -40,8 +40,8 @@ constexpr int LEVEL = 7;
 constexpr int COLS = 128;
 constexpr int ROWS = 16;
 constexpr int BLEN = COLS * ROWS;      /* 2048 */
-constexpr int S = 32;                  /* stream slots per CTA = lanes of the scan warp */
-constexpr int W = 16;                  /* worker warps */
+constexpr int W = 15;                  /* worker warps (+1 scan warp = 512 threads, 128 regs) */
+constexpr int S = 2 * W;               /* stream slots per CTA = active lanes of the scan warp */
 constexpr int THREADS = 32 * (W + 1);
 constexpr int SLOTS_PER_WORKER = S / W;
 constexpr int OFF_PITCH = 33;          /* u16 per column row of the offset table (bank spread) */
@@ -151,14 +151,17 @@ juggle_and_store(Smem &sm, uint32_t *xs, int slot, int lane, uint8_t *out, uint3
 	uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)pos0 + 64u * lane) * 2u);
 	uint32_t pk[4];
 #pragma unroll
-	for (int t = 0; t < 128; t++) {
-		if ((t & 3) == 0) {
-			uint4 q = t < 64 ? prev[t >> 2] : own[(t - 64) >> 2];
-			u[t] = q.x; u[t + 1] = q.y; u[t + 2] = q.z; u[t + 3] = q.w;
-		}
+	for (int t = 0; t < 36; t += 4) {
+		uint4 q = prev[t >> 2];
+		u[t] = q.x; u[t + 1] = q.y; u[t + 2] = q.z; u[t + 3] = q.w;
 	}
 #pragma unroll
 	for (int t = 34; t < 128; t++) {
+		if ((t & 3) == 0 && t >= 36) {
+			/* just-in-time halo / chunk load keeps ~70 words live instead of 128 */
+			uint4 q = t < 64 ? prev[t >> 2] : own[(t - 64) >> 2];
+			u[t] = q.x; u[t + 1] = q.y; u[t + 2] = q.z; u[t + 3] = q.w;
+		}
 		a3[t] = lift(u[t], u[t - 16], u[t - 32], (t >> 4) & 1);          /* C = 16 */
 		if (t >= 50)
 			a4[t] = lift(a3[t], a3[t - 8], a3[t - 16], (t >> 3) & 1); /* C = 8 */
@@ -205,110 +208,6 @@ juggle_and_store(Smem &sm, uint32_t *xs, int slot, int lane, uint8_t *out, uint3
 	return cks;
 }
 
-/* generic-format output path (wordlen 3/4): same transform, plain stores */
-__device__ __noinline__ unsigned long long
-juggle_and_store_wide(Smem &sm, uint32_t *xs, int slot, int lane, uint8_t *out, uint32_t pos0,
-		      uint32_t n, const Format fmt)
-{
-	/* run the 16-bit routine's arithmetic through shared memory in flat form: the wide
-	 * formats are an extension with no reference counterpart, so this path favours
-	 * simplicity (three sweeps per stage over the warp's 2048-word buffer) */
-	uint32_t *h0 = sm.hist0[slot], *h1 = sm.hist1[slot], *h2 = sm.hist2[slot];
-	unsigned long long cks = 0ull;
-	/* bring history into the flat layout the sweeps expect */
-	uint32_t hx[4], hy[2];
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		hx[k] = h0[32 * k + lane]; /* X0[-128 + 32k + lane] */
-	hy[0] = h1[lane];              /* X1[-64 + lane]  */
-	hy[1] = h1[32 + lane];         /* X1[-32 + lane]  */
-	uint32_t v[64];
-	/* stage 1 (C=64) */
-#pragma unroll
-	for (int i = 0; i < 64; i++)
-		v[i] = xs[32 * i + lane];
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		h0[32 * k + lane] = v[60 + k];
-	uint32_t y[64];
-#pragma unroll
-	for (int i = 0; i < 64; i++) {
-		uint32_t p1 = i >= 2 ? v[i - 2] : hx[i + 2];
-		uint32_t p2 = i >= 4 ? v[i - 4] : hx[i];
-		y[i] = lift(v[i], p1, p2, (i >> 1) & 1) + (((i & 1) == 0 && lane == 0) ? 1u : 0u);
-	}
-	h1[lane] = y[62];
-	h1[32 + lane] = y[63];
-	__syncwarp();
-#pragma unroll
-	for (int i = 0; i < 64; i++) {
-		uint32_t p1 = i >= 1 ? y[i - 1] : hy[1];
-		uint32_t p2 = i >= 2 ? y[i - 2] : hy[i];
-		xs[32 * i + lane] = lift(y[i], p1, p2, i & 1); /* X2, flat */
-	}
-	__syncwarp();
-	/* stages 3..7 flat, in place through registers: out[m] needs in[m], in[m-C], in[m-2C] */
-	uint32_t tail[2]; /* X2[2048-64 + 32k + lane] for the next block's history */
-	tail[0] = xs[BLEN - 64 + lane];
-	tail[1] = xs[BLEN - 32 + lane];
-	uint32_t hprev[2] = { h2[lane], h2[32 + lane] }; /* X_{l-1}[-64 + ...] for the current stage */
-	for (int C = 16; C >= 1; C >>= 1) {
-#pragma unroll
-		for (int i = 0; i < 64; i++) {
-			int m = 32 * i + lane;
-			uint32_t p1, p2;
-			/* history words live in lanes: X[-64 + 32k + lane'] = hprev[k] of lane' */
-			int m1 = m - C, m2 = m - 2 * C;
-			uint32_t g1 = __shfl_sync(0xFFFFFFFFu, hprev[1], (m1 + 64) & 31);
-			uint32_t g2 = __shfl_sync(0xFFFFFFFFu, hprev[1], (m2 + 64) & 31);
-			p1 = m1 >= 0 ? xs[m1] : g1; /* 2C <= 32, so only the last 32 history words matter */
-			p2 = m2 >= 0 ? xs[m2] : g2;
-			v[i] = lift(xs[m], p1, p2, (m / C) & 1);
-		}
-		/* history for the NEXT stage = this stage's outputs of the previous block's tail:
-		 * they are the stage outputs at m = -64..-1, which we recompute from hprev */
-		uint32_t nh[2];
-#pragma unroll
-		for (int k = 0; k < 2; k++) {
-			int m = -64 + 32 * k + lane;
-			int m1 = m - C, m2 = m - 2 * C;
-			/* sources are hprev words at -64..-1; words before -64 are not available, but
-			 * they are only needed for m < -64 + 2C, which later stages never read
-			 * (dependency cone: 62 words) */
-			uint32_t s0 = hprev[k];
-			uint32_t a1 = __shfl_sync(0xFFFFFFFFu, hprev[0], (m1 + 64) & 31);
-			uint32_t b1 = __shfl_sync(0xFFFFFFFFu, hprev[1], (m1 + 64) & 31);
-			uint32_t a2 = __shfl_sync(0xFFFFFFFFu, hprev[0], (m2 + 64) & 31);
-			uint32_t b2 = __shfl_sync(0xFFFFFFFFu, hprev[1], (m2 + 64) & 31);
-			uint32_t p1 = (m1 + 64) >= 32 ? b1 : a1;
-			uint32_t p2 = (m2 + 64) >= 32 ? b2 : a2;
-			if (m1 + 64 < 0) p1 = 0;
-			if (m2 + 64 < 0) p2 = 0;
-			nh[k] = lift(s0, p1, p2, ((m + 64 * 1024) / C) & 1);
-		}
-		__syncwarp();
-#pragma unroll
-		for (int i = 0; i < 64; i++)
-			xs[32 * i + lane] = v[i];
-		hprev[0] = nh[0];
-		hprev[1] = nh[1];
-		__syncwarp();
-	}
-	h2[lane] = tail[0];
-	h2[32 + lane] = tail[1];
-#pragma unroll 4
-	for (int i = 0; i < 64; i++) {
-		uint32_t m = 32u * i + lane;
-		if (m < n) {
-			uint32_t uu = emit_word(out + ((size_t)pos0 + m) * fmt.wordlen, (int32_t)v[i] >> LEVEL, fmt);
-			if (fmt.checksums)
-				cks += (unsigned long long)(pos0 + m + 1u) * (unsigned long long)(uu + 1ull);
-		}
-	}
-	__syncwarp();
-	return cks;
-}
-
 template <bool CKS>
 __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs a)
 {
@@ -344,9 +243,10 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 			Entry e;
 			e.status = ENT_IDLE;
 			e.pblock = 0; e.desc = 0; e.blk = 0; e.ncols = 0; e.val = 0;
-			if (active && sm.dead[lane] == cur + 1u)
+			const bool has_slot = lane < S;
+			if (active && sm.dead[lane < S ? lane : 0] == cur + 1u)
 				active = false; /* a worker found a corrupt t-code: abandon the stream */
-			if (!active) {
+			if (!active && has_slot) {
 				uint32_t idx = atomicAdd(a.counter, 1u);
 				if (idx < a.count) {
 					const DevStream d = a.streams[idx];
@@ -383,7 +283,8 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					}
 				}
 			}
-			sm.ent[buf][lane] = e;
+			if (has_slot)
+				sm.ent[buf][lane] = e;
 			const int any = __any_sync(0xFFFFFFFFu, e.status != ENT_IDLE);
 			if (lane == 0)
 				sm.more[buf] = any;
@@ -446,13 +347,9 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					if (n > (uint32_t)BLEN)
 						n = BLEN;
 					uint8_t *out = a.out + d.out_off;
-					unsigned long long c2;
-					if (a.fmt.wordlen == 2)
-						c2 = juggle_and_store<CKS>(sm, xs, slot, lane, out, pos, n, a.fmt);
-					else
-						c2 = juggle_and_store_wide(sm, xs, slot, lane, out, pos, n, a.fmt);
+					unsigned long long c2 = juggle_and_store<CKS>(sm, xs, slot, lane, out, pos, n, a.fmt);
 					pos += n;
-					if (CKS || a.fmt.wordlen != 2) {
+					if (CKS) {
 						for (int o = 16; o; o >>= 1)
 							c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
 						if (lane == 0)

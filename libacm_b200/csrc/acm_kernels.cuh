@@ -40,6 +40,11 @@ inline size_t generic_scratch_words(uint32_t max_blen, uint32_t max_cols)
 cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_ctas,
 			   cudaStream_t st);
 
+/* level-7 / 16-row kernel (acm_fast.cu); 16-bit output formats only */
+bool fast_shape(uint32_t level, uint32_t rows);
+size_t fast_smem_bytes();
+cudaError_t launch_fast(const KernelArgs &a, int n_ctas, cudaStream_t st);
+
 /* gathers the first 48 bytes of every image (header parse on the host) */
 cudaError_t launch_gather_headers(const uint8_t *blob, uint64_t blob_len, const uint64_t *in_off,
 				  const uint32_t *in_len, uint8_t *dst, uint64_t n, cudaStream_t st);
