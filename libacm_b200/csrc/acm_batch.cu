@@ -161,6 +161,7 @@ struct acm_gpu_plan {
 	uint64_t n;          /* caller's stream count */
 	uint64_t n_dev;      /* streams that reach the device */
 	uint64_t n_fast, n_generic;
+	uint64_t blob_room;  /* bytes the kernels may read: end of the last image, rounded up to 16 */
 	Format fmt;
 	std::vector<int32_t> host_status; /* statuses decided on the host (NOT_ACM, OTHER) */
 	DevStream *d_streams;
@@ -240,6 +241,7 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 	p->fmt.bias = opts->sgned ? 0u : (1u << (8 * opts->wordlen - 1));
 	p->fmt.checksums = opts->want_checksums ? 1 : 0;
 	p->host_status.assign(n, 0);
+	p->blob_room = 0;
 
 	for (uint64_t i = 0; i < n; i++) {
 		const acm_gpu_stream &g = s[i];
@@ -254,6 +256,7 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 			continue;
 		}
 		uint32_t blen = g.rows << g.level;
+		p->blob_room = std::max(p->blob_room, (g.in_off + g.in_len + 15u) & ~(uint64_t)15u);
 		if (opts->kernel != 1 && fast_eligible(g, opts)) {
 			fast.push_back(d);
 		} else {
@@ -334,7 +337,13 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 	CU(cudaSetDevice(p->device));
 	CU(cudaMemsetAsync(p->d_counters, 0, 64, st));
 	CU(cudaEventRecord(p->ev0, st));
+	if (((uintptr_t)d_blob & 15u) || ((uintptr_t)d_out & 15u)) {
+		acm_set_error("acm_gpu_plan_run: blob and out must be 16-byte aligned");
+		return ACM_ERR_OTHER;
+	}
 	a.blob = (const uint8_t *)d_blob;
+	a.blob_room = p->blob_room;
+	a.errflag = p->d_counters + 2;
 	a.out = (uint8_t *)d_out;
 	a.status = p->d_status;
 	a.words = p->d_words;
@@ -370,9 +379,15 @@ extern "C" int acm_gpu_plan_fetch(acm_gpu_plan *p, acm_gpu_stream *s, void *cuda
 	std::vector<int32_t> status(p->n);
 	std::vector<uint32_t> words(p->n);
 	std::vector<unsigned long long> cks(p->n);
+	uint32_t flag = 0;
 	g_err[0] = 0;
 	CU(cudaSetDevice(p->device));
 	CU(cudaStreamSynchronize(st));
+	CU(cudaMemcpy(&flag, p->d_counters + 2, sizeof(flag), cudaMemcpyDeviceToHost));
+	if (flag) {
+		acm_set_error("decode kernel reported internal failure %u (bulk-copy timeout)", flag);
+		return ACM_ERR_OTHER;
+	}
 	if (p->n) {
 		CU(cudaMemcpy(status.data(), p->d_status, p->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
 		CU(cudaMemcpy(words.data(), p->d_words, p->n * sizeof(uint32_t), cudaMemcpyDeviceToHost));

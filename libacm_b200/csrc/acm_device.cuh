@@ -4,9 +4,10 @@
  * same code on the CPU (tests/emu) where no GPU is available; the product only
  * ever calls it from the kernels in acm_kernels.cu.
  *
- * Coordinates: every stream is addressed through a 4-byte aligned base word
- * pointer; bit positions ("P") count from bit 0 of that base word, so the first
- * data bit (right after the 14/42-byte header) sits at P = bit0 in {0,8,16,24}.
+ * Coordinates: every stream is addressed through a 16-byte aligned base pointer
+ * (so that 128-bit loads and TMA bulk copies can fetch it); bit positions ("P")
+ * count from bit 0 of that base, so the first data bit (right after the 14/42-byte
+ * header) sits at P = bit0 in {0,8,...,120}.
  * file_end is the P one past the last bit of the file image; the reference's
  * single zero byte at EOF (decode.c:57-61) makes limit = file_end + 8 the first
  * position that cannot be read.  A GET_BITS of n bits at P succeeds iff
@@ -28,7 +29,7 @@ namespace acm {
 
 /* per-stream device descriptor, built on the host by acm_batch.cu */
 struct DevStream {
-	uint64_t base_off;    /* byte offset (multiple of 4) of the base word inside the blob */
+	uint64_t base_off;    /* byte offset (multiple of 16) of the stream base inside the blob */
 	uint64_t out_off;     /* byte offset of the PCM inside out */
 	uint32_t bit0;        /* P of the first data bit */
 	uint32_t file_end;    /* P one past the last file bit */
@@ -111,7 +112,8 @@ ACM_HD int nib_s(uint32_t x, int j) { return ((int32_t)(x << (28 - 4 * j))) >> 2
  * Length scan of one column payload: returns the P just past it.  Mirrors the bit
  * consumption of the reference fillers (decode.c:181-476) without producing values.
  */
-ACM_HD uint32_t scan_column(BitReader &br, uint32_t P, uint32_t ind, uint32_t kind, uint32_t rows,
+template <typename BR>
+ACM_HD uint32_t scan_column(BR &br, uint32_t P, uint32_t ind, uint32_t kind, uint32_t rows,
 			    const uint64_t *k8)
 {
 	uint32_t cls = kind & 7u, sub = kind >> 3;
@@ -142,8 +144,8 @@ ACM_HD uint32_t scan_column(BitReader &br, uint32_t P, uint32_t ind, uint32_t ki
  * the limit, exactly the codes the reference gets to read.  Returns 0, or
  * ACM_ERR_CORRUPT (-6) if such a code is out of range.
  */
-template <typename T>
-ACM_HD int decode_column(BitReader &br, uint32_t P, uint32_t limit, uint32_t ind, uint32_t kind,
+template <typename T, typename BR>
+ACM_HD int decode_column(BR &br, uint32_t P, uint32_t limit, uint32_t ind, uint32_t kind,
 			 uint32_t rows, int val, T *dst, uint32_t stride, const uint64_t *k8,
 			 const uint16_t *tt)
 {
@@ -205,8 +207,8 @@ struct ScanResult {
  *     that still fits is out of range       -> ACM_ERR_CORRUPT (checked by the caller's
  *     decode of column ncols, which this function leaves to decode_column)
  */
-template <typename OFF>
-ACM_HD ScanResult scan_block(BitReader &br, uint32_t P, uint32_t limit, uint32_t cols,
+template <typename OFF, typename BR>
+ACM_HD ScanResult scan_block(BR &br, uint32_t P, uint32_t limit, uint32_t cols,
 			     uint32_t rows, OFF *coloff, uint32_t off_base, const uint8_t *kind,
 			     const uint64_t *k8, uint32_t pitch = 1)
 {

@@ -133,11 +133,11 @@ int acm_make_devstream(const acm_gpu_stream *g, uint32_t index, int pad_tail, ac
 	if (g->level > 15 || g->rows > 4095)
 		return ACM_ERR_NOT_ACM; /* not representable in the 4+12-bit header field */
 	/* bit positions are 32-bit on the device: images of 512 MiB and more are refused */
-	if (data_len * 8 + 64 + (1u << 20) >= 0xFFFFFFFFull)
+	if (data_len * 8 + 256 + (1u << 20) >= 0xFFFFFFFFull)
 		return ACM_ERR_OTHER;
 	memset(d, 0, sizeof(*d));
-	d->base_off = data_off & ~(uint64_t)3;
-	d->bit0 = (uint32_t)(data_off & 3u) * 8u;
+	d->base_off = data_off & ~(uint64_t)15;
+	d->bit0 = (uint32_t)(data_off & 15u) * 8u;
 	d->file_end = d->bit0 + (uint32_t)data_len * 8u;
 	d->out_off = g->out_off;
 	d->rows = g->rows;

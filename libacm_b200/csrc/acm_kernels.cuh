@@ -12,7 +12,8 @@
 namespace acm {
 
 struct KernelArgs {
-	const uint8_t *blob;
+	const uint8_t *blob;      /* 16-byte aligned */
+	uint64_t blob_room;       /* readable bytes at blob: blob_len rounded up to 16 */
 	uint8_t *out;
 	const DevStream *streams; /* this kernel's slice of the descriptor table */
 	uint32_t count;
@@ -21,6 +22,7 @@ struct KernelArgs {
 	unsigned long long *cks;
 	const acm_tables *tables; /* device copy */
 	uint32_t *counter;        /* work-queue cursor (zeroed before launch) */
+	uint32_t *errflag;        /* set non-zero on an internal failure (e.g. copy timeout) */
 	Format fmt;
 };
 

@@ -1,0 +1,38 @@
+"""Small driver for ncu captures: decodes N config-2-shaped streams a few times.
+
+    ncu --set full --clock-control none --import-source on -k regex:acm_decode_fast -s 1 -c 1 \
+        -o gpurun_out/prof python tools/profile_run.py --streams 2000 --runs 2
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+from libacm_b200 import api  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--streams", type=int, default=2000)
+ap.add_argument("--runs", type=int, default=2)
+ap.add_argument("--kernel", type=int, default=0)
+args = ap.parse_args()
+
+blob, offs, lens = bench.build_corpus(args.streams, 0)
+opts = api.make_opts(device=0, kernel=args.kernel)
+s = api.new_streams(offs, lens)
+d_blob = torch.from_numpy(blob).cuda()
+api.probe(blob, s, opts)
+nbytes = api.layout(s, 2)
+d_out = torch.empty(nbytes + 64, dtype=torch.uint8, device="cuda")
+plan = api.Plan(s, opts)
+cs = torch.cuda.current_stream().cuda_stream
+for _ in range(args.runs):
+    plan.run(d_blob, d_out, cs)
+    torch.cuda.synchronize()
+    print("ms", plan.last_ms(), "Msamples/s", s["total_values"].sum() / plan.last_ms() / 1e3)
+plan.fetch(s, cs)
+assert np.all(s["status"] == 0)
