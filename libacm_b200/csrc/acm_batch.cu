@@ -171,6 +171,8 @@ struct acm_gpu_plan {
 	acm_tables *d_tables;
 	uint32_t *d_counters; /* [0] fast queue, [1] generic queue */
 	GenericScratch scratch;
+	uint32_t *d_hist;    /* fast kernel history, fast_ctas * fast_hist_words_per_cta() words */
+	int fast_ctas;
 	int generic_ctas;
 	int sm_count;
 	cudaEvent_t ev0, ev1;
@@ -188,6 +190,7 @@ static void plan_free(acm_gpu_plan *p)
 	cudaFree(p->d_tables);
 	cudaFree(p->d_counters);
 	cudaFree(p->scratch.buf);
+	cudaFree(p->d_hist);
 	if (p->ev0)
 		cudaEventDestroy(p->ev0);
 	if (p->ev1)
@@ -232,6 +235,7 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 	memset(&p->scratch, 0, sizeof(p->scratch));
 	p->d_streams = nullptr; p->d_status = nullptr; p->d_words = nullptr; p->d_cks = nullptr;
 	p->d_tables = nullptr; p->d_counters = nullptr; p->ev0 = nullptr; p->ev1 = nullptr;
+	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
 	p->device = dev;
 	p->n = n;
 	p->sm_count = prop.multiProcessorCount;
@@ -305,6 +309,12 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 	CU(cudaEventCreate(&p->ev0));
 	CU(cudaEventCreate(&p->ev1));
 
+	if (p->n_fast) {
+		uint64_t per = (uint64_t)fast_slots_per_cta();
+		uint64_t groups = (p->n_fast + per - 1) / per;
+		p->fast_ctas = (uint64_t)p->sm_count < groups ? p->sm_count : (int)groups;
+		CU(cudaMalloc(&p->d_hist, (size_t)p->fast_ctas * fast_hist_words_per_cta() * 4));
+	}
 	if (p->n_generic) {
 		size_t stride = generic_scratch_words(max_blen, max_cols);
 		size_t budget = (size_t)4 << 30; /* bytes of scratch we are willing to hold */
@@ -350,15 +360,12 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 	a.cks = p->d_cks;
 	a.tables = p->d_tables;
 	a.fmt = p->fmt;
+	a.hist = p->d_hist;
 	if (p->n_fast) {
-		int ctas = p->sm_count;
-		uint64_t groups = (p->n_fast + 29) / 30;
-		if ((uint64_t)ctas > groups)
-			ctas = (int)groups;
 		a.streams = p->d_streams;
 		a.count = (uint32_t)p->n_fast;
 		a.counter = p->d_counters;
-		CU(launch_fast(a, ctas, st));
+		CU(launch_fast(a, p->fast_ctas, st));
 	}
 	if (p->n_generic) {
 		a.streams = p->d_streams + p->n_fast;

@@ -9,11 +9,16 @@
  *    "scan" warp per CTA runs it with one stream per lane (S streams in flight per
  *    CTA) as a flat, divergence-free state machine: every iteration each lane either
  *    reads a column selector (and, for prefix codes, the first table step out of the
- *    same 32-bit peek) or takes one more multi-symbol table step.  Each lane reads its
- *    stream through a 1 KiB shared-memory ring that is refilled 256 bytes at a time by
- *    TMA bulk copies (cp.async.bulk + mbarrier), two quarters ahead of the read
- *    position, so the walk never waits on HBM.  The 128 column offsets of each block
- *    are published through shared memory.
+ *    same 32-bit peek, via the 13-bit sel13 table) or takes one more multi-symbol table
+ *    step (kstep table, row cap folded in).  Each lane reads its stream straight from
+ *    global memory through a three-word register window: the 128-byte line it is in is
+ *    L1 resident, the next line is prefetched, and the refill is a handful of predicated
+ *    instructions.  (A per-lane TMA ring in shared memory was tried first: every ring
+ *    refill is a single-lane slow path with a proxy fence and an mbarrier wait that
+ *    stalls the other 31 lanes -- profiles/r01_ncu_v4_summary.md.)  The walk is a
+ *    dependent chain (~450 steps per block), so a CTA runs TWO scan warps = 64 stream
+ *    slots to cover the latency with streams.  The 128 column offsets of each block are
+ *    published through shared memory.
  *  - Everything else is parallel inside a block.  W "worker" warps each own S/W of the
  *    CTA's stream slots.  Per block a worker warp
  *      stage    copies the block's compressed bytes (<= 4.2 KB, known from the scan)
@@ -28,8 +33,9 @@
  *               62-word halo that is recomputed instead of exchanged;
  *      output   >>7, low 16 bits, byte order / sign bias folded into one PRMT (+LOP),
  *               eight 128-bit stores per lane: the block leaves as 4 KiB of PCM.
- *    The reference's wrapbuf (decode.c:803, 2*cols-2 = 254 words) becomes per-slot
- *    history in shared memory: last 128 X0 words, last 64 X1 words, last 64 X2 words.
+ *    The reference's wrapbuf (decode.c:803, 2*cols-2 = 254 words) becomes 256 words of
+ *    per-slot history (last 128 X0, 64 X1, 64 X2 words) kept in an L2-resident global
+ *    array, which lets any worker warp take any slot (dynamic slot queue per round).
  *  - Scan and workers are double buffered: in round r the scan warp walks block r of
  *    every slot while the workers decode block r-1; one __syncthreads per round.
  *  - Streams are handed out by an atomic cursor in longest-first order; a slot that
@@ -47,19 +53,18 @@ namespace fast {
 constexpr int LEVEL = 7;
 constexpr int COLS = 128;
 constexpr int ROWS = 16;
-constexpr int BLEN = COLS * ROWS;      /* 2048 */
-constexpr int W = 15;                  /* worker warps (+1 scan warp = 512 threads, 128 regs) */
-constexpr int S = 2 * W;               /* stream slots per CTA = active lanes of the scan warp */
-constexpr int THREADS = 32 * (W + 1);
-constexpr int SLOTS_PER_WORKER = S / W;
-constexpr int OFF_PITCH = 33;          /* u16 per column row of the offset table (bank spread) */
-constexpr int XWORDS = BLEN + 4 * 32;  /* transpose layout: 4 pad words per 64 */
-constexpr int X0_BYTES = BLEN * 2;     /* int16 indices */
-constexpr int STAGE_BYTES = XWORDS * 4 - X0_BYTES; /* 4608: a whole block (<= 4179 B) + slack */
+constexpr int BLEN = COLS * ROWS;        /* 2048 */
+constexpr int NSCAN = 2;                 /* scan warps */
+constexpr int W = 13;                    /* worker warps; 15 warps = 480 threads -> 128 regs/thread */
+constexpr int S = 32 * NSCAN;            /* stream slots per CTA */
+constexpr int THREADS = 32 * (W + NSCAN);
+constexpr int OFF_PITCH = S + 2;         /* u16 per column row of the offset table (bank spread) */
+constexpr int XPRE = 68;                 /* chunk -1: the previous block's last 64 X2 words (+4 pad) */
+constexpr int XWORDS = XPRE + BLEN + 4 * 32; /* transpose layout: 4 pad words per 64 */
+constexpr int X0_WORDS = BLEN / 2;       /* int16 indices */
+constexpr int STAGE_BYTES = (BLEN + 4 * 32 - X0_WORDS) * 4; /* 4608: a whole block (<= 4179 B) + slack */
 constexpr int STAGE_CHUNKS = STAGE_BYTES / 16;
-constexpr int RING_WORDS = 256;        /* per-slot compressed window: 4 quarters of 256 B */
-constexpr int QWORDS = 64;
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
+constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [128,192) X2 tail [192,256) */
 
 enum { ENT_IDLE = -100 };
 
@@ -76,57 +81,22 @@ struct Entry {
 
 struct Smem {
 	uint64_t k8[ACM_K8_SIZE];
-	uint32_t x[W][XWORDS];       /* per worker: int16 X0 + staged bytes, later transposed X2 */
-	uint32_t ring[S][RING_WORDS];
-	uint32_t hist0[S][128];      /* last 128 X0 words: [k*32+lane] = x[60+k] of that lane */
-	uint32_t hist1[S][64];       /* last 64 X1 words: [k*32+lane] = y[62+k] */
-	uint32_t hist2[S][64];       /* last 64 X2 words, flat order */
-	unsigned long long bar[S][4];
-	unsigned long long cks[S];
+	uint16_t sel13[8192];
+	uint8_t kstep[8 * 8 * 256];
+	uint32_t x[W][XWORDS];       /* per worker: chunk -1 | int16 X0 + staged bytes, later transposed X2 */
+	uint16_t coloff[2][COLS * OFF_PITCH];
 	Entry ent[2][S];
+	unsigned long long cks[S];
 	uint32_t pos[S];
 	uint32_t dead[S];
-	uint16_t coloff[2][COLS * OFF_PITCH];
 	uint32_t info[32];
 	uint16_t t[ACM_T_SIZE];
-	uint8_t kind[32];
-	int more[2];
+	int more[2][NSCAN];
+	uint32_t next_slot[2];
 };
 
 /* ------------------------------------------------------------------ PTX helpers */
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-	return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count)
-{
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes)
-{
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-		     : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity)
-{
-	uint32_t ok;
-	asm volatile("{\n\t.reg .pred p;\n\t"
-		     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-		     "selp.u32 %0, 1, 0, p;\n\t}"
-		     : "=r"(ok)
-		     : "r"(smem_u32(bar)), "r"(parity)
-		     : "memory");
-	return ok != 0;
-}
-/* TMA 1-D bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP) */
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar)
-{
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-			     smem_u32(dst)),
-		     "l"(src), "r"(bytes), "r"(smem_u32(bar))
-		     : "memory");
-}
 __device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
 {
 	uint4 r;
@@ -135,161 +105,82 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
 		     : "l"(p));
 	return r;
 }
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+}
 
 /* ------------------------------------------------------------------ bit readers */
 
 /*
- * Scan-lane reader: the stream is seen through a 4-quarter shared-memory ring.  Quarter
- * numbers G are global per lane (they keep counting across streams) so that ring slot
- * G&3 and mbarrier parity (G>>2)&1 stay consistent.  The ring always holds the quarter
- * before the read position and up to two ahead.
+ * Scan-lane reader: a three-word register window (w0,w1 = the words under the read
+ * position, w2 = the next one, already loaded) over the stream in global memory.  The
+ * EOF rule -- file bits, then one zero byte, then nothing (decode.c:57-61) -- only costs
+ * a compare on the refill path: words below fe_word are loaded as they are.
  */
-struct RingReader {
-	const uint32_t *ring;
-	unsigned long long *bars;
-	const uint8_t *src;  /* stream base in global memory (16-byte aligned) */
-	uint64_t room;       /* bytes readable at src */
-	uint32_t file_end;
-	int32_t g0;          /* G of the current stream's quarter 0 */
-	int32_t g_rd;        /* highest G waited for */
-	int32_t g_is;        /* next G to issue */
-	uint32_t widx, w0, w1;
-	uint32_t *errflag;
+struct ScanReader {
+	const uint32_t *base; /* stream base (16-byte aligned) */
+	uint32_t fe_word, fe_tail;
+	uint32_t widx, w0, w1, w2;
 
-	__device__ __forceinline__ void issue(int32_t G)
+	__device__ __forceinline__ uint32_t ld(uint32_t i) const
 	{
-		const uint64_t off = (uint64_t)(uint32_t)(G - g0) * (QWORDS * 4);
-		uint32_t bytes = 0;
-		if (off < room)
-			bytes = room - off < (uint64_t)(QWORDS * 4) ? (uint32_t)(room - off) : (uint32_t)(QWORDS * 4);
-		unsigned long long *bar = bars + (G & 3);
-		/* order this lane's earlier generic-proxy reads of the slot before the async write */
-		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-		mbar_expect_tx(bar, bytes);
-		if (bytes)
-			bulk_g2s((void *)(ring + (G & 3) * QWORDS), src + off, bytes, bar);
-	}
-	__device__ __forceinline__ void wait(int32_t G)
-	{
-		unsigned long long *bar = bars + (G & 3);
-		const uint32_t parity = ((uint32_t)G >> 2) & 1u;
-		uint32_t spins = 0;
-		while (!mbar_try_wait(bar, parity)) {
-			if (++spins > SPIN_LIMIT) {
-				atomicExch(errflag, 1u);
-				break;
-			}
-		}
-	}
-	__device__ __forceinline__ void drain()
-	{
-		while (g_rd + 1 < g_is) {
-			g_rd++;
-			wait(g_rd);
-		}
+		if (i < fe_word)
+			return __ldg(base + i);
+		if (i == fe_word && fe_tail)
+			return __ldg(base + i) & ((1u << fe_tail) - 1u);
+		return 0u;
 	}
 	__device__ __forceinline__ void reset()
 	{
-		g0 = 0;
-		g_rd = -1;
-		g_is = 0;
-		widx = 0xFFFFFFF0u;
-		w0 = w1 = 0;
-		src = nullptr;
-		room = 0;
-		file_end = 0;
+		base = nullptr;
+		fe_word = fe_tail = 0;
+		widx = w0 = w1 = w2 = 0;
 	}
-	__device__ __forceinline__ void start(const uint8_t *s, uint64_t r, uint32_t fe)
+	__device__ __forceinline__ void start(const uint8_t *src, uint32_t file_end, uint32_t P0)
 	{
-		drain();             /* nothing of the previous stream may still be landing */
-		g0 = g_is;
-		g_rd = g_is - 1;
-		src = s;
-		room = r;
-		file_end = fe;
-		widx = 0xFFFFFFF0u;
-		issue(g_is++);
-		issue(g_is++);
-		issue(g_is++);
+		base = reinterpret_cast<const uint32_t *>(src);
+		fe_word = file_end >> 5;
+		fe_tail = file_end & 31u;
+		widx = P0 >> 5;
+		w0 = ld(widx);
+		w1 = ld(widx + 1);
+		w2 = ld(widx + 2);
+		prefetch_l1(base + widx + 32);
 	}
-	/* make word i readable: wait for its quarter, keep two quarters in flight behind it */
-	__device__ __forceinline__ void ensure(uint32_t i)
+	/* reposition the window on P; must follow every change of the read position */
+	__device__ __forceinline__ void advance(uint32_t P)
 	{
-		const int32_t G = g0 + (int32_t)(i / QWORDS);
-		while (g_rd < G) {
-			g_rd++;
-			wait(g_rd);
-			while (g_is <= g_rd + 2)
-				issue(g_is++);
-		}
-	}
-	__device__ __forceinline__ uint32_t word(uint32_t i) const
-	{
-		const uint32_t last = file_end >> 5, tail = file_end & 31u;
-		if (i > last || (i == last && !tail))
-			return 0u; /* decode.c:57-61: one zero byte, then nothing */
-		uint32_t v = ring[(((uint32_t)g0 + i / QWORDS) & 3u) * QWORDS + (i % QWORDS)];
-		if (i == last)
-			v &= (1u << tail) - 1u;
-		return v;
-	}
-	__device__ __forceinline__ uint32_t peek(uint32_t P)
-	{
-		const uint32_t i = P >> 5, s = P & 31u;
+		const uint32_t i = P >> 5;
 		if (i != widx) {
-			ensure(i + 1);
 			if (i == widx + 1) {
 				w0 = w1;
-				w1 = word(i + 1);
+				w1 = w2;
 			} else {
-				w0 = word(i);
-				w1 = word(i + 1);
+				w0 = ld(i);
+				w1 = ld(i + 1);
 			}
+			w2 = ld(i + 2);
+			if ((i >> 5) != (widx >> 5))
+				prefetch_l1(base + i + 32); /* next 128-byte line */
 			widx = i;
 		}
-		return __funnelshift_r(w0, w1, s);
+	}
+	__device__ __forceinline__ uint32_t peek(uint32_t P) const
+	{
+		return __funnelshift_r(w0, w1, P & 31u);
 	}
 };
 
-/* Worker reader: the block's bytes staged in shared memory, words [w_lo, w_lo + n). */
+/* Worker view of the staged block: stream words [w_lo, w_lo + n) in shared memory, EOF
+ * already patched in at staging time; anything outside reads as zero. */
 struct StageReader {
 	const uint32_t *st;
-	uint32_t w_lo, n, file_end;
-	uint32_t widx, w0, w1;
-
-	__device__ __forceinline__ void init(const uint32_t *s, uint32_t lo, uint32_t cnt, uint32_t fe)
-	{
-		st = s;
-		w_lo = lo;
-		n = cnt;
-		file_end = fe;
-		widx = 0xFFFFFFF0u;
-		w0 = w1 = 0;
-	}
+	uint32_t w_lo, n;
 	__device__ __forceinline__ uint32_t word(uint32_t i) const
 	{
-		const uint32_t last = file_end >> 5, tail = file_end & 31u;
-		if (i > last || (i == last && !tail) || i - w_lo >= n)
-			return 0u;
-		uint32_t v = st[i - w_lo];
-		if (i == last)
-			v &= (1u << tail) - 1u;
-		return v;
-	}
-	__device__ __forceinline__ uint32_t peek(uint32_t P)
-	{
-		const uint32_t i = P >> 5, s = P & 31u;
-		if (i != widx) {
-			if (i == widx + 1) {
-				w0 = w1;
-				w1 = word(i + 1);
-			} else {
-				w0 = word(i);
-				w1 = word(i + 1);
-			}
-			widx = i;
-		}
-		return __funnelshift_r(w0, w1, s);
+		const uint32_t k = i - w_lo;
+		return k < n ? st[k] : 0u;
 	}
 };
 
@@ -297,21 +188,19 @@ struct StageReader {
 
 /*
  * Per-selector facts for this block shape (16 rows), one 32-bit word each:
- *   bits 0..15  payload bits of a fixed-size filler (zero 0, linear 16*ind, t15 6*5,
- *               t27 6*7, t37 8*7)
  *   bit 16 prefix-coded (k) filler, bit 17 bad selector, bit 18 t filler, bit 19 linear
  *   bits 20..23 sub-type: k8 table number / t table number
  */
 enum { INF_K = 1u << 16, INF_BAD = 1u << 17, INF_T = 1u << 18, INF_LIN = 1u << 19 };
 
-__device__ __forceinline__ uint32_t make_info(uint32_t ind, uint32_t kind)
+__device__ __forceinline__ uint32_t make_info(uint32_t kind)
 {
 	const uint32_t cls = kind & 7u, sub = kind >> 3;
 	uint32_t v = sub << 20;
 	if (cls == ACM_CLS_LINEAR)
-		v |= INF_LIN | ((uint32_t)ROWS * ind);
+		v |= INF_LIN;
 	else if (cls == ACM_CLS_T)
-		v |= INF_T | (sub == 0 ? 30u : (sub == 1 ? 42u : 56u));
+		v |= INF_T;
 	else if (cls == ACM_CLS_K)
 		v |= INF_K;
 	else if (cls == ACM_CLS_BAD)
@@ -320,26 +209,26 @@ __device__ __forceinline__ uint32_t make_info(uint32_t ind, uint32_t kind)
 }
 
 /*
- * Flat walk over one block for every lane of the scan warp at once (replaces the
+ * Flat walk over one block for every lane of a scan warp at once (replaces the
  * per-column loop nest of scan_block for this shape; same verdicts).  Each iteration a
- * lane is either AT A SELECTOR (rem == 0) or INSIDE a prefix-coded column (rem rows
- * still to come).  The body is written with selects instead of branches and the loop
- * condition is a warp vote, so the 32 lanes execute ONE instruction stream however
- * their column types differ (the first version let the compiler rebuild nested loops:
- * 4-8 active lanes per instruction, profiles/r01_ncu_v2_summary.md).
+ * lane is either AT A SELECTOR (rem == 0: one sel13 lookup gives the whole advance of a
+ * fixed-size column, or the selector plus the first prefix-code step and its table) or
+ * INSIDE a prefix-coded column (one kstep lookup).  The body is written with selects
+ * instead of branches and the loop condition is a warp vote, so the 32 lanes execute
+ * ONE instruction stream however their column types differ
+ * (profiles/r01_ncu_v2_v3_summary.md).
  */
-__device__ __forceinline__ ScanResult scan_block_flat(RingReader &br, uint32_t P, uint32_t limit,
-						      uint16_t *coloff, const uint32_t *info,
-						      const uint64_t *k8, bool active)
+__device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P, uint32_t limit,
+						      uint16_t *coloff, const uint16_t *sel13,
+						      const uint8_t *kstep, bool active)
 {
-	const uint32_t *k8lo = reinterpret_cast<const uint32_t *>(k8); /* low halves: nv + cum */
 	const uint32_t pblock = P;
 	ScanResult s;
 	s.status = SCAN_OK;
 	s.ncols = 0;
 	s.val = 0;
 	bool done = !active;
-	uint32_t col = 0, rem = 0, ksub = 0;
+	uint32_t col = 0, rem = 0, kbase = 0;
 	if (!done) {
 		if (P + 20 > limit) { /* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
 			s.status = SCAN_EOF;
@@ -347,28 +236,26 @@ __device__ __forceinline__ ScanResult scan_block_flat(RingReader &br, uint32_t P
 		} else {
 			s.val = (int)((br.peek(P) >> 4) & 0xFFFFu);
 			P += 20;
+			br.advance(P);
 		}
 	}
 	while (__any_sync(0xFFFFFFFFu, !done)) {
 		if (!done) {
 			const uint32_t w = br.peek(P);
 			const bool at_sel = rem == 0;
-			const uint32_t inf = info[w & 31u];
+			const uint32_t es = sel13[w & 0x1FFFu];
+			const uint32_t ek = kstep[kbase + umin32(rem, 7u) * 256u + (w & 255u)];
 			/* selector: GET_BITS_EXPECT_EOF decode.c:496; f_bad decode.c:190-194 */
 			const bool sel_eof = at_sel && (P + 5u > limit);
-			const bool sel_bad = at_sel && (inf & INF_BAD) != 0u;
+			const bool sel_bad = at_sel && (es & 511u) == 0u;
 			if (at_sel && !sel_eof)
 				coloff[col * OFF_PITCH] = (uint16_t)(P - pblock);
-			const bool isk = at_sel ? (inf & INF_K) != 0u : true;
-			ksub = at_sel ? (inf >> 20) * 256u : ksub;
-			/* the selector's own peek already holds the first 8 payload bits */
-			const uint32_t sym = (at_sel ? (w >> 5) : w) & 255u;
-			const uint32_t e = k8lo[2u * (ksub + sym)];
-			const uint32_t remk = at_sel ? (uint32_t)ROWS : rem;
-			const uint32_t kk = umin32(e & 15u, remk);
-			const uint32_t klen = (e >> (4u * kk)) & 15u;
-			P += (at_sel ? 5u : 0u) + (isk ? klen : (inf & 0xFFFFu));
-			rem = isk ? remk - kk : 0u;
+			const uint32_t ks = (es >> 9) & 7u;
+			if (at_sel)
+				kbase = ((es >> 12) & 7u) * 2048u;
+			P += at_sel ? (es & 511u) : (ek & 15u);
+			rem = at_sel ? (ks ? (uint32_t)ROWS - ks : 0u) : rem - (ek >> 4);
+			br.advance(P);
 			if (sel_eof) {
 				s.status = SCAN_EOF;
 				done = true;
@@ -395,59 +282,82 @@ __device__ __forceinline__ ScanResult scan_block_flat(RingReader &br, uint32_t P
 
 /*
  * Decode one column (lane = column) into 16-bit indices x0c[r*128], r < 16.  One
- * straight-line routine per filler class, fully unrolled with predicated stores, so a
- * warp whose 32 columns mix classes pays each routine once per pass instead of
- * diverging inside data-dependent inner loops.  Returns non-zero if a t-code that the
- * reference gets to read is out of range (decode.c:412/:438/:464).
+ * straight-line routine per filler class.  Prefix- and radix-coded columns only produce
+ * values in -5..5, so their 16 rows are accumulated as 4-bit fields in two registers and
+ * stored once at the end (the first version spent 60 % of its step loop on predicated
+ * per-value stores).  Returns non-zero if a t-code that the reference gets to read is out
+ * of range (decode.c:412/:438/:464).
  */
-__device__ __forceinline__ int unpack_column(StageReader &br, uint32_t P, uint32_t limit, uint32_t ind,
+__device__ __forceinline__ int unpack_column(const StageReader &sr, uint32_t P, uint32_t limit, uint32_t ind,
 					     uint32_t inf, int16_t *x0c, const uint64_t *k8,
 					     const uint16_t *tt)
 {
 	int bad = 0;
-	if (inf & INF_K) {
-		/* prefix codes (decode.c:208-403): up to 7 values per table step */
-		const uint64_t *tab = k8 + (inf >> 20) * 256u;
-		uint32_t r = 0;
-		while (r < (uint32_t)ROWS) {
-			const uint64_t e64 = tab[br.peek(P) & 255u];
-			const uint32_t e = (uint32_t)e64, hi = (uint32_t)(e64 >> 32);
-			const uint32_t k = umin32(e & 15u, (uint32_t)ROWS - r);
-			P += (e >> (4u * k)) & 15u;
-			int16_t *d = x0c + r * COLS;
+	if (inf & (INF_K | INF_T)) {
+		uint32_t a0 = 0u, a1 = 0u; /* rows 0-7 / 8-15, one nibble each */
+		if (inf & INF_K) {
+			/* prefix codes (decode.c:208-403): up to 7 values per table step */
+			const uint64_t *tab = k8 + (inf >> 20) * 256u;
+			uint32_t i = P >> 5, lo = sr.word(i), hi = sr.word(i + 1), r = 0;
+			while (r < (uint32_t)ROWS) {
+				const uint32_t ni = P >> 5;
+				if (ni != i) { /* a step consumes <= 8 bits: at most one word further */
+					lo = hi;
+					hi = sr.word(ni + 1);
+					i = ni;
+				}
+				const uint64_t e64 = tab[__funnelshift_r(lo, hi, P & 31u) & 255u];
+				const uint32_t e = (uint32_t)e64, hv = (uint32_t)(e64 >> 32);
+				const uint32_t k = umin32(e & 15u, (uint32_t)ROWS - r);
+				P += (e >> (4u * k)) & 15u;
+				const unsigned long long vv = (unsigned long long)(hv & ((1u << (4u * k)) - 1u)) << (4u * r);
+				a0 |= (uint32_t)vv;
+				a1 |= (uint32_t)(vv >> 32);
+				r += k;
+			}
+		} else {
+			/* f_t15 / f_t27 / f_t37 (decode.c:405-476): all codes sit in one 64-bit window */
+			const uint32_t sub = inf >> 20;
+			const uint32_t width = sub == 0 ? 5u : 7u, per = sub == 2 ? 2u : 3u;
+			const uint32_t ncodes = sub == 2 ? 8u : 6u, cmask = (1u << width) - 1u;
+			const uint32_t vmask = sub == 2 ? 0xFFu : 0xFFFu;
+			const uint16_t *tab = tt + sub * 128u;
+			const uint32_t i = P >> 5, sh = P & 31u;
+			const uint32_t w0 = sr.word(i), w1 = sr.word(i + 1), w2 = sr.word(i + 2);
+			const unsigned long long win =
+				(unsigned long long)__funnelshift_r(w0, w1, sh) |
+				((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
 #pragma unroll
-			for (int j = 0; j < 7; j++)
-				if ((uint32_t)j < k)
-					d[j * COLS] = (int16_t)nib_s(hi, j);
-			r += k;
+			for (int q = 0; q < 8; q++) {
+				if ((uint32_t)q < ncodes) {
+					const uint32_t e = tab[(uint32_t)(win >> (q * width)) & cmask];
+					if (P + (q + 1) * width <= limit && (e & 0x8000u))
+						bad = 1;
+					const unsigned long long vv = (unsigned long long)(e & vmask) << (4u * q * per);
+					a0 |= (uint32_t)vv;
+					a1 |= (uint32_t)(vv >> 32);
+				}
+			}
 		}
+#pragma unroll
+		for (int r = 0; r < ROWS; r++)
+			x0c[r * COLS] = (int16_t)nib_s(r < 8 ? a0 : a1, r & 7);
 	} else if (inf & INF_LIN) {
-		/* f_linear decode.c:196-206 */
+		/* f_linear (decode.c:196-206): sliding 64-bit window, branch-free refill */
 		const uint32_t mask = (1u << ind) - 1u;
 		const int mid = 1 << (ind - 1);
+		const uint32_t i = P >> 5, sh = P & 31u;
+		unsigned long long win = (((unsigned long long)sr.word(i + 1) << 32) | sr.word(i)) >> sh;
+		uint32_t avail = 64u - sh, nx = i + 2;
 #pragma unroll
 		for (int r = 0; r < ROWS; r++) {
-			x0c[r * COLS] = (int16_t)((int)(br.peek(P) & mask) - mid);
-			P += ind;
-		}
-	} else if (inf & INF_T) {
-		/* f_t15 / f_t27 / f_t37 decode.c:405-476 */
-		const uint32_t sub = inf >> 20;
-		const uint32_t width = sub == 0 ? 5u : 7u, per = sub == 2 ? 2u : 3u;
-		const uint32_t ncodes = sub == 2 ? 8u : 6u, mask = (1u << width) - 1u;
-		const uint16_t *tab = tt + sub * 128u;
-#pragma unroll
-		for (int q = 0; q < 8; q++) {
-			if ((uint32_t)q < ncodes) {
-				const uint32_t e = tab[br.peek(P) & mask];
-				if (P + width <= limit && (e & 0x8000u))
-					bad = 1;
-				P += width;
-				const uint32_t r0 = (uint32_t)q * per;
-#pragma unroll
-				for (int j = 0; j < 3; j++)
-					if ((uint32_t)j < per && r0 + j < (uint32_t)ROWS)
-						x0c[(r0 + j) * COLS] = (int16_t)nib_s(e, j);
+			x0c[r * COLS] = (int16_t)((int)((uint32_t)win & mask) - mid);
+			win >>= ind;
+			avail -= ind;
+			if (avail <= 32u) {
+				win |= (unsigned long long)sr.word(nx) << avail;
+				avail += 32u;
+				nx++;
 			}
 		}
 	} else {
@@ -477,34 +387,38 @@ __device__ __forceinline__ uint32_t pack2(uint32_t a, uint32_t b, uint32_t sel, 
 }
 
 /*
- * Transform + output of one block by one warp.  xs holds the 16-bit indices
- * X0[row*128+col]; val is the block's multiplier.  n = words to emit (<= 2048).
+ * Transform + output of one block by one warp.  xs[0..1024) holds the 16-bit indices
+ * X0[row*128+col]; val is the block's multiplier; gh is the slot's history in global
+ * memory (first == true: all-zero history, decode.c:812).  n = words to emit (<= 2048).
  * Returns this lane's checksum contribution.
  */
 template <bool CKS>
 __device__ __forceinline__ unsigned long long
-juggle_and_store(Smem &sm, uint32_t *xs, int slot, int lane, int val, uint8_t *out, uint32_t pos0,
+juggle_and_store(uint32_t *xs, uint32_t *gh, bool first, int lane, int val, uint8_t *out, uint32_t pos0,
 		 uint32_t n, const Format fmt)
 {
-	uint32_t *h0 = sm.hist0[slot], *h1 = sm.hist1[slot], *h2 = sm.hist2[slot];
 	const int16_t *x0 = reinterpret_cast<const int16_t *>(xs);
 	uint32_t x[64];
 	unsigned long long cks = 0ull;
+
+	/* history of the previous block (L2 resident; .cg: never a stale L1 line) */
+	uint32_t hx[4], hy[2], hz[2];
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		hx[k] = first ? 0u : __ldcg(gh + 32 * k + lane);       /* X0[-128 + 32k + lane] */
+	hy[0] = first ? 0u : __ldcg(gh + 128 + lane);               /* X1[-64 + lane] */
+	hy[1] = first ? 0u : __ldcg(gh + 160 + lane);               /* X1[-32 + lane] */
+	hz[0] = first ? 0u : __ldcg(gh + 192 + lane);               /* X2[-64 + lane] */
+	hz[1] = first ? 0u : __ldcg(gh + 224 + lane);               /* X2[-32 + lane] */
 
 	/* ---- dequantise (decode.c:174-177, :591-600) and stages 1, 2 in registers:
 	 * lane owns m = 32*i + lane */
 #pragma unroll
 	for (int i = 0; i < 64; i++)
 		x[i] = (uint32_t)((int)x0[32 * i + lane] * val);
-	uint32_t hx[4], hy[2];
 #pragma unroll
 	for (int k = 0; k < 4; k++)
-		hx[k] = h0[32 * k + lane];
-	hy[0] = h1[lane];
-	hy[1] = h1[32 + lane];
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-		h0[32 * k + lane] = x[60 + k];
+		__stcg(gh + 32 * k + lane, x[60 + k]);
 	const uint32_t one0 = lane == 0 ? 1u : 0u; /* decode.c:561-564: +1 where m % 64 == 0 */
 	uint32_t y[64];
 #pragma unroll
@@ -516,9 +430,12 @@ juggle_and_store(Smem &sm, uint32_t *xs, int slot, int lane, int val, uint8_t *o
 		if ((i & 1) == 0)
 			y[i] += one0;
 	}
-	h1[lane] = y[62];
-	h1[32 + lane] = y[63];
+	__stcg(gh + 128 + lane, y[62]);
+	__stcg(gh + 160 + lane, y[63]);
 	__syncwarp(); /* every lane has read its X0 indices: the buffer can be overwritten */
+	/* chunk -1 = the previous block's last 64 X2 words */
+	xs[-XPRE + lane] = hz[0];
+	xs[-XPRE + 32 + lane] = hz[1];
 #pragma unroll
 	for (int i = 0; i < 64; i++) {
 		/* C = 32: m-32 -> i-1, m-64 -> i-2; row parity = i&1 */
@@ -527,13 +444,17 @@ juggle_and_store(Smem &sm, uint32_t *xs, int slot, int lane, int val, uint8_t *o
 		uint32_t z = lift(y[i], p1, p2, i & 1);
 		/* transpose layout: word m lives at m + 4*(m/64); m/64 = i/2 for every lane */
 		xs[32 * i + lane + 4 * (i >> 1)] = z;
+		if (i == 62)
+			__stcg(gh + 192 + lane, z);
+		if (i == 63)
+			__stcg(gh + 224 + lane, z);
 	}
 	__syncwarp();
 
 	/* ---- stages 3..7 in registers: lane owns m in [64*lane, 64*lane+64), halo = the 64
-	 * words before it (previous lane's chunk, or the previous block's tail for lane 0) */
+	 * words before it (previous lane's chunk; chunk -1 for lane 0: 68*(lane-1) = -XPRE) */
 	const uint4 *own = reinterpret_cast<const uint4 *>(xs + 68 * lane);
-	const uint4 *prev = reinterpret_cast<const uint4 *>(lane ? xs + 68 * (lane - 1) : h2);
+	const uint4 *prev = reinterpret_cast<const uint4 *>(xs + 68 * (lane - 1));
 	uint32_t u[128], a3[128], a4[128], a5[128], a6[128], a7[2];
 	const uint32_t sel = fmt.be ? 0x6701u : 0x7610u;
 	const uint32_t flip = fmt.bias ? (fmt.be ? 0x00800080u : 0x80008000u) : 0u;
@@ -592,9 +513,7 @@ juggle_and_store(Smem &sm, uint32_t *xs, int slot, int lane, int val, uint8_t *o
 			}
 		}
 	}
-	__syncwarp(); /* all halo reads done before the tail of this block becomes history */
-	if (lane < 16)
-		reinterpret_cast<uint4 *>(h2)[lane] = reinterpret_cast<const uint4 *>(xs + 68 * 31)[lane];
+	__syncwarp(); /* all shared-memory reads of this block are done */
 	return cks;
 }
 
@@ -609,45 +528,46 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 
 	for (int i = tid; i < ACM_K8_SIZE; i += THREADS)
 		sm.k8[i] = a.tables->k8[i];
+	for (int i = tid; i < 8192; i += THREADS)
+		sm.sel13[i] = a.tables->sel13_r16[i];
+	for (int i = tid; i < 8 * 8 * 256 / 4; i += THREADS)
+		reinterpret_cast<uint32_t *>(sm.kstep)[i] = reinterpret_cast<const uint32_t *>(a.tables->kstep)[i];
 	for (int i = tid; i < ACM_T_SIZE; i += THREADS)
 		sm.t[i] = a.tables->t[i];
-	if (tid < 32) {
-		sm.kind[tid] = a.tables->kind[tid];
-		sm.info[tid] = make_info((uint32_t)tid, a.tables->kind[tid]);
+	if (tid < 32)
+		sm.info[tid] = make_info(a.tables->kind[tid]);
+	for (int i = tid; i < S; i += THREADS) {
+		sm.dead[i] = 0;
+		sm.pos[i] = 0;
+		sm.cks[i] = 0ull;
 	}
-	if (tid < S) {
-		sm.dead[tid] = 0;
-		sm.pos[tid] = 0;
-		sm.cks[tid] = 0ull;
-	}
-	if (tid < S * 4)
-		mbar_init(&sm.bar[0][0] + tid, 1u);
+	if (tid < 2 * NSCAN)
+		(&sm.more[0][0])[tid] = 0;
 	if (tid < 2)
-		sm.more[tid] = 0;
-	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		sm.next_slot[tid] = 0;
 	__syncthreads();
 
-	/* scan-lane state (meaningful in the scan warp only) */
-	const bool has_slot = warp == W && lane < S;
-	const int myslot = lane < S ? lane : 0;
+	/* scan-lane state (meaningful in the scan warps only) */
+	const bool is_scan = warp >= W;
+	const int myslot = is_scan ? 32 * (warp - W) + lane : 0;
 	bool active = false;
 	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0;
-	RingReader sbr;
+	ScanReader sbr;
 	sbr.reset();
-	sbr.ring = sm.ring[myslot];
-	sbr.bars = sm.bar[myslot];
-	sbr.errflag = a.errflag;
+	uint32_t *const cta_hist = a.hist + (size_t)blockIdx.x * S * HIST_WORDS;
 
 	for (int round = 0;; round++) {
 		const int buf = round & 1;
-		if (warp == W) {
-			/* ================= scan warp: lane = stream slot ================= */
+		if (is_scan) {
+			/* ================= scan warps: lane = stream slot ================= */
 			Entry e;
 			e.status = ENT_IDLE;
 			e.pblock = 0; e.pend = 0; e.desc = 0; e.blk = 0; e.ncols = 0; e.val = 0; e.pad = 0;
+			if (warp == W && lane == 0)
+				sm.next_slot[buf] = 0; /* the workers drain this queue next round */
 			if (active && sm.dead[myslot] == cur + 1u)
 				active = false; /* a worker found a corrupt t-code: abandon the stream */
-			if (!active && has_slot) {
+			if (!active) {
 				uint32_t idx = atomicAdd(a.counter, 1u);
 				if (idx < a.count) {
 					const DevStream d = a.streams[idx];
@@ -656,8 +576,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					blk = 0;
 					limit = d.file_end + 8u;
 					n_attempt = d.n_attempt;
-					sbr.start(a.blob + d.base_off,
-						  a.blob_room > d.base_off ? a.blob_room - d.base_off : 0, d.file_end);
+					sbr.start(a.blob + d.base_off, d.file_end, P);
 					active = true;
 				}
 			}
@@ -677,8 +596,8 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 				}
 			}
 			{
-				ScanResult sc = scan_block_flat(sbr, P, limit, sm.coloff[buf] + myslot, sm.info,
-								sm.k8, walk);
+				ScanResult sc = scan_block_flat(sbr, P, limit, sm.coloff[buf] + myslot, sm.sel13,
+								sm.kstep, walk);
 				if (walk) {
 					e.status = sc.status;
 					e.ncols = sc.ncols;
@@ -692,19 +611,23 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					}
 				}
 			}
-			if (has_slot)
-				sm.ent[buf][lane] = e;
+			sm.ent[buf][myslot] = e;
 			const int any = __any_sync(0xFFFFFFFFu, e.status != ENT_IDLE);
 			if (lane == 0)
-				sm.more[buf] = any;
+				sm.more[buf][warp - W] = any;
 		} else if (round > 0) {
-			/* ================= worker warps ================= */
+			/* ================= worker warps: take slots from the round's queue ================= */
 			const int pb = buf ^ 1;
-			uint32_t *xs = sm.x[warp];
+			uint32_t *xs = sm.x[warp] + XPRE;
 			int16_t *x0 = reinterpret_cast<int16_t *>(xs);
-			uint32_t *stage = xs + X0_BYTES / 4;
-			for (int k = 0; k < SLOTS_PER_WORKER; k++) {
-				const int slot = warp + k * W;
+			uint32_t *stage = xs + X0_WORDS;
+			for (;;) {
+				int slot = 0;
+				if (lane == 0)
+					slot = (int)atomicAdd(&sm.next_slot[pb], 1u);
+				slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
+				if (slot >= S)
+					break;
 				const Entry e = sm.ent[pb][slot];
 				if (e.status == ENT_IDLE)
 					continue;
@@ -712,12 +635,6 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 				const uint32_t bno = e.blk & 0x7FFFFFFFu;
 				const bool last = (e.blk >> 31) != 0;
 				if (bno == 0) {
-					/* new stream in this slot: zero history (decode.c:812) */
-#pragma unroll
-					for (int q = 0; q < 4; q++)
-						sm.hist0[slot][32 * q + lane] = 0u;
-					sm.hist1[slot][lane] = 0u; sm.hist1[slot][32 + lane] = 0u;
-					sm.hist2[slot][lane] = 0u; sm.hist2[slot][32 + lane] = 0u;
 					if (lane == 0) {
 						sm.pos[slot] = 0u;
 						sm.cks[slot] = 0ull;
@@ -732,22 +649,38 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 				const uint32_t ncheck = ok ? (uint32_t)COLS : e.ncols + (e.status == -7 ? 1u : 0u);
 				int bad = 0;
 				if (ncheck) {
-					/* ---- stage the block's bytes: 16-byte chunks [c_lo, c_hi) of the stream */
+					/* ---- stage the block's bytes: 16-byte chunks [c_lo, c_hi) of the stream,
+					 * with the EOF rule applied (bits at and past file_end read as zero) */
 					const uint32_t c_lo = e.pblock >> 7;
-					uint32_t c_hi = (e.pend + 32u + 127u) >> 7;
+					uint32_t c_hi = (e.pend + 96u + 127u) >> 7;
 					if (c_hi > c_lo + (uint32_t)STAGE_CHUNKS)
 						c_hi = c_lo + (uint32_t)STAGE_CHUNKS;
 					const uint8_t *src = a.blob + d.base_off;
 					const uint64_t room = a.blob_room > d.base_off ? a.blob_room - d.base_off : 0;
+					const uint32_t fe_word = d.file_end >> 5, fe_tail = d.file_end & 31u;
 					for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
 						uint4 v = make_uint4(0u, 0u, 0u, 0u);
 						if ((uint64_t)c * 16u + 16u <= room)
 							v = ldg_nc_v4(src + (size_t)c * 16u);
+						if (4u * c + 3u >= fe_word) {
+							uint32_t q[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+							for (int j = 0; j < 4; j++) {
+								const uint32_t k = 4u * c + j;
+								if (k > fe_word || (k == fe_word && !fe_tail))
+									q[j] = 0u;
+								else if (k == fe_word)
+									q[j] &= (1u << fe_tail) - 1u;
+							}
+							v = make_uint4(q[0], q[1], q[2], q[3]);
+						}
 						reinterpret_cast<uint4 *>(stage)[c - c_lo] = v;
 					}
 					__syncwarp();
-					StageReader br;
-					br.init(stage, c_lo * 4u, (c_hi - c_lo) * 4u, d.file_end);
+					StageReader sr;
+					sr.st = stage;
+					sr.w_lo = c_lo * 4u;
+					sr.n = (c_hi - c_lo) * 4u;
 					/* ---- unpack: lane = column */
 					const uint16_t *offs = sm.coloff[pb] + slot;
 #pragma unroll 1
@@ -755,9 +688,11 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 						const uint32_t c = 32u * p + lane;
 						if (c < ncheck) {
 							const uint32_t Pc = e.pblock + offs[c * OFF_PITCH];
-							const uint32_t ind = br.peek(Pc) & 31u;
-							bad |= unpack_column(br, Pc + 5u, limit_w, ind, sm.info[ind], x0 + c,
-									     sm.k8, sm.t);
+							const uint32_t i = Pc >> 5;
+							const uint32_t ind =
+								__funnelshift_r(sr.word(i), sr.word(i + 1), Pc & 31u) & 31u;
+							bad |= unpack_column(sr, Pc + 5u, limit_w, ind, sm.info[ind], x0 + c, sm.k8,
+									     sm.t);
 						}
 					}
 				}
@@ -774,8 +709,8 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					if (n > (uint32_t)BLEN)
 						n = BLEN;
 					uint8_t *out = a.out + d.out_off;
-					unsigned long long c2 =
-						juggle_and_store<CKS>(sm, xs, slot, lane, e.val, out, pos, n, a.fmt);
+					unsigned long long c2 = juggle_and_store<CKS>(xs, cta_hist + slot * HIST_WORDS, bno == 0,
+										       lane, e.val, out, pos, n, a.fmt);
 					pos += n;
 					if (CKS) {
 						for (int o = 16; o; o >>= 1)
@@ -804,11 +739,13 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 			}
 		}
 		__syncthreads();
-		if (!sm.more[buf])
-			break; /* the scan warp produced nothing this round: all streams are done */
+		int more = 0;
+#pragma unroll
+		for (int k = 0; k < NSCAN; k++)
+			more |= sm.more[buf][k];
+		if (!more)
+			break; /* the scan warps produced nothing this round: all streams are done */
 	}
-	if (warp == W)
-		sbr.drain(); /* no bulk copy may still be landing when the CTA exits */
 }
 
 } // namespace fast
@@ -818,6 +755,8 @@ bool fast_shape(uint32_t level, uint32_t rows) { return level == fast::LEVEL && 
 size_t fast_smem_bytes() { return sizeof(fast::Smem); }
 
 int fast_slots_per_cta() { return fast::S; }
+
+size_t fast_hist_words_per_cta() { return (size_t)fast::S * fast::HIST_WORDS; }
 
 cudaError_t launch_fast(const KernelArgs &a, int n_ctas, cudaStream_t st)
 {

@@ -23,6 +23,7 @@ struct KernelArgs {
 	const acm_tables *tables; /* device copy */
 	uint32_t *counter;        /* work-queue cursor (zeroed before launch) */
 	uint32_t *errflag;        /* set non-zero on an internal failure (e.g. copy timeout) */
+	uint32_t *hist;           /* fast kernel: per-CTA, per-slot transform history (256 words each) */
 	Format fmt;
 };
 
@@ -45,6 +46,8 @@ cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_c
 /* level-7 / 16-row kernel (acm_fast.cu); 16-bit output formats only */
 bool fast_shape(uint32_t level, uint32_t rows);
 size_t fast_smem_bytes();
+int fast_slots_per_cta();
+size_t fast_hist_words_per_cta();
 cudaError_t launch_fast(const KernelArgs &a, int n_ctas, cudaStream_t st);
 
 /* gathers the first 48 bytes of every image (header parse on the host) */

@@ -18,6 +18,17 @@
  *   t[tt][b]    tt = 0,1,2 for selectors 19 (t15), 22 (t27), 29 (t37); b = the 5/7-bit
  *               code.  16-bit entry: three 4-bit two's complement digits, bit 15 set
  *               when the code is out of range (ACM_ERR_CORRUPT, decode.c:412/438/464).
+ *   sel13_r16[w]  scan-only, for the 16-row block shape: w = the 13 stream bits at a column
+ *               boundary (5-bit selector + first 8 payload bits).  16-bit entry:
+ *                 bits 0..8    bits to advance: 5 + the whole payload of a fixed-size filler
+ *                              (zero, linear, t15/t27/t37), or 5 + the first k8 step;
+ *                              0 marks a bad selector (f_bad, decode.c:190-194)
+ *                 bits 9..11   values that first k8 step produced; non-zero exactly for the
+ *                              prefix-coded fillers (more steps follow while rows remain)
+ *                 bits 12..14  k8 table number of that filler
+ *   kstep[kt][m][b]  scan-only: one prefix-code step with m = min(rows remaining, 7) and b = the
+ *               next 8 stream bits.  8-bit entry: bits 0..3 bits consumed, bits 4..6 values
+ *               produced (k8's nv and cum with the row cap already applied).
  */
 #ifndef ACM_TABLES_H
 #define ACM_TABLES_H
@@ -31,6 +42,8 @@
 typedef struct acm_tables {
 	uint64_t k8[ACM_K8_SIZE];
 	uint16_t t[ACM_T_SIZE];
+	uint16_t sel13_r16[8192];
+	uint8_t kstep[8 * 8 * 256];
 	uint8_t kind[32];  /* per selector: class | (subtype << 3); see ACM_CLS_* */
 	uint8_t pad[32];
 } acm_tables;
