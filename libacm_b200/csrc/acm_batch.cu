@@ -361,6 +361,9 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 	a.tables = p->d_tables;
 	a.fmt = p->fmt;
 	a.hist = p->d_hist;
+	a.resume_hist = nullptr;
+	a.resume_stride = 0;
+	a.end_pos = nullptr;
 	if (p->n_fast) {
 		a.streams = p->d_streams;
 		a.count = (uint32_t)p->n_fast;

@@ -39,6 +39,8 @@ struct DevStream {
 	uint32_t index;       /* slot in the result arrays (caller's order) */
 	uint32_t rows;
 	uint32_t level;
+	uint32_t resume;      /* 1: continue a stream (history comes from KernelArgs::resume_hist) */
+	uint32_t reserved;
 };
 
 struct Format {

@@ -72,11 +72,13 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 		br.init((const uint32_t *)(a.blob + d.base_off), d.file_end);
 		uint8_t *out = a.out + d.out_off;
 
+		uint32_t *rh = a.resume_hist ? a.resume_hist + (size_t)si * a.resume_stride : nullptr;
 		for (uint32_t i = tid; i < 2 * cols; i += GEN_THREADS)
-			hist[i] = 0u; /* zeroed history: decode.c:812 */
+			hist[i] = (rh && d.resume) ? rh[i] : 0u; /* zeroed history: decode.c:812 */
 		uint32_t *cur = buf0, *nxt = buf1;
 		uint32_t P = d.bit0, pos = 0;
 		int st = 0;
+		uint32_t nok = 0;
 		unsigned long long cks = 0ull;
 		__syncthreads();
 
@@ -138,6 +140,7 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 					cks += (unsigned long long)(pos + m + 1u) * (unsigned long long)(u + 1ull);
 			}
 			pos += n;
+			nok = b + 1;
 			__syncthreads();
 		}
 
@@ -155,10 +158,17 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 				atomicAdd(&s_cks, cks);
 		}
 		__syncthreads();
+		if (rh)
+			for (uint32_t i = tid; i < 2 * cols; i += GEN_THREADS)
+				rh[i] = hist[i];
 		if (tid == 0) {
 			a.status[d.index] = st;
 			a.words[d.index] = pos;
 			a.cks[d.index] = s_cks;
+			if (a.end_pos) {
+				a.end_pos[2 * si] = P;
+				a.end_pos[2 * si + 1] = nok;
+			}
 		}
 		__syncthreads();
 	}

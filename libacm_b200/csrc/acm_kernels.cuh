@@ -24,6 +24,14 @@ struct KernelArgs {
 	uint32_t *counter;        /* work-queue cursor (zeroed before launch) */
 	uint32_t *errflag;        /* set non-zero on an internal failure (e.g. copy timeout) */
 	uint32_t *hist;           /* fast kernel: per-CTA, per-slot transform history (256 words each) */
+	/* generic kernel, resumable decode (acm_stream.cu): when resume_hist != NULL stream i of the
+	 * slice starts from / leaves its per-stage history at resume_hist + i * resume_stride (2*cols
+	 * words); a stream whose DevStream::resume is 0 still starts from zero history.
+	 * end_pos[2i] receives the bit position after the last block that decoded, end_pos[2i+1]
+	 * the number of blocks that decoded. */
+	uint32_t *resume_hist;
+	uint32_t resume_stride;
+	uint32_t *end_pos;
 	Format fmt;
 };
 

@@ -1,0 +1,614 @@
+/*
+ * acm_stream.cu -- the libacm.h drop-in surface (reference src/libacm.h:120-170) on top
+ * of the CUDA decoder.
+ *
+ * Same signatures, argument meaning, return codes and bookkeeping as the reference's
+ * acm_open_decoder / acm_read / acm_close (decode.c:758-893) and util.c (acm_open_file,
+ * the info getters, acm_seek_pcm / acm_seek_time, acm_read_loop, acm_strerror).  What is
+ * different is where decode_block (decode.c:580-611) runs: blocks are decoded on the
+ * GPU in look-ahead chunks (resumable generic kernel: bit position + per-stage history
+ * carried from chunk to chunk) into a host-side PCM cache that acm_read serves from.
+ *
+ *  - acm_open_decoder pulls the whole image through read_func (the reference pulls
+ *    64 KiB at a time, decode.c:41-67; short reads are fine), parses the header on the
+ *    host and uploads the image once.
+ *  - acm_read keeps the reference's contract to the letter: never crosses a block
+ *    boundary, clips to total_values, rounds down to whole frames, dst == NULL decodes
+ *    and discards (decode.c:826-876).  The PCM format is a per-call argument, so the
+ *    cache remembers the format it holds and a chunk is simply decoded again if a
+ *    caller switches formats mid-stream.
+ *  - acm_seek_pcm follows util.c:214-253 (one seek_func call on a backward seek,
+ *    ACM_ERR_NOT_SEEKABLE without it, forward skipping by acm_read(NULL)), but every
+ *    chunk boundary visited so far is an index entry (block number, bit position,
+ *    history snapshot), so a seek re-decodes at most one chunk instead of the whole
+ *    prefix.
+ *
+ * Deviations, all outside what the reference defines: ACM_ERR_CORRUPT is sticky (the
+ * reference has no resync and re-enters decode_block at an undefined position, SURVEY
+ * Q17; after ACM_ERR_UNEXPECTED_EOF it reports a clean end of stream, and so do we);
+ * acm_raw_tell reports the bytes consumed up to the end of the decoded look-ahead;
+ * wordlen 3 and 4 are accepted (the reference returns ACM_ERR_BADFMT).
+ * There is no CPU decode path: without a usable CUDA device acm_open_decoder fails
+ * with ACM_ERR_OTHER.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "acm_gpu.h"
+#include "acm_host.h"
+#include "acm_kernels.cuh"
+#include "libacm.h"
+
+using namespace acm;
+
+namespace {
+
+struct SavedState {
+	uint32_t block;             /* state at the START of this block */
+	uint32_t P;                 /* bit position (P coordinates) */
+	std::vector<uint32_t> hist; /* 2*cols words; empty = all zero (block 0) */
+};
+
+struct GpuState {
+	int device = 0;
+	std::vector<uint8_t> file;
+	acm_header hdr{};
+	DevStream base{};            /* descriptor of the whole stream (block 0 start) */
+	uint32_t n_attempt_total = 0, words_limit = 0, chunk_blocks = 1, cols = 1;
+	bool read_error = false;
+
+	/* device side */
+	uint8_t *d_blob = nullptr;
+	uint64_t blob_room = 0;
+	DevStream *d_desc = nullptr;
+	int32_t *d_status = nullptr;
+	uint32_t *d_words = nullptr;
+	unsigned long long *d_cks = nullptr;
+	uint32_t *d_counter = nullptr;
+	uint32_t *d_endpos = nullptr;
+	uint32_t *d_hist = nullptr;
+	acm_tables *d_tables = nullptr;
+	GenericScratch scratch{};
+	uint8_t *d_pcm = nullptr;
+	size_t pcm_cap = 0;
+	cudaStream_t stream = nullptr;
+
+	/* host chunk cache */
+	std::vector<uint8_t> pcm;
+	bool c_valid = false;
+	int c_fmt = -1;
+	uint32_t c_block0 = 0, c_attempted = 0, c_nok = 0, c_words = 0, c_endP = 0;
+	int c_status = 0;            /* verdict of attempt c_block0 + c_nok when c_nok < c_attempted */
+
+	std::vector<SavedState> index;  /* sorted by block; [0] is block 0 */
+	uint32_t next_block = 0;        /* block acm_read decodes next when !block_ready */
+	uint32_t cur_block = 0;         /* block the current block_pos refers to */
+	uint32_t consumed_P = 0;        /* for acm_raw_tell */
+	bool drained = false;           /* an UNEXPECTED_EOF was reported: the reference's bit reader is
+					   empty after it, so every later decode_block is a clean EOF */
+};
+
+inline int fmt_key(int be, int wordlen, int sgned) { return (be ? 1 : 0) | (wordlen << 1) | (sgned ? 16 : 0); }
+
+#define CUS(call)                                                                   \
+	do {                                                                        \
+		cudaError_t e_ = (call);                                            \
+		if (e_ != cudaSuccess) {                                            \
+			acm_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call,   \
+				      cudaGetErrorString(e_));                      \
+			return ACM_ERR_OTHER;                                       \
+		}                                                                   \
+	} while (0)
+
+void gpu_free(GpuState *g)
+{
+	if (!g)
+		return;
+	cudaSetDevice(g->device);
+	cudaFree(g->d_blob);
+	cudaFree(g->d_desc);
+	cudaFree(g->d_status);
+	cudaFree(g->d_words);
+	cudaFree(g->d_cks);
+	cudaFree(g->d_counter);
+	cudaFree(g->d_endpos);
+	cudaFree(g->d_hist);
+	cudaFree(g->d_tables);
+	cudaFree(g->scratch.buf);
+	cudaFree(g->d_pcm);
+	if (g->stream)
+		cudaStreamDestroy(g->stream);
+	delete g;
+}
+
+int gpu_setup(GpuState *g)
+{
+	acm_tables tab;
+	const uint32_t blen = g->hdr.rows << g->hdr.level;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		acm_set_error("no CUDA device: libacm_b200 has no CPU decode path");
+		return ACM_ERR_OTHER;
+	}
+	CUS(cudaGetDevice(&g->device));
+	CUS(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+	g->blob_room = (g->file.size() + 15u) & ~(uint64_t)15u;
+	CUS(cudaMalloc(&g->d_blob, g->blob_room + 64));
+	CUS(cudaMemsetAsync(g->d_blob, 0, g->blob_room + 64, g->stream));
+	CUS(cudaMemcpyAsync(g->d_blob, g->file.data(), g->file.size(), cudaMemcpyHostToDevice, g->stream));
+	CUS(cudaMalloc(&g->d_desc, sizeof(DevStream)));
+	CUS(cudaMalloc(&g->d_status, 16));
+	CUS(cudaMalloc(&g->d_words, 16));
+	CUS(cudaMalloc(&g->d_cks, 16));
+	CUS(cudaMalloc(&g->d_counter, 64));
+	CUS(cudaMalloc(&g->d_endpos, 16));
+	CUS(cudaMalloc(&g->d_hist, (size_t)2 * g->cols * 4 + 16));
+	acm_tables_build(&tab);
+	CUS(cudaMalloc(&g->d_tables, sizeof(acm_tables)));
+	CUS(cudaMemcpyAsync(g->d_tables, &tab, sizeof(tab), cudaMemcpyHostToDevice, g->stream));
+	g->scratch.stride = generic_scratch_words(blen, g->cols);
+	g->scratch.max_blen = blen;
+	g->scratch.max_cols = g->cols;
+	CUS(cudaMalloc(&g->scratch.buf, g->scratch.stride * 4));
+	g->pcm_cap = (size_t)g->chunk_blocks * blen * 4 + 64;
+	CUS(cudaMalloc(&g->d_pcm, g->pcm_cap));
+	CUS(cudaStreamSynchronize(g->stream)); /* `tab` is on this stack frame */
+	return ACM_OK;
+}
+
+/*
+ * Decode the chunk that starts at index entry `si` (blocks [b0, b0 + nb)) in format key
+ * `fmt` into the host cache.  On full success the end state becomes a new index entry.
+ */
+int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, int sgned)
+{
+	const SavedState &s0 = g->index[si];
+	const uint32_t blen = acm->block_len, b0 = s0.block;
+	uint32_t nb = g->n_attempt_total - b0;
+	if (nb > g->chunk_blocks)
+		nb = g->chunk_blocks;
+	DevStream d = g->base;
+	KernelArgs a;
+	uint32_t endpos[2] = { 0, 0 }, words = 0;
+	int32_t status = 0;
+
+	CUS(cudaSetDevice(g->device));
+	d.bit0 = s0.P;
+	d.out_off = 0;
+	d.index = 0;
+	d.pad_words = 0;
+	d.n_attempt = nb;
+	d.resume = s0.hist.empty() ? 0u : 1u;
+	{
+		/* words the read loop may still deliver from block b0 on, capped to this chunk */
+		uint64_t done = (uint64_t)b0 * blen;
+		uint64_t left = g->words_limit > done ? g->words_limit - done : 0;
+		uint64_t cap = (uint64_t)nb * blen;
+		d.words_limit = (uint32_t)(left < cap ? left : cap);
+	}
+	CUS(cudaMemcpyAsync(g->d_desc, &d, sizeof(d), cudaMemcpyHostToDevice, g->stream));
+	if (d.resume)
+		CUS(cudaMemcpyAsync(g->d_hist, s0.hist.data(), s0.hist.size() * 4, cudaMemcpyHostToDevice, g->stream));
+	CUS(cudaMemsetAsync(g->d_counter, 0, 64, g->stream));
+	memset(&a, 0, sizeof(a));
+	a.blob = g->d_blob;
+	a.blob_room = g->blob_room;
+	a.out = g->d_pcm;
+	a.streams = g->d_desc;
+	a.count = 1;
+	a.status = g->d_status;
+	a.words = g->d_words;
+	a.cks = g->d_cks;
+	a.tables = g->d_tables;
+	a.counter = g->d_counter;
+	a.errflag = g->d_counter + 2;
+	a.fmt.wordlen = wordlen;
+	a.fmt.be = be ? 1 : 0;
+	a.fmt.bias = sgned ? 0u : (1u << (8 * wordlen - 1));
+	a.fmt.checksums = 0;
+	a.resume_hist = g->d_hist;
+	a.resume_stride = 2 * g->cols;
+	a.end_pos = g->d_endpos;
+	CUS(launch_generic(a, g->scratch, 1, g->stream));
+	CUS(cudaMemcpyAsync(&status, g->d_status, 4, cudaMemcpyDeviceToHost, g->stream));
+	CUS(cudaMemcpyAsync(&words, g->d_words, 4, cudaMemcpyDeviceToHost, g->stream));
+	CUS(cudaMemcpyAsync(endpos, g->d_endpos, 8, cudaMemcpyDeviceToHost, g->stream));
+	CUS(cudaStreamSynchronize(g->stream));
+	g->pcm.resize((size_t)words * wordlen + 16);
+	if (words)
+		CUS(cudaMemcpy(g->pcm.data(), g->d_pcm, (size_t)words * wordlen, cudaMemcpyDeviceToHost));
+	g->c_valid = true;
+	g->c_fmt = fmt_key(be, wordlen, sgned);
+	g->c_block0 = b0;
+	g->c_attempted = nb;
+	g->c_nok = endpos[1];
+	g->c_words = words;
+	g->c_endP = endpos[0];
+	g->c_status = status;
+	if (g->c_endP > g->consumed_P)
+		g->consumed_P = g->c_endP;
+	if (g->c_nok == nb && b0 + nb < g->n_attempt_total && si + 1 == g->index.size()) {
+		SavedState n;
+		n.block = b0 + nb;
+		n.P = g->c_endP;
+		n.hist.resize((size_t)2 * g->cols);
+		CUS(cudaMemcpy(n.hist.data(), g->d_hist, n.hist.size() * 4, cudaMemcpyDeviceToHost));
+		g->index.push_back(std::move(n));
+	}
+	return ACM_OK;
+}
+
+/*
+ * Make block b available in the cache (in the given format).  Returns 1 if the block
+ * decoded, 0 for a clean end of stream at that block (decode.c:842-843), <0 for the
+ * error the reference's decode_block would return.
+ */
+int ensure_block(ACMStream *acm, GpuState *g, uint32_t b, int be, int wordlen, int sgned)
+{
+	const int key = fmt_key(be, wordlen, sgned);
+	for (;;) {
+		if (g->c_valid && g->c_fmt == key && b >= g->c_block0 && b < g->c_block0 + g->c_attempted) {
+			if (b < g->c_block0 + g->c_nok)
+				return 1;
+			/* b is the failing attempt (later blocks are never reached); if the data source
+			 * itself failed, running out of bits is a read error (decode.c:54-55) */
+			if (g->read_error && (g->c_status == 0 || g->c_status == ACM_ERR_UNEXPECTED_EOF))
+				return ACM_ERR_READ_ERR;
+			return g->c_status;
+		}
+		if (b >= g->n_attempt_total)
+			return 0;
+		/* index entry with the largest block <= b */
+		size_t si = g->index.size() - 1;
+		while (si > 0 && g->index[si].block > b)
+			si--;
+		/* entries are chunk starts; if b lies past the chunk of the last entry, walk forward */
+		int err = decode_chunk(acm, g, si, be, wordlen, sgned);
+		if (err < 0)
+			return err;
+		if (b >= g->c_block0 + g->c_attempted) {
+			if (g->c_nok < g->c_attempted) {
+				/* an earlier block fails: b is unreachable, report that failure */
+				if (g->read_error && (g->c_status == 0 || g->c_status == ACM_ERR_UNEXPECTED_EOF))
+					return ACM_ERR_READ_ERR;
+				return g->c_status;
+			}
+			continue; /* a new index entry was appended: decode the next chunk */
+		}
+	}
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------ open / close */
+
+extern "C" int acm_open_decoder(ACMStream **res, void *io_arg, acm_io_callbacks io, int force_chans)
+{
+	ACMStream *acm = (ACMStream *)calloc(1, sizeof(*acm));
+	GpuState *g = nullptr;
+	int err = ACM_ERR_OTHER;
+	if (!acm)
+		return ACM_ERR_OTHER;
+	acm->io_arg = io_arg;
+	acm->io = io;
+	acm->data_len = io.get_length_func ? (unsigned)io.get_length_func(io_arg) : 0; /* decode.c:771-775 */
+	g = new (std::nothrow) GpuState();
+	if (!g)
+		goto fail;
+	/* pull the whole image; the reference asks for (1, 65536) items (decode.c:50-52) */
+	{
+		std::vector<uint8_t> chunk(65536);
+		for (;;) {
+			int got = io.read_func ? io.read_func(chunk.data(), 1, (int)chunk.size(), io_arg) : 0;
+			if (got < 0) {
+				g->read_error = true;
+				break;
+			}
+			if (got == 0)
+				break;
+			g->file.insert(g->file.end(), chunk.begin(), chunk.begin() + got);
+		}
+	}
+	err = ACM_ERR_NOT_ACM; /* decode.c:783-785: every header problem */
+	if (acm_parse_header(g->file.data(), g->file.size(), force_chans, &g->hdr) < 0)
+		goto fail;
+	acm->info.channels = g->hdr.channels;
+	acm->info.rate = g->hdr.rate;
+	acm->info.acm_id = ACM_ID;
+	acm->info.acm_version = 1;
+	acm->info.acm_channels = g->hdr.acm_channels;
+	acm->info.acm_level = g->hdr.level;
+	acm->info.acm_cols = 1u << g->hdr.level;
+	acm->info.acm_rows = g->hdr.rows;
+	acm->total_values = g->hdr.total_values;
+	acm->wavc_file = g->hdr.wavc ? 1 : 0;
+	acm->block_len = g->hdr.rows << g->hdr.level;           /* decode.c:802-804 */
+	acm->wrapbuf_len = 2 * acm->info.acm_cols - 2;
+	acm->buf_start_ofs = g->hdr.header_len;
+	g->cols = acm->info.acm_cols;
+	{
+		acm_gpu_stream s;
+		memset(&s, 0, sizeof(s));
+		s.in_off = 0;
+		s.in_len = (uint32_t)g->file.size();
+		s.total_values = g->hdr.total_values;
+		s.channels = g->hdr.channels;
+		s.level = g->hdr.level;
+		s.rows = g->hdr.rows;
+		s.wavc = g->hdr.wavc;
+		err = acm_make_devstream(&s, 0, 0, &g->base);
+		if (err < 0)
+			goto fail;
+		err = ACM_ERR_OTHER;
+	}
+	g->n_attempt_total = g->base.n_attempt;
+	g->words_limit = g->base.words_limit;
+	{
+		/* look-ahead chunk: about 256 K words, 1..256 blocks */
+		uint32_t cb = 262144u / (acm->block_len ? acm->block_len : 1u);
+		g->chunk_blocks = cb < 1 ? 1 : (cb > 256 ? 256 : cb);
+	}
+	if (gpu_setup(g) < 0)
+		goto fail;
+	{
+		SavedState s0;
+		s0.block = 0;
+		s0.P = g->base.bit0;
+		g->index.push_back(std::move(s0));
+	}
+	g->consumed_P = g->base.bit0;
+	acm->gpu = g;
+	*res = acm;
+	return ACM_OK;
+fail:
+	/* decode.c:817-823: the callbacks are dropped, close_func is NOT called */
+	gpu_free(g);
+	free(acm);
+	return err;
+}
+
+extern "C" void acm_close(ACMStream *acm)
+{
+	if (!acm)
+		return; /* decode.c:880-881 */
+	if (acm->io.close_func)
+		acm->io.close_func(acm->io_arg);
+	gpu_free((GpuState *)acm->gpu);
+	free(acm);
+}
+
+/* ------------------------------------------------------------------ read */
+
+extern "C" int acm_read(ACMStream *acm, void *dst, unsigned numbytes, int bigendianp, int wordlen, int sgned)
+{
+	GpuState *g = (GpuState *)acm->gpu;
+	int numwords, avail, gotbytes;
+
+	if (wordlen < 2 || wordlen > 4)
+		return ACM_ERR_BADFMT; /* decode.c:832-835 (2 only there) */
+	numwords = (int)(numbytes / (unsigned)wordlen);
+	if (acm->stream_pos >= acm->total_values)
+		return 0; /* decode.c:837-838 */
+
+	if (!acm->block_ready) {
+		if (g->drained)
+			return 0;
+		int err = ensure_block(acm, g, g->next_block, bigendianp, wordlen, sgned);
+		if (err == 0)
+			return 0; /* EXPECTED_EOF, decode.c:842-843 */
+		if (err == ACM_ERR_UNEXPECTED_EOF)
+			g->drained = true; /* fewer bits are left than a block header needs */
+		if (err < 0)
+			return err;
+		g->cur_block = g->next_block;
+		acm->block_ready = 1;
+		acm->block_pos = 0;
+	} else if (dst) {
+		/* same block, but the cache may hold another chunk or another format by now */
+		int err = ensure_block(acm, g, g->cur_block, bigendianp, wordlen, sgned);
+		if (err <= 0)
+			return err < 0 ? err : ACM_ERR_OTHER;
+	}
+
+	/* decode.c:849-857 */
+	avail = (int)(acm->block_len - acm->block_pos);
+	if (avail < numwords)
+		numwords = avail;
+	if (acm->stream_pos + (unsigned)numwords > acm->total_values)
+		numwords = (int)(acm->total_values - acm->stream_pos);
+	if (acm->info.channels > 1)
+		numwords -= numwords % (int)acm->info.channels;
+
+	gotbytes = numwords * wordlen;
+	if (dst && numwords > 0) {
+		size_t off = ((size_t)(g->cur_block - g->c_block0) * acm->block_len + acm->block_pos) * (size_t)wordlen;
+		if (off + (size_t)gotbytes > (size_t)g->c_words * wordlen)
+			return ACM_ERR_OTHER; /* cannot happen: the block decoded and holds these words */
+		memcpy(dst, g->pcm.data() + off, (size_t)gotbytes);
+	}
+	/* decode.c:868-873 */
+	acm->stream_pos += (unsigned)numwords;
+	acm->block_pos += (unsigned)numwords;
+	if (acm->block_pos == acm->block_len) {
+		acm->block_ready = 0;
+		g->next_block = g->cur_block + 1;
+	}
+	return gotbytes;
+}
+
+/* util.c:258-277 */
+extern "C" int acm_read_loop(ACMStream *acm, void *dst, unsigned bytes, int bigendianp, int wordlen, int sgned)
+{
+	unsigned char *dstp = (unsigned char *)dst;
+	int res, got = 0;
+	while (bytes > 0) {
+		res = acm_read(acm, dstp, bytes, bigendianp, wordlen, sgned);
+		if (res > 0) {
+			if (dstp)
+				dstp += res;
+			got += res;
+			bytes -= (unsigned)res;
+		} else {
+			if (res < 0 && got == 0)
+				return res;
+			break;
+		}
+	}
+	return got;
+}
+
+/* ------------------------------------------------------------------ seek */
+
+/* util.c:214-253, with the chunk index standing in for "decode again from the start" */
+extern "C" int acm_seek_pcm(ACMStream *acm, unsigned pcm_pos)
+{
+	GpuState *g = (GpuState *)acm->gpu;
+	unsigned word_pos = pcm_pos * acm->info.channels;
+
+	if (word_pos < acm->stream_pos) {
+		if (acm->io.seek_func == NULL)
+			return ACM_ERR_NOT_SEEKABLE;
+		if (acm->io.seek_func(acm->io_arg, (int)g->hdr.header_len, SEEK_SET) < 0)
+			return ACM_ERR_NOT_SEEKABLE;
+		acm->stream_pos = 0;
+		acm->block_pos = 0;
+		acm->block_ready = 0;
+		acm->buf_start_ofs = 14; /* util.c:239 (Q12: 14 even for WAVC) */
+		g->next_block = 0;
+		g->cur_block = 0;
+		g->drained = false; /* util.c:230-234: the reader starts over */
+	}
+	while (acm->stream_pos < word_pos) {
+		int step = 2048, res;
+		/* at a block boundary, jump over whole blocks that are known to decode: to the start
+		 * of the last visited chunk at or before the target (only when blocks hold whole
+		 * frames; otherwise the read loop stalls inside block 0 anyway, Q3) */
+		if (!acm->block_ready && acm->block_len % acm->info.channels == 0) {
+			const uint32_t tb = word_pos / acm->block_len;
+			for (size_t i = g->index.size(); i-- > 0;) {
+				const SavedState &s = g->index[i];
+				if (s.block <= g->next_block)
+					break;
+				if (s.block <= tb) {
+					g->next_block = s.block;
+					acm->stream_pos = s.block * acm->block_len;
+					break;
+				}
+			}
+			if (acm->stream_pos >= word_pos)
+				break;
+		}
+		if (acm->stream_pos + (unsigned)step > word_pos)
+			step = (int)(word_pos - acm->stream_pos);
+		res = acm_read(acm, NULL, (unsigned)step * 2, 0, 2, 1);
+		if (res < 1)
+			break;
+	}
+	return (int)(acm->stream_pos / acm->info.channels);
+}
+
+static unsigned pcm2time(ACMStream *acm, unsigned long long pcm) { return (unsigned)(pcm * 1000 / acm->info.rate); }
+static unsigned time2pcm(ACMStream *acm, unsigned long long ms) { return (unsigned)(ms * acm->info.rate / 1000); }
+
+/* util.c:206-212 */
+extern "C" int acm_seek_time(ACMStream *acm, unsigned time_ms)
+{
+	int res = acm_seek_pcm(acm, time2pcm(acm, time_ms));
+	if (res <= 0)
+		return res;
+	return (int)pcm2time(acm, (unsigned)res);
+}
+
+/* ------------------------------------------------------------------ util.c getters */
+
+extern "C" const ACMInfo *acm_info(ACMStream *acm) { return &acm->info; }
+extern "C" unsigned acm_rate(ACMStream *acm) { return acm->info.rate; }
+extern "C" unsigned acm_channels(ACMStream *acm) { return acm->info.channels; }
+extern "C" int acm_seekable(ACMStream *acm) { return acm->data_len > 0; } /* util.c:152-155 */
+extern "C" unsigned acm_pcm_tell(ACMStream *acm) { return acm->stream_pos / acm->info.channels; }
+extern "C" unsigned acm_pcm_total(ACMStream *acm) { return acm->total_values / acm->info.channels; }
+extern "C" unsigned acm_time_tell(ACMStream *acm) { return pcm2time(acm, acm_pcm_tell(acm)); }
+extern "C" unsigned acm_time_total(ACMStream *acm) { return pcm2time(acm, acm_pcm_total(acm)); }
+extern "C" unsigned acm_raw_total(ACMStream *acm) { return acm->data_len; }
+
+extern "C" unsigned acm_raw_tell(ACMStream *acm)
+{
+	/* the reference reports bytes pulled into its bit accumulator, 4 at a time (decode.c:117-121);
+	 * here: the same rounding applied to the end of the decoded look-ahead */
+	GpuState *g = (GpuState *)acm->gpu;
+	unsigned long long bits = (unsigned long long)g->hdr.header_len * 8 + (g->consumed_P - g->base.bit0);
+	unsigned long long bytes = 4 * ((bits + 31) / 32);
+	unsigned long long cap = (unsigned long long)g->file.size() + 1;
+	return (unsigned)(bytes < cap ? bytes : cap);
+}
+
+/* util.c:157-170 */
+extern "C" unsigned acm_bitrate(ACMStream *acm)
+{
+	unsigned long long bits, time, bitrate = 0;
+	if (acm_raw_total(acm) == 0)
+		return 13000;
+	time = acm_time_total(acm);
+	if (time > 0) {
+		bits = 8ull * acm_raw_total(acm);
+		bitrate = 1000 * bits / time;
+	}
+	return (unsigned)bitrate;
+}
+
+/* util.c:34-52 */
+extern "C" const char *acm_strerror(int err)
+{
+	static const char *const msgs[] = { "No error", "ACM error", "Cannot open file", "Not an ACM file",
+					    "Read error", "Bad format", "Corrupt file", "Unexcpected EOF",
+					    "Stream not seekable" };
+	const int n = (int)(sizeof(msgs) / sizeof(msgs[0]));
+	if (-err < 0 || -err >= n)
+		return "Unknown error";
+	return msgs[-err];
+}
+
+/* ------------------------------------------------------------------ stdio front end (util.c:58-115) */
+
+static int file_read(void *ptr, int size, int n, void *arg) { return (int)fread(ptr, (size_t)size, (size_t)n, (FILE *)arg); }
+static int file_close(void *arg) { return fclose((FILE *)arg); }
+static int file_seek(void *arg, int offset, int whence) { return fseek((FILE *)arg, offset, whence); }
+static int file_length(void *arg)
+{
+	FILE *f = (FILE *)arg;
+	long pos = ftell(f), len = -1;
+	if (pos < 0)
+		return -1;
+	if (fseek(f, 0, SEEK_END) >= 0) {
+		len = ftell(f);
+		fseek(f, pos, SEEK_SET);
+	}
+	return (int)len;
+}
+
+extern "C" int acm_open_file(ACMStream **res, const char *filename, int force_chans)
+{
+	acm_io_callbacks io;
+	ACMStream *acm = NULL;
+	FILE *f = fopen(filename, "rb");
+	int err;
+	if (!f)
+		return ACM_ERR_OPEN;
+	memset(&io, 0, sizeof(io));
+	io.read_func = file_read;
+	io.seek_func = file_seek;
+	io.close_func = file_close;
+	io.get_length_func = file_length;
+	if ((err = acm_open_decoder(&acm, f, io, force_chans)) < 0) {
+		fclose(f); /* a failed open leaves the data source with the caller (util.c:109-111) */
+		return err;
+	}
+	*res = acm;
+	return ACM_OK;
+}

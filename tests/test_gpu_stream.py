@@ -1,0 +1,194 @@
+"""GPU tier: the libacm.h drop-in surface (acm_open_decoder / acm_read / acm_read_loop / acm_seek_pcm /
+getters / acm_close) against the UNMODIFIED reference, call by call, through the same C harness
+(BASELINE config 5 scaled to test size)."""
+import numpy as np
+import pytest
+
+from libacm_b200 import gen
+from tests import api_driver as ad
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ad.have_ref(), reason="oracle/_ref not built")]
+
+STREAMS = {
+    "l7r16_stereo_44k": dict(level=7, rows=16, channels=2, rate=44100, total_values=2048 * 300 + 1001, seed=1),
+    "l10r2_stereo": dict(level=10, rows=2, channels=2, rate=44100, total_values=2048 * 40 + 7, seed=2,
+                         dist=gen.DIST_STRESS),
+    "l5r7_mono_wavc": dict(level=5, rows=7, channels=1, rate=22050, total_values=224 * 90 + 13, seed=3,
+                           dist=gen.DIST_STRESS, wavc=1),
+    "l0r5_stereo_stall": dict(level=0, rows=5, channels=2, rate=8000, total_values=333, seed=4, dist=gen.DIST_STRESS),
+}
+
+
+@pytest.fixture(scope="module")
+def libs():
+    return ad.mine(), ad.ref()
+
+
+def _pair(libs, img, **kw):
+    return ad.Handle(libs[0], img, **kw), ad.Handle(libs[1], img, **kw)
+
+
+@pytest.mark.parametrize("name", sorted(STREAMS))
+def test_open_state_and_getters(libs, name):
+    img = gen.make_stream(**STREAMS[name])
+    for fc in (-1, 0, 1, 2, 3):
+        a, b = _pair(libs, img, force_chans=fc)
+        assert a.err == b.err == 0
+        assert a.state() == b.state()
+        assert a.getters() == b.getters()
+        a.close(), b.close()
+
+
+@pytest.mark.parametrize("name", sorted(STREAMS))
+@pytest.mark.parametrize("bufsize", [64, 1024, 4096])
+def test_sequential_reads_small_buffers(libs, name, bufsize):
+    img = gen.make_stream(**STREAMS[name])
+    a, b = _pair(libs, img)
+    n = 0
+    while True:
+        ra, da = a.read(bufsize)
+        rb, db = b.read(bufsize)
+        assert ra == rb, (n, ra, rb)
+        assert da == db, n
+        assert a.state()["stream_pos"] == b.state()["stream_pos"]
+        assert a.state()["block_pos"] == b.state()["block_pos"]
+        n += 1
+        if ra <= 0:
+            break
+    assert a.getters()["pcm_tell"] == b.getters()["pcm_tell"]
+    a.close(), b.close()
+
+
+@pytest.mark.parametrize("fmt", [(0, 1), (1, 1), (0, 0), (1, 0)])
+def test_read_loop_formats(libs, fmt):
+    be, sg = fmt
+    img = gen.make_stream(**STREAMS["l7r16_stereo_44k"])
+    a, b = _pair(libs, img)
+    while True:
+        ra, da = a.read(50_000, be=be, sgned=sg, loop=True)
+        rb, db = b.read(50_000, be=be, sgned=sg, loop=True)
+        assert ra == rb and da == db
+        if ra <= 0:
+            break
+    a.close(), b.close()
+
+
+def test_format_switch_mid_stream(libs):
+    img = gen.make_stream(**STREAMS["l5r7_mono_wavc"])
+    a, b = _pair(libs, img)
+    for k in range(40):
+        be, sg = k & 1, (k >> 1) & 1
+        ra, da = a.read(700, be=be, sgned=sg)
+        rb, db = b.read(700, be=be, sgned=sg)
+        assert ra == rb and da == db
+    a.close(), b.close()
+
+
+@pytest.mark.parametrize("name", ["l7r16_stereo_44k", "l10r2_stereo", "l5r7_mono_wavc"])
+def test_seek_pcm_forward_backward(libs, name):
+    img = gen.make_stream(**STREAMS[name])
+    a, b = _pair(libs, img)
+    total = b.getters()["pcm_total"]
+    targets = [0, 5, total // 3, total // 2, total - 1, total, total + 100, total // 2, 5, total // 3 + 1, 0]
+    for t in targets:
+        ra, rb = a.seek(t), b.seek(t)
+        assert ra == rb, (t, ra, rb)
+        assert a.state()["stream_pos"] == b.state()["stream_pos"]
+        assert a.state()["block_pos"] == b.state()["block_pos"]
+        assert a.getters()["pcm_tell"] == b.getters()["pcm_tell"]
+        assert a.getters()["time_tell"] == b.getters()["time_tell"]
+        x, y = a.read(3000, loop=True), b.read(3000, loop=True)
+        assert x == y, t
+        assert a.counts()[0] == b.counts()[0]  # same number of seek_func calls (Q11)
+    ra, rb = a.seek_time(1234), b.seek_time(1234)
+    assert ra == rb
+    assert a.read(512) == b.read(512)
+    a.close(), b.close()
+
+
+def test_backward_seek_without_seek_func(libs):
+    img = gen.make_stream(**STREAMS["l5r7_mono_wavc"])
+    a, b = _pair(libs, img, with_seek=0)
+    assert a.read(5000, loop=True) == b.read(5000, loop=True)
+    assert a.seek(10) == b.seek(10) == -8          # ACM_ERR_NOT_SEEKABLE
+    fwd = b.getters()["pcm_tell"] + 1000
+    assert a.seek(fwd) == b.seek(fwd)              # forward seeking always works
+    assert a.read(999) == b.read(999)
+    a.close(), b.close()
+
+
+def test_unseekable_source_and_short_reads(libs):
+    """get_length_func absent -> acm_seekable 0, bitrate fallback 13000 (Q11, Q13); 7-byte read chunks"""
+    img = gen.make_stream(**STREAMS["l5r7_mono_wavc"])
+    a, b = _pair(libs, img, seekable=0, chunk=7)
+    assert a.getters() == b.getters()
+    assert b.getters()["seekable"] == 0 and b.getters()["bitrate"] == 13000
+    assert a.read(30_000, loop=True) == b.read(30_000, loop=True)
+    a.close(), b.close()
+
+
+def test_open_failures_leave_data_source_open(libs):
+    img = gen.make_stream(**STREAMS["l5r7_mono_wavc"])
+    for bad in (b"", img[:5], img[:41], b"RIFF" + img[4:], img[:28] + b"\x00" * 40):
+        a, b = _pair(libs, bad)
+        assert a.err == b.err
+        if b.err < 0:
+            assert a.h is None and b.h is None
+            assert a.closed_on_fail == b.closed_on_fail == 0   # Q10
+        else:
+            a.close(), b.close()
+
+
+def test_truncated_stream_first_error_matches(libs):
+    """Every truncation: identical data, identical FIRST end-of-stream / error code.  What the
+    reference does after ACM_ERR_CORRUPT is undefined (it re-enters decode_block mid-stream, Q17:
+    parity unpinned); after EOF / UNEXPECTED_EOF it keeps returning 0 and so must we."""
+    img = gen.make_stream(**STREAMS["l7r16_stereo_44k"])
+    seen = set()
+    for cut in (len(img) // 2, len(img) // 2 + 1, len(img) - 3, 14 + 3, 14 + 700, 14 + 701, 14 + 2000, 4000, 4001):
+        a, b = _pair(libs, img[:cut])
+        assert a.err == b.err == 0
+        while True:
+            x, y = a.read(8192), b.read(8192)
+            assert x == y, cut
+            if x[0] <= 0:
+                break
+        seen.add(x[0])
+        if x[0] != -6:
+            assert a.read(8192)[0] == b.read(8192)[0] == 0, cut
+        assert a.state()["stream_pos"] == b.state()["stream_pos"]
+        a.close(), b.close()
+    assert -7 in seen
+
+
+def test_tiny_requests_and_badfmt(libs):
+    img = gen.make_stream(**STREAMS["l7r16_stereo_44k"])
+    a, b = _pair(libs, img)
+    assert a.read(2) == b.read(2) == (0, b"")      # Q3: less than one stereo frame
+    assert a.read(3) == b.read(3)
+    assert a.read(4) == b.read(4)
+    assert a.read(16, wordlen=1)[0] == b.read(16, wordlen=1)[0] == -5
+    assert b.read(16, wordlen=4)[0] == -5          # the reference only knows wordlen 2
+    r, d = a.read(16, wordlen=4)                   # extension: same samples, 32-bit
+    assert r == 16
+    a.close(), b.close()
+
+
+def test_open_file_and_strerror(libs, tmp_path):
+    import ctypes as C
+    img = gen.make_stream(**STREAMS["l5r7_mono_wavc"])
+    p = tmp_path / "x.acm"
+    p.write_bytes(img)
+    outs = []
+    for lib in libs:
+        L = lib.lib
+        s = C.POINTER(ad.ACMStream)()
+        assert L.acm_open_file(C.byref(s), str(p).encode(), 0) == 0
+        buf = np.zeros(20000, np.uint8)
+        n = L.acm_read_loop(s, buf.ctypes.data, 20000, 0, 2, 1)
+        outs.append((n, bytes(buf[:n]), L.acm_pcm_total(s), L.acm_raw_total(s), L.acm_seekable(s)))
+        assert L.acm_seek_pcm(s, 3) == 3
+        L.acm_close(s)
+        assert L.acm_open_file(C.byref(s), b"/nonexistent/file.acm", 0) == -2
+        outs.append(tuple(L.acm_strerror(e) for e in range(1, -11, -1)))
+    assert outs[0] == outs[2] and outs[1] == outs[3]
