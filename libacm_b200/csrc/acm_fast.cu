@@ -113,15 +113,20 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
 /* ------------------------------------------------------------------ bit readers */
 
 /*
- * Scan-lane reader: a three-word register window (w0,w1 = the words under the read
- * position, w2 = the next one, already loaded) over the stream in global memory.  The
- * EOF rule -- file bits, then one zero byte, then nothing (decode.c:57-61) -- only costs
- * a compare on the refill path: words below fe_word are loaded as they are.
+ * Scan-lane reader: a 96-bit shift register (lo, mid, hi) over the stream in global
+ * memory.  `lo` always holds the next 32 stream bits, so a table lookup needs no funnel
+ * shift by the bit position; consuming `step` <= 32 bits is three funnel shifts, only the
+ * first of which (lo) is on the walk's dependent chain.  At least 64 bits are valid at
+ * the top of every iteration; when fewer remain the word fetched ONE refill earlier (nw)
+ * is spliced in above them and the next word is requested, so the load latency never
+ * reaches the chain.  The EOF rule -- file bits, then one zero byte, then nothing
+ * (decode.c:57-61) -- only exists in the CAREFUL variant of the refill.
  */
 struct ScanReader {
 	const uint32_t *base; /* stream base (16-byte aligned) */
 	uint32_t fe_word, fe_tail;
-	uint32_t widx, w0, w1, w2;
+	uint32_t lo, mid, hi, avail; /* bits [0, avail) of hi:mid:lo are the stream at the read position */
+	uint32_t nw, widx;           /* nw = word `widx`, the next one to splice in */
 
 	__device__ __forceinline__ uint32_t ld(uint32_t i) const
 	{
@@ -135,40 +140,57 @@ struct ScanReader {
 	{
 		base = nullptr;
 		fe_word = fe_tail = 0;
-		widx = w0 = w1 = w2 = 0;
+		lo = mid = hi = nw = widx = 0;
+		avail = 96;
+	}
+	/* position the window on bit P */
+	__device__ __forceinline__ void seek(uint32_t P)
+	{
+		const uint32_t i = P >> 5, sh = P & 31u;
+		const uint32_t a = ld(i), b = ld(i + 1), c = ld(i + 2);
+		lo = __funnelshift_r(a, b, sh);
+		mid = __funnelshift_r(b, c, sh);
+		hi = c >> sh;
+		avail = 96u - sh;
+		widx = i + 3;
+		nw = ld(widx);
+		prefetch_l1(base + i + 32);
 	}
 	__device__ __forceinline__ void start(const uint8_t *src, uint32_t file_end, uint32_t P0)
 	{
 		base = reinterpret_cast<const uint32_t *>(src);
 		fe_word = file_end >> 5;
 		fe_tail = file_end & 31u;
-		widx = P0 >> 5;
-		w0 = ld(widx);
-		w1 = ld(widx + 1);
-		w2 = ld(widx + 2);
-		prefetch_l1(base + widx + 32);
+		seek(P0);
 	}
-	/* reposition the window on P; must follow every change of the read position */
-	__device__ __forceinline__ void advance(uint32_t P)
+	__device__ __forceinline__ uint32_t peek() const { return lo; }
+	/* consume step <= 32 bits */
+	template <bool CAREFUL>
+	__device__ __forceinline__ void consume(uint32_t step)
 	{
-		const uint32_t i = P >> 5;
-		if (i != widx) {
-			if (i == widx + 1) {
-				w0 = w1;
-				w1 = w2;
-			} else {
-				w0 = ld(i);
-				w1 = ld(i + 1);
-			}
-			w2 = ld(i + 2);
-			if ((i >> 5) != (widx >> 5))
-				prefetch_l1(base + i + 32); /* next 128-byte line */
-			widx = i;
+		lo = __funnelshift_rc(lo, mid, step);
+		mid = __funnelshift_rc(mid, hi, step);
+		hi = __funnelshift_rc(hi, 0u, step);
+		avail -= step;
+		const bool refill = avail <= 64u; /* then avail is in (32, 64] and hi holds nothing */
+		const unsigned long long t = (unsigned long long)nw << ((avail - 32u) & 63u);
+		mid = refill ? (mid | (uint32_t)t) : mid;
+		hi = refill ? (uint32_t)(t >> 32) : hi;
+		avail = refill ? avail + 32u : avail;
+		widx = refill ? widx + 1u : widx;
+		if (CAREFUL) {
+			if (refill)
+				nw = ld(widx);
+		} else {
+			/* predicated load straight into nw: nothing waits for it until the next refill */
+			asm volatile("{\n\t.reg .pred p;\n\t"
+				     "setp.ne.u32 p, %1, 0;\n\t"
+				     "@p ld.global.nc.u32 %0, [%2];\n\t}"
+				     : "+r"(nw)
+				     : "r"((uint32_t)refill), "l"(base + widx));
 		}
-	}
-	__device__ __forceinline__ uint32_t peek(uint32_t P) const
-	{
-		return __funnelshift_r(w0, w1, P & 31u);
+		if (refill && (widx & 31u) == 0u)
+			prefetch_l1(base + widx + 32); /* next 128-byte line */
 	}
 };
 
@@ -210,72 +232,144 @@ __device__ __forceinline__ uint32_t make_info(uint32_t kind)
 
 /*
  * Flat walk over one block for every lane of a scan warp at once (replaces the
- * per-column loop nest of scan_block for this shape; same verdicts).  Each iteration a
- * lane is either AT A SELECTOR (rem == 0: one sel13 lookup gives the whole advance of a
- * fixed-size column, or the selector plus the first prefix-code step and its table) or
- * INSIDE a prefix-coded column (one kstep lookup).  The body is written with selects
- * instead of branches and the loop condition is a warp vote, so the 32 lanes execute
- * ONE instruction stream however their column types differ
- * (profiles/r01_ncu_v2_v3_summary.md).
+ * per-column loop nest of scan_block for this shape; same verdicts).  Per iteration a
+ * lane is in one of three states:
+ *   at a selector (rem == 0, pend == 0): one sel13 lookup gives the whole advance of a
+ *       fixed-size column, or the selector plus the first prefix-code step and its table;
+ *   inside a prefix-coded column (rem rows to come): one kstep lookup (row cap folded in);
+ *   inside a fixed-size payload (pend bits to come): skip, at most 32 bits per iteration
+ *       (the shift-register window consumes at most one word per step).
+ * The loop condition is a warp vote and the body is straight-line code, so the 32 lanes
+ * execute ONE instruction stream however their column types differ.  It runs twice:
+ *   HOT     no end-of-file logic at all, unmasked loads; legal while the lane is at least
+ *           512 bits away from the end of its file (a step is <= 32 bits and the window
+ *           reads at most 160 bits ahead).  A bad selector only raises a flag.
+ *   CAREFUL masked loads and the reference's EOF / corruption checks: the last few dozen
+ *           steps of a stream, and (from the block start) any block whose hot pass saw a
+ *           bad selector.
+ * profiles/r01_ncu_v4_summary.md has the measurements that led here.
  */
-__device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P, uint32_t limit,
-						      uint16_t *coloff, const uint16_t *sel13,
-						      const uint8_t *kstep, bool active)
+struct ScanState {
+	uint32_t P, rem, pend, col, kbase;
+	int status;
+	bool done, bad;
+};
+
+__device__ __forceinline__ void scan_pass_hot(ScanReader &br, ScanState &s, uint32_t hot_end, uint16_t *&cp,
+					      uint32_t pblock, const uint16_t *sel13, const uint8_t *kstep)
 {
-	const uint32_t pblock = P;
-	ScanResult s;
+	bool run = !s.done && s.P < hot_end;
+	while (__any_sync(0xFFFFFFFFu, run)) {
+		/* lanes that are not running execute the same instructions on dead state: every
+		 * update below is guarded by `run`, and their loads stay inside the tables */
+		const uint32_t w = br.peek();
+		const bool at_sel = (s.rem | s.pend) == 0u;
+		const uint32_t es = sel13[w & 0x1FFFu];
+		const uint32_t ek = kstep[s.kbase + umin32(s.rem, 7u) * 256u + (w & 255u)];
+		const uint32_t adv_s = es & 511u, hi7 = es >> 9, rem_s = hi7 & 15u;
+		const bool sel = run && at_sel;
+		s.bad = s.bad || (sel && hi7 == 0x70u);
+		if (sel)
+			*cp = (uint16_t)(s.P - pblock);
+		cp = sel ? cp + OFF_PITCH : cp;
+		s.col = sel ? s.col + 1u : s.col;
+		s.kbase = sel ? (es >> 13) * 2048u : s.kbase;
+		const bool is_k = at_sel ? rem_s != 0u : s.rem != 0u;
+		const uint32_t tot = at_sel ? adv_s : s.pend;
+		uint32_t step = is_k ? (at_sel ? adv_s : (ek & 15u)) : umin32(tot, 32u);
+		step = run ? step : 0u;
+		s.pend = run ? (is_k ? 0u : tot - step) : s.pend;
+		s.rem = run ? (at_sel ? rem_s : s.rem - (ek >> 4)) : s.rem; /* kstep[.][0][.] = 0 */
+		s.P += step;
+		br.consume<false>(step);
+		const bool fin = (s.rem | s.pend) == 0u && s.col == (uint32_t)COLS;
+		s.done = s.done || (run && fin);
+		run = run && !fin && s.P < hot_end;
+	}
+}
+
+__device__ __forceinline__ void scan_pass_careful(ScanReader &br, ScanState &s, uint32_t limit, uint16_t *&cp,
+						  uint32_t pblock, const uint16_t *sel13, const uint8_t *kstep)
+{
+	while (!s.done) {
+		const uint32_t w = br.peek();
+		const bool at_sel = (s.rem | s.pend) == 0u;
+		const uint32_t es = sel13[w & 0x1FFFu];
+		const uint32_t ek = kstep[s.kbase + umin32(s.rem, 7u) * 256u + (w & 255u)];
+		const uint32_t adv_s = es & 511u, hi7 = es >> 9, rem_s = hi7 & 15u;
+		if (at_sel) {
+			if (s.P + 5u > limit) { /* GET_BITS_EXPECT_EOF decode.c:496 */
+				s.status = SCAN_EOF;
+				break;
+			}
+			*cp = (uint16_t)(s.P - pblock);
+			if (hi7 == 0x70u) { /* f_bad decode.c:190-194 */
+				s.status = -6;
+				break;
+			}
+			cp += OFF_PITCH;
+			s.col++;
+			s.kbase = (es >> 13) * 2048u;
+		}
+		const bool is_k = at_sel ? rem_s != 0u : s.rem != 0u;
+		const uint32_t tot = at_sel ? adv_s : s.pend;
+		const uint32_t step = is_k ? (at_sel ? adv_s : (ek & 15u)) : umin32(tot, 32u);
+		s.pend = is_k ? 0u : tot - step;
+		s.rem = at_sel ? rem_s : s.rem - (ek >> 4);
+		s.P += step;
+		br.consume<true>(step);
+		if ((s.rem | s.pend) == 0u) {
+			if (s.P > limit) { /* a GET_BITS inside the payload ran dry: decode.c:146-152 */
+				s.status = -7;
+				s.col--; /* the selector was consumed, the payload did not complete */
+				break;
+			}
+			if (s.col == (uint32_t)COLS)
+				break;
+		}
+	}
+	s.done = true;
+}
+
+__device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P, uint32_t limit,
+						      uint32_t hot_end, uint16_t *coloff,
+						      const uint16_t *sel13, const uint8_t *kstep, bool active)
+{
+	ScanState s;
+	ScanResult r;
+	uint16_t *cp = coloff;
+	s.P = P;
+	s.rem = s.pend = s.col = s.kbase = 0;
 	s.status = SCAN_OK;
-	s.ncols = 0;
-	s.val = 0;
-	bool done = !active;
-	uint32_t col = 0, rem = 0, kbase = 0;
-	if (!done) {
+	s.done = !active;
+	s.bad = false;
+	r.val = 0;
+	if (active) {
 		if (P + 20 > limit) { /* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
 			s.status = SCAN_EOF;
-			done = true;
+			s.done = true;
 		} else {
-			s.val = (int)((br.peek(P) >> 4) & 0xFFFFu);
-			P += 20;
-			br.advance(P);
+			r.val = (int)((br.peek() >> 4) & 0xFFFFu);
+			s.P = P + 20;
+			br.consume<true>(20u);
 		}
 	}
-	while (__any_sync(0xFFFFFFFFu, !done)) {
-		if (!done) {
-			const uint32_t w = br.peek(P);
-			const bool at_sel = rem == 0;
-			const uint32_t es = sel13[w & 0x1FFFu];
-			const uint32_t ek = kstep[kbase + umin32(rem, 7u) * 256u + (w & 255u)];
-			/* selector: GET_BITS_EXPECT_EOF decode.c:496; f_bad decode.c:190-194 */
-			const bool sel_eof = at_sel && (P + 5u > limit);
-			const bool sel_bad = at_sel && (es & 511u) == 0u;
-			if (at_sel && !sel_eof)
-				coloff[col * OFF_PITCH] = (uint16_t)(P - pblock);
-			const uint32_t ks = (es >> 9) & 7u;
-			if (at_sel)
-				kbase = ((es >> 12) & 7u) * 2048u;
-			P += at_sel ? (es & 511u) : (ek & 15u);
-			rem = at_sel ? (ks ? (uint32_t)ROWS - ks : 0u) : rem - (ek >> 4);
-			br.advance(P);
-			if (sel_eof) {
-				s.status = SCAN_EOF;
-				done = true;
-			} else if (sel_bad) {
-				s.status = -6;
-				done = true;
-			} else if (rem == 0u) {
-				if (P > limit) { /* a GET_BITS inside the payload ran dry: decode.c:146-152 */
-					s.status = -7;
-					done = true;
-				} else {
-					col++;
-					done = col == (uint32_t)COLS;
-				}
-			}
+	scan_pass_hot(br, s, hot_end, cp, P, sel13, kstep);
+	if (active && s.status == SCAN_OK && (!s.done || s.bad)) {
+		if (s.bad) {
+			/* redo the whole block with the reference's checks, from just after its header */
+			s.P = P + 20;
+			s.rem = s.pend = s.col = s.kbase = 0;
+			s.done = false;
+			cp = coloff;
+			br.seek(s.P);
 		}
+		scan_pass_careful(br, s, limit, cp, P, sel13, kstep);
 	}
-	s.ncols = col;
-	s.end = P;
-	return s;
+	r.status = s.status;
+	r.ncols = s.col;
+	r.end = s.P;
+	return r;
 }
 
 /* ------------------------------------------------------------------ unpack */
@@ -551,7 +645,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 	const bool is_scan = warp >= W;
 	const int myslot = is_scan ? 32 * (warp - W) + lane : 0;
 	bool active = false;
-	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0;
+	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, hot_end = 0;
 	ScanReader sbr;
 	sbr.reset();
 	uint32_t *const cta_hist = a.hist + (size_t)blockIdx.x * S * HIST_WORDS;
@@ -575,6 +669,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					P = d.bit0;
 					blk = 0;
 					limit = d.file_end + 8u;
+					hot_end = d.file_end > 512u ? d.file_end - 512u : 0u;
 					n_attempt = d.n_attempt;
 					sbr.start(a.blob + d.base_off, d.file_end, P);
 					active = true;
@@ -596,8 +691,8 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 				}
 			}
 			{
-				ScanResult sc = scan_block_flat(sbr, P, limit, sm.coloff[buf] + myslot, sm.sel13,
-								sm.kstep, walk);
+				ScanResult sc = scan_block_flat(sbr, P, limit, hot_end, sm.coloff[buf] + myslot,
+								sm.sel13, sm.kstep, walk);
 				if (walk) {
 					e.status = sc.status;
 					e.ncols = sc.ncols;

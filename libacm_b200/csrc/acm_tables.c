@@ -126,10 +126,10 @@ void acm_tables_build(acm_tables *t)
 		unsigned ind = b & 31u, sym = (b >> 5) & 255u, k = t->kind[ind], cls = k & 7u, sub = k >> 3;
 		unsigned v;
 		if (cls == ACM_CLS_BAD) {
-			v = 0u;
+			v = 5u | (7u << 13); /* rows-to-come 0 with table 7: no valid entry looks like this */
 		} else if (cls == ACM_CLS_K) {
 			unsigned e = (unsigned)t->k8[sub * 256 + sym], nv = e & 15u;
-			v = (5u + ((e >> (4 * nv)) & 15u)) | (nv << 9) | (sub << 12); /* nv in 1..7 < 16 rows */
+			v = (5u + ((e >> (4 * nv)) & 15u)) | ((16u - nv) << 9) | (sub << 13); /* nv in 1..7 */
 		} else if (cls == ACM_CLS_LINEAR) {
 			v = 5u + 16u * ind;
 		} else if (cls == ACM_CLS_T) {

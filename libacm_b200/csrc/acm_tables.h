@@ -21,11 +21,11 @@
  *   sel13_r16[w]  scan-only, for the 16-row block shape: w = the 13 stream bits at a column
  *               boundary (5-bit selector + first 8 payload bits).  16-bit entry:
  *                 bits 0..8    bits to advance: 5 + the whole payload of a fixed-size filler
- *                              (zero, linear, t15/t27/t37), or 5 + the first k8 step;
- *                              0 marks a bad selector (f_bad, decode.c:190-194)
- *                 bits 9..11   values that first k8 step produced; non-zero exactly for the
- *                              prefix-coded fillers (more steps follow while rows remain)
- *                 bits 12..14  k8 table number of that filler
+ *                              (zero, linear, t15/t27/t37), or 5 + the first k8 step
+ *                 bits 9..12   rows still to come after that first step; non-zero exactly for
+ *                              the prefix-coded fillers (a step yields at most 7 of 16 rows)
+ *                 bits 13..15  k8 table number of that filler; a bad selector (f_bad,
+ *                              decode.c:190-194) is entry >> 9 == 0x70 (table 7, no rows)
  *   kstep[kt][m][b]  scan-only: one prefix-code step with m = min(rows remaining, 7) and b = the
  *               next 8 stream bits.  8-bit entry: bits 0..3 bits consumed, bits 4..6 values
  *               produced (k8's nv and cum with the row cap already applied).
