@@ -10,12 +10,15 @@
  *    CTA) as a flat, divergence-free state machine: every iteration each lane either
  *    reads a column selector (and, for prefix codes, the first table step out of the
  *    same 32-bit peek, via the 13-bit sel13 table) or takes one more multi-symbol table
- *    step (kstep table, row cap folded in).  Each lane reads its stream straight from
- *    global memory through a three-word register window: the 128-byte line it is in is
- *    L1 resident, the next line is prefetched, and the refill is a handful of predicated
- *    instructions.  (A per-lane TMA ring in shared memory was tried first: every ring
- *    refill is a single-lane slow path with a proxy fence and an mbarrier wait that
- *    stalls the other 31 lanes -- profiles/r01_ncu_v4_summary.md.)  The walk is a
+ *    step (kstep table, row cap folded in).  Each lane sees its stream through a 96-bit
+ *    shift register fed from a private 256-byte shared-memory ring; the ring is topped up
+ *    by all lanes AT THE SAME TIME every 8 iterations with 128-bit global loads whose data
+ *    is only stored to the ring at the following top-up, so no instruction of the walk
+ *    ever waits on global memory (register scoreboards are per warp: with 32 independent
+ *    streams, any load issued at a lane-specific moment stalls all lanes -- a TMA ring
+ *    with per-lane mbarriers and a register look-ahead were both tried and measured,
+ *    profiles/r01_ncu_v4_summary.md, r01_ncu_v7_summary.md).  The EOF rule (one zero byte,
+ *    decode.c:57-61) is applied while storing to the ring.  The walk is a
  *    dependent chain (~450 steps per block), so a CTA runs TWO scan warps = 64 stream
  *    slots to cover the latency with streams.  The 128 column offsets of each block are
  *    published through shared memory.
@@ -64,6 +67,9 @@ constexpr int XWORDS = XPRE + BLEN + 4 * 32; /* transpose layout: 4 pad words pe
 constexpr int X0_WORDS = BLEN / 2;       /* int16 indices */
 constexpr int STAGE_BYTES = (BLEN + 4 * 32 - X0_WORDS) * 4; /* 4608: a whole block (<= 4179 B) + slack */
 constexpr int STAGE_CHUNKS = STAGE_BYTES / 16;
+constexpr int RING_WORDS = 64;           /* 16 chunks of 16 bytes per scan lane */
+constexpr int RING_LEAD = 8;             /* chunks kept ahead of the read position */
+constexpr int SCAN_PERIOD = 8;           /* walk iterations between two ring top-ups */
 constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [128,192) X2 tail [192,256) */
 
 enum { ENT_IDLE = -100 };
@@ -84,6 +90,7 @@ struct Smem {
 	uint16_t sel13[8192];
 	uint8_t kstep[8 * 8 * 256];
 	uint32_t x[W][XWORDS];       /* per worker: chunk -1 | int16 X0 + staged bytes, later transposed X2 */
+	uint32_t ring[S][RING_WORDS]; /* per scan lane: compressed window */
 	uint16_t coloff[2][COLS * OFF_PITCH];
 	Entry ent[2][S];
 	unsigned long long cks[S];
@@ -113,84 +120,116 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
 /* ------------------------------------------------------------------ bit readers */
 
 /*
- * Scan-lane reader: a 96-bit shift register (lo, mid, hi) over the stream in global
- * memory.  `lo` always holds the next 32 stream bits, so a table lookup needs no funnel
+ * Scan-lane reader: a 96-bit shift register (lo, mid, hi) over a private shared-memory
+ * ring.  `lo` always holds the next 32 stream bits, so a table lookup needs no funnel
  * shift by the bit position; consuming `step` <= 32 bits is three funnel shifts, only the
  * first of which (lo) is on the walk's dependent chain.  At least 64 bits are valid at
- * the top of every iteration; when fewer remain the word fetched ONE refill earlier (nw)
- * is spliced in above them and the next word is requested, so the load latency never
- * reaches the chain.  The EOF rule -- file bits, then one zero byte, then nothing
- * (decode.c:57-61) -- only exists in the CAREFUL variant of the refill.
+ * the top of every iteration; when fewer remain, ring word `widx` (read unconditionally
+ * at the top of the iteration, next to the table lookups) is spliced in above them.
+ *
+ * topup() runs for all lanes together every SCAN_PERIOD iterations: it stores the (at most
+ * two) 16-byte chunks requested by the previous top-up into the ring -- zeroing everything
+ * at and past the end of the file, which is the reference's "one zero byte, then nothing"
+ * (decode.c:57-61) -- and requests the next ones so that RING_LEAD chunks stay ahead of
+ * the read position.  SCAN_PERIOD iterations consume at most 32 bytes = the two chunks a
+ * top-up can add, so the ring never runs dry and nothing ever waits on a load.
  */
 struct ScanReader {
-	const uint32_t *base; /* stream base (16-byte aligned) */
+	const uint4 *base16;  /* stream base (16-byte aligned) */
+	uint32_t room16;      /* 16-byte chunks readable at base16 */
 	uint32_t fe_word, fe_tail;
+	uint32_t *ring;       /* this lane's RING_WORDS words of shared memory */
 	uint32_t lo, mid, hi, avail; /* bits [0, avail) of hi:mid:lo are the stream at the read position */
-	uint32_t nw, widx;           /* nw = word `widx`, the next one to splice in */
+	uint32_t widx;        /* stream word that will be spliced in next */
+	uint32_t fill;        /* chunks stored so far = index of the next chunk to store */
+	uint32_t npend;       /* chunks requested at the last top-up (0..2) */
+	uint4 pa, pb;
 
-	__device__ __forceinline__ uint32_t ld(uint32_t i) const
+	__device__ __forceinline__ uint4 load_chunk(uint32_t c) const
 	{
-		if (i < fe_word)
-			return __ldg(base + i);
-		if (i == fe_word && fe_tail)
-			return __ldg(base + i) & ((1u << fe_tail) - 1u);
-		return 0u;
+		uint4 v = make_uint4(0u, 0u, 0u, 0u);
+		if (c < room16)
+			v = ldg_nc_v4(base16 + c);
+		return v;
 	}
-	__device__ __forceinline__ void reset()
+	__device__ __forceinline__ void store_chunk(uint32_t c, uint4 v)
 	{
-		base = nullptr;
+		if (4u * c + 3u >= fe_word) { /* touches the end of the file: rare */
+			uint32_t q[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const uint32_t k = 4u * c + j;
+				if (k > fe_word || (k == fe_word && !fe_tail))
+					q[j] = 0u;
+				else if (k == fe_word)
+					q[j] &= (1u << fe_tail) - 1u;
+			}
+			v = make_uint4(q[0], q[1], q[2], q[3]);
+		}
+		reinterpret_cast<uint4 *>(ring)[c & (RING_WORDS / 4 - 1)] = v;
+	}
+	__device__ __forceinline__ void reset(uint32_t *r)
+	{
+		ring = r;
+		base16 = nullptr;
+		room16 = 0;
 		fe_word = fe_tail = 0;
-		lo = mid = hi = nw = widx = 0;
+		lo = mid = hi = widx = 0;
 		avail = 96;
+		fill = 0x40000000u; /* never asks for data */
+		npend = 0;
+		pa = pb = make_uint4(0u, 0u, 0u, 0u);
 	}
-	/* position the window on bit P */
-	__device__ __forceinline__ void seek(uint32_t P)
+	/* new stream: fill the ring synchronously once, position the window on bit P0 */
+	__device__ __forceinline__ void start(const uint8_t *src, uint64_t room, uint32_t file_end, uint32_t P0)
 	{
-		const uint32_t i = P >> 5, sh = P & 31u;
-		const uint32_t a = ld(i), b = ld(i + 1), c = ld(i + 2);
+		base16 = reinterpret_cast<const uint4 *>(src);
+		room16 = (uint32_t)(room >> 4);
+		fe_word = file_end >> 5;
+		fe_tail = file_end & 31u;
+		const uint32_t i = P0 >> 5, sh = P0 & 31u, c0 = i >> 2;
+#pragma unroll
+		for (int j = 0; j < RING_LEAD; j++)
+			store_chunk(c0 + j, load_chunk(c0 + j));
+		fill = c0 + RING_LEAD;
+		npend = 0;
+		const uint32_t a = ring[i & (RING_WORDS - 1)], b = ring[(i + 1) & (RING_WORDS - 1)],
+			       c = ring[(i + 2) & (RING_WORDS - 1)];
 		lo = __funnelshift_r(a, b, sh);
 		mid = __funnelshift_r(b, c, sh);
 		hi = c >> sh;
 		avail = 96u - sh;
 		widx = i + 3;
-		nw = ld(widx);
-		prefetch_l1(base + i + 32);
 	}
-	__device__ __forceinline__ void start(const uint8_t *src, uint32_t file_end, uint32_t P0)
+	__device__ __forceinline__ void topup()
 	{
-		base = reinterpret_cast<const uint32_t *>(src);
-		fe_word = file_end >> 5;
-		fe_tail = file_end & 31u;
-		seek(P0);
+		if (npend >= 1)
+			store_chunk(fill, pa);
+		if (npend >= 2)
+			store_chunk(fill + 1, pb);
+		fill += npend;
+		const int want = (int)((widx >> 2) + RING_LEAD) - (int)fill;
+		npend = want <= 0 ? 0u : (want >= 2 ? 2u : 1u);
+		if (npend >= 1)
+			pa = load_chunk(fill);
+		if (npend >= 2)
+			pb = load_chunk(fill + 1);
 	}
 	__device__ __forceinline__ uint32_t peek() const { return lo; }
-	/* consume step <= 32 bits */
-	template <bool CAREFUL>
-	__device__ __forceinline__ void consume(uint32_t step)
+	__device__ __forceinline__ uint32_t next_word() const { return ring[widx & (RING_WORDS - 1)]; }
+	/* consume step <= 32 bits; cand = next_word() read earlier in the iteration */
+	__device__ __forceinline__ void consume(uint32_t step, uint32_t cand)
 	{
 		lo = __funnelshift_rc(lo, mid, step);
 		mid = __funnelshift_rc(mid, hi, step);
 		hi = __funnelshift_rc(hi, 0u, step);
 		avail -= step;
 		const bool refill = avail <= 64u; /* then avail is in (32, 64] and hi holds nothing */
-		const unsigned long long t = (unsigned long long)nw << ((avail - 32u) & 63u);
+		const unsigned long long t = (unsigned long long)cand << ((avail - 32u) & 63u);
 		mid = refill ? (mid | (uint32_t)t) : mid;
 		hi = refill ? (uint32_t)(t >> 32) : hi;
 		avail = refill ? avail + 32u : avail;
 		widx = refill ? widx + 1u : widx;
-		if (CAREFUL) {
-			if (refill)
-				nw = ld(widx);
-		} else {
-			/* predicated load straight into nw: nothing waits for it until the next refill */
-			asm volatile("{\n\t.reg .pred p;\n\t"
-				     "setp.ne.u32 p, %1, 0;\n\t"
-				     "@p ld.global.nc.u32 %0, [%2];\n\t}"
-				     : "+r"(nw)
-				     : "r"((uint32_t)refill), "l"(base + widx));
-		}
-		if (refill && (widx & 31u) == 0u)
-			prefetch_l1(base + widx + 32); /* next 128-byte line */
 	}
 };
 
@@ -239,101 +278,55 @@ __device__ __forceinline__ uint32_t make_info(uint32_t kind)
  *   inside a prefix-coded column (rem rows to come): one kstep lookup (row cap folded in);
  *   inside a fixed-size payload (pend bits to come): skip, at most 32 bits per iteration
  *       (the shift-register window consumes at most one word per step).
- * The loop condition is a warp vote and the body is straight-line code, so the 32 lanes
- * execute ONE instruction stream however their column types differ.  It runs twice:
- *   HOT     no end-of-file logic at all, unmasked loads; legal while the lane is at least
- *           512 bits away from the end of its file (a step is <= 32 bits and the window
- *           reads at most 160 bits ahead).  A bad selector only raises a flag.
- *   CAREFUL masked loads and the reference's EOF / corruption checks: the last few dozen
- *           steps of a stream, and (from the block start) any block whose hot pass saw a
- *           bad selector.
- * profiles/r01_ncu_v4_summary.md has the measurements that led here.
+ * The body is straight-line code (every update is a select on the lane's state, including
+ * the reference's end-of-file and corruption verdicts), unrolled SCAN_PERIOD times between
+ * two ring top-ups, and the loop condition is a warp vote: the 32 lanes execute ONE
+ * instruction stream however their column types differ.
  */
 struct ScanState {
 	uint32_t P, rem, pend, col, kbase;
 	int status;
-	bool done, bad;
+	bool done;
 };
 
-__device__ __forceinline__ void scan_pass_hot(ScanReader &br, ScanState &s, uint32_t hot_end, uint16_t *&cp,
-					      uint32_t pblock, const uint16_t *sel13, const uint8_t *kstep)
+__device__ __forceinline__ void scan_step(ScanReader &br, ScanState &s, uint32_t limit, uint16_t *&cp,
+					  uint32_t pblock, const uint16_t *sel13, const uint8_t *kstep)
 {
-	bool run = !s.done && s.P < hot_end;
-	while (__any_sync(0xFFFFFFFFu, run)) {
-		/* lanes that are not running execute the same instructions on dead state: every
-		 * update below is guarded by `run`, and their loads stay inside the tables */
-		const uint32_t w = br.peek();
-		const bool at_sel = (s.rem | s.pend) == 0u;
-		const uint32_t es = sel13[w & 0x1FFFu];
-		const uint32_t ek = kstep[s.kbase + umin32(s.rem, 7u) * 256u + (w & 255u)];
-		const uint32_t adv_s = es & 511u, hi7 = es >> 9, rem_s = hi7 & 15u;
-		const bool sel = run && at_sel;
-		s.bad = s.bad || (sel && hi7 == 0x70u);
-		if (sel)
-			*cp = (uint16_t)(s.P - pblock);
-		cp = sel ? cp + OFF_PITCH : cp;
-		s.col = sel ? s.col + 1u : s.col;
-		s.kbase = sel ? (es >> 13) * 2048u : s.kbase;
-		const bool is_k = at_sel ? rem_s != 0u : s.rem != 0u;
-		const uint32_t tot = at_sel ? adv_s : s.pend;
-		uint32_t step = is_k ? (at_sel ? adv_s : (ek & 15u)) : umin32(tot, 32u);
-		step = run ? step : 0u;
-		s.pend = run ? (is_k ? 0u : tot - step) : s.pend;
-		s.rem = run ? (at_sel ? rem_s : s.rem - (ek >> 4)) : s.rem; /* kstep[.][0][.] = 0 */
-		s.P += step;
-		br.consume<false>(step);
-		const bool fin = (s.rem | s.pend) == 0u && s.col == (uint32_t)COLS;
-		s.done = s.done || (run && fin);
-		run = run && !fin && s.P < hot_end;
-	}
-}
-
-__device__ __forceinline__ void scan_pass_careful(ScanReader &br, ScanState &s, uint32_t limit, uint16_t *&cp,
-						  uint32_t pblock, const uint16_t *sel13, const uint8_t *kstep)
-{
-	while (!s.done) {
-		const uint32_t w = br.peek();
-		const bool at_sel = (s.rem | s.pend) == 0u;
-		const uint32_t es = sel13[w & 0x1FFFu];
-		const uint32_t ek = kstep[s.kbase + umin32(s.rem, 7u) * 256u + (w & 255u)];
-		const uint32_t adv_s = es & 511u, hi7 = es >> 9, rem_s = hi7 & 15u;
-		if (at_sel) {
-			if (s.P + 5u > limit) { /* GET_BITS_EXPECT_EOF decode.c:496 */
-				s.status = SCAN_EOF;
-				break;
-			}
-			*cp = (uint16_t)(s.P - pblock);
-			if (hi7 == 0x70u) { /* f_bad decode.c:190-194 */
-				s.status = -6;
-				break;
-			}
-			cp += OFF_PITCH;
-			s.col++;
-			s.kbase = (es >> 13) * 2048u;
-		}
-		const bool is_k = at_sel ? rem_s != 0u : s.rem != 0u;
-		const uint32_t tot = at_sel ? adv_s : s.pend;
-		const uint32_t step = is_k ? (at_sel ? adv_s : (ek & 15u)) : umin32(tot, 32u);
-		s.pend = is_k ? 0u : tot - step;
-		s.rem = at_sel ? rem_s : s.rem - (ek >> 4);
-		s.P += step;
-		br.consume<true>(step);
-		if ((s.rem | s.pend) == 0u) {
-			if (s.P > limit) { /* a GET_BITS inside the payload ran dry: decode.c:146-152 */
-				s.status = -7;
-				s.col--; /* the selector was consumed, the payload did not complete */
-				break;
-			}
-			if (s.col == (uint32_t)COLS)
-				break;
-		}
-	}
-	s.done = true;
+	const uint32_t w = br.peek();
+	const uint32_t cand = br.next_word();
+	const bool at_sel = (s.rem | s.pend) == 0u;
+	const uint32_t es = sel13[w & 0x1FFFu];
+	const uint32_t ek = kstep[s.kbase + umin32(s.rem, 7u) * 256u + (w & 255u)];
+	const uint32_t adv_s = es & 511u, hi7 = es >> 9, rem_s = hi7 & 15u;
+	const bool run = !s.done;
+	/* selector: GET_BITS_EXPECT_EOF decode.c:496, then f_bad decode.c:190-194 */
+	const bool eof = run && at_sel && (s.P + 5u > limit);
+	const bool bad = run && at_sel && !eof && hi7 == 0x70u;
+	const bool go = run && !eof && !bad;
+	const bool sel = go && at_sel;
+	if (sel)
+		*cp = (uint16_t)(s.P - pblock);
+	cp = sel ? cp + OFF_PITCH : cp;
+	s.col = sel ? s.col + 1u : s.col;
+	s.kbase = sel ? (es >> 13) * 2048u : s.kbase;
+	const bool is_k = at_sel ? rem_s != 0u : s.rem != 0u;
+	const uint32_t tot = at_sel ? adv_s : s.pend; /* fixed-size payload still to skip */
+	uint32_t step = is_k ? (at_sel ? adv_s : (ek & 15u)) : umin32(tot, 32u);
+	step = go ? step : 0u;
+	s.pend = go ? (is_k ? 0u : tot - step) : s.pend;
+	s.rem = go ? (at_sel ? rem_s : s.rem - (ek >> 4)) : s.rem; /* kstep[.][0][.] = 0 */
+	s.P += step;
+	br.consume(step, cand);
+	const bool fin = go && (s.rem | s.pend) == 0u;
+	const bool over = fin && s.P > limit; /* a GET_BITS inside the payload ran dry: decode.c:146-152 */
+	s.col = over ? s.col - 1u : s.col;    /* its selector was consumed, its payload did not complete */
+	s.status = eof ? (int)SCAN_EOF : (bad ? -6 : (over ? -7 : s.status));
+	s.done = s.done || eof || bad || over || (fin && s.col == (uint32_t)COLS);
 }
 
 __device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P, uint32_t limit,
-						      uint32_t hot_end, uint16_t *coloff,
-						      const uint16_t *sel13, const uint8_t *kstep, bool active)
+						      uint16_t *coloff, const uint16_t *sel13,
+						      const uint8_t *kstep, bool active)
 {
 	ScanState s;
 	ScanResult r;
@@ -342,7 +335,6 @@ __device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P
 	s.rem = s.pend = s.col = s.kbase = 0;
 	s.status = SCAN_OK;
 	s.done = !active;
-	s.bad = false;
 	r.val = 0;
 	if (active) {
 		if (P + 20 > limit) { /* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
@@ -351,20 +343,14 @@ __device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P
 		} else {
 			r.val = (int)((br.peek() >> 4) & 0xFFFFu);
 			s.P = P + 20;
-			br.consume<true>(20u);
+			br.consume(20u, br.next_word());
 		}
 	}
-	scan_pass_hot(br, s, hot_end, cp, P, sel13, kstep);
-	if (active && s.status == SCAN_OK && (!s.done || s.bad)) {
-		if (s.bad) {
-			/* redo the whole block with the reference's checks, from just after its header */
-			s.P = P + 20;
-			s.rem = s.pend = s.col = s.kbase = 0;
-			s.done = false;
-			cp = coloff;
-			br.seek(s.P);
-		}
-		scan_pass_careful(br, s, limit, cp, P, sel13, kstep);
+	while (__any_sync(0xFFFFFFFFu, !s.done)) {
+		br.topup();
+#pragma unroll
+		for (int k = 0; k < SCAN_PERIOD; k++)
+			scan_step(br, s, limit, cp, P, sel13, kstep);
 	}
 	r.status = s.status;
 	r.ncols = s.col;
@@ -645,9 +631,9 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 	const bool is_scan = warp >= W;
 	const int myslot = is_scan ? 32 * (warp - W) + lane : 0;
 	bool active = false;
-	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, hot_end = 0;
+	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0;
 	ScanReader sbr;
-	sbr.reset();
+	sbr.reset(sm.ring[myslot]);
 	uint32_t *const cta_hist = a.hist + (size_t)blockIdx.x * S * HIST_WORDS;
 
 	for (int round = 0;; round++) {
@@ -669,9 +655,9 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					P = d.bit0;
 					blk = 0;
 					limit = d.file_end + 8u;
-					hot_end = d.file_end > 512u ? d.file_end - 512u : 0u;
 					n_attempt = d.n_attempt;
-					sbr.start(a.blob + d.base_off, d.file_end, P);
+					sbr.start(a.blob + d.base_off, a.blob_room > d.base_off ? a.blob_room - d.base_off : 0,
+						  d.file_end, P);
 					active = true;
 				}
 			}
@@ -691,8 +677,8 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 				}
 			}
 			{
-				ScanResult sc = scan_block_flat(sbr, P, limit, hot_end, sm.coloff[buf] + myslot,
-								sm.sel13, sm.kstep, walk);
+				ScanResult sc = scan_block_flat(sbr, P, limit, sm.coloff[buf] + myslot, sm.sel13,
+								sm.kstep, walk);
 				if (walk) {
 					e.status = sc.status;
 					e.ncols = sc.ncols;
