@@ -263,11 +263,12 @@ def run_ours(args):
     if use_dist:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        # optional checksum gather (the only collective; outside the timed region)
-        ck = torch.from_numpy(checksums.astype(np.int64)).to(dev)
-        allck = torch.empty(world * ck.numel(), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(allck, ck)
-        ck_of_ck = int(allck.sum().item())
+        # optional result gather (the only collective; NCCL, outside the timed region)
+        from libacm_b200 import shard
+        base = rank * args.streams
+        _, g_words, g_cks = shard.gather_results(np.arange(base, base + args.streams), streams["status"],
+                                                 streams["words"], checksums, world * args.streams, device=dev)
+        ck_of_ck = int(np.sum(g_cks, dtype=np.uint64))
     else:
         ck_of_ck = int(np.sum(checksums.astype(np.uint64), dtype=np.uint64))
     ms_total, e2e_ms = float(t[0]), float(t[1])

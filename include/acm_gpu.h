@@ -92,10 +92,12 @@ int64_t acm_gpu_probe(const void *blob, uint64_t blob_len, int blob_on_device,
 uint64_t acm_gpu_layout(acm_gpu_stream *streams, uint64_t n, int wordlen);
 
 /*
- * One-shot decode.  Host blobs/outputs are staged through pinned buffers and
- * copied inside the call (pipelined with the kernels); device pointers are used
- * in place.  Streams must have been probed.  Returns ACM_OK, or ACM_ERR_OTHER for
- * a CUDA/runtime failure (per-stream problems are reported in streams[i].status).
+ * One-shot decode.  Host blobs/outputs are copied inside the call: the batch is cut
+ * into segments whose copy-in, decode and copy-out overlap on three CUDA streams (pass
+ * pinned host memory for full PCIe speed; the streams must be listed in blob/out byte
+ * order, which is what acm_gpu_layout produces).  Device pointers are used in place.
+ * Streams must have been probed.  Returns ACM_OK, or ACM_ERR_OTHER for a CUDA/runtime
+ * failure (per-stream problems are reported in streams[i].status).
  */
 int acm_gpu_decode_batch(const acm_gpu_batch *batch, const acm_gpu_opts *opts);
 
@@ -118,6 +120,10 @@ void acm_gpu_plan_split(const acm_gpu_plan *plan, uint64_t *n_fast, uint64_t *n_
 /* average device time of the kernels of the last run on that plan, ms (CUDA events on cuda_stream) */
 float acm_gpu_plan_last_ms(acm_gpu_plan *plan);
 void acm_gpu_plan_destroy(acm_gpu_plan *plan);
+
+/* acm_gpu_decode_batch keeps its device staging buffers and streams between calls (host-buffer
+ * path); this frees them */
+void acm_gpu_release_workspace(void);
 
 /* last CUDA / runtime error text of the calling thread ("" if none) */
 const char *acm_gpu_last_error(void);

@@ -156,6 +156,23 @@ extern "C" uint64_t acm_gpu_layout(acm_gpu_stream *s, uint64_t n, int wordlen)
 
 /* ------------------------------------------------------------------ plan */
 
+/*
+ * A plan may be cut into SEGMENTS: contiguous ranges of the caller's stream array whose
+ * images and PCM occupy contiguous byte ranges of blob / out.  Every segment has its own
+ * slices of the descriptor table and its own work-queue cursors, so the host path of
+ * acm_gpu_decode_batch can copy segment g+1 in while segment g decodes and segment g-1
+ * copies out.  The resident path (acm_gpu_plan_create) uses one segment.
+ */
+struct Segment {
+	uint64_t s_first, s_count;        /* caller's streams [s_first, s_first + s_count) */
+	uint64_t fast_first, n_fast;      /* slices of d_streams */
+	uint64_t gen_first, n_gen;
+	uint64_t blob_lo, blob_hi;        /* byte ranges touched (16-byte granular) */
+	uint64_t out_lo, out_hi;
+	int fast_ctas, gen_ctas;          /* grid sizes; segments may run concurrently, so each has */
+	size_t hist_off, scratch_off;     /* its own history / scratch region (offsets in words) */
+};
+
 struct acm_gpu_plan {
 	int device;
 	uint64_t n;          /* caller's stream count */
@@ -164,12 +181,13 @@ struct acm_gpu_plan {
 	uint64_t blob_room;  /* bytes the kernels may read: end of the last image, rounded up to 16 */
 	Format fmt;
 	std::vector<int32_t> host_status; /* statuses decided on the host (NOT_ACM, OTHER) */
+	std::vector<Segment> seg;
 	DevStream *d_streams;
 	int32_t *d_status;
 	uint32_t *d_words;
 	unsigned long long *d_cks;
 	acm_tables *d_tables;
-	uint32_t *d_counters; /* [0] fast queue, [1] generic queue */
+	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue; [4*nseg] error flag */
 	GenericScratch scratch;
 	uint32_t *d_hist;    /* fast kernel history, fast_ctas * fast_hist_words_per_cta() words */
 	int fast_ctas;
@@ -205,16 +223,17 @@ static bool fast_eligible(const acm_gpu_stream &g, const acm_gpu_opts *o)
 	return o->wordlen == 2 && fast_shape(g.level, g.rows);
 }
 
-extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n,
-					     const acm_gpu_opts *opts, int *err_out)
+static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_gpu_opts *opts,
+				 unsigned nseg, int *err_out)
 {
 	acm_gpu_opts defaults;
 	acm_gpu_plan *p = nullptr;
-	std::vector<DevStream> fast, gen;
+	std::vector<DevStream> all;
 	acm_tables host_tab;
 	cudaDeviceProp prop;
 	int err = ACM_ERR_OTHER, dev = 0;
 	uint32_t max_blen = 1, max_cols = 1;
+	uint64_t max_fast = 0, max_gen = 0;
 
 	g_err[0] = 0;
 	if (!opts) {
@@ -238,6 +257,7 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
 	p->device = dev;
 	p->n = n;
+	p->n_fast = p->n_generic = 0;
 	p->sm_count = prop.multiProcessorCount;
 	p->timed = false;
 	p->fmt.wordlen = opts->wordlen;
@@ -247,30 +267,72 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 	p->host_status.assign(n, 0);
 	p->blob_room = 0;
 
-	for (uint64_t i = 0; i < n; i++) {
-		const acm_gpu_stream &g = s[i];
-		if (g.status == 0 && (g.out_off & 15u)) {
-			acm_set_error("stream %llu: out_off must be a multiple of 16", (unsigned long long)i);
-			goto fail;
-		}
-		DevStream d;
-		int hs = acm_make_devstream(&g, (uint32_t)i, opts->pad_tail, &d);
-		if (hs < 0) {
-			p->host_status[i] = hs;
-			continue;
-		}
-		uint32_t blen = g.rows << g.level;
-		p->blob_room = std::max(p->blob_room, (g.in_off + g.in_len + 15u) & ~(uint64_t)15u);
-		if (opts->kernel != 1 && fast_eligible(g, opts)) {
-			fast.push_back(d);
-		} else {
-			gen.push_back(d);
-			max_blen = std::max(max_blen, blen);
-			max_cols = std::max(max_cols, 1u << g.level);
+	if (nseg < 1)
+		nseg = 1;
+	if (nseg > n)
+		nseg = n ? (unsigned)n : 1;
+	{
+		/* segment boundaries: equal shares of the output words */
+		uint64_t total = 0, acc = 0, first = 0;
+		for (uint64_t i = 0; i < n; i++)
+			total += s[i].total_values;
+		for (unsigned g = 0; g < nseg; g++) {
+			Segment sg;
+			memset(&sg, 0, sizeof(sg));
+			sg.s_first = first;
+			uint64_t target = total / nseg * (g + 1);
+			uint64_t i = first;
+			if (g + 1 == nseg) {
+				i = n;
+			} else {
+				while (i < n && (acc < target || i == first)) {
+					acc += s[i].total_values;
+					i++;
+				}
+				if (n - i < nseg - 1 - g) /* leave at least one stream per remaining segment */
+					i = n - (nseg - 1 - g);
+			}
+			sg.s_count = i - first;
+			first = i;
+			p->seg.push_back(sg);
 		}
 	}
-	/* longest first: the work queues hand out streams in this order (LPT) */
-	{
+	for (Segment &sg : p->seg) {
+		std::vector<DevStream> fast, gen;
+		sg.blob_lo = sg.out_lo = ~(uint64_t)0;
+		for (uint64_t i = sg.s_first; i < sg.s_first + sg.s_count; i++) {
+			const acm_gpu_stream &g = s[i];
+			if (g.status == 0 && (g.out_off & 15u)) {
+				acm_set_error("stream %llu: out_off must be a multiple of 16", (unsigned long long)i);
+				goto fail;
+			}
+			DevStream d;
+			int hs = acm_make_devstream(&g, (uint32_t)i, opts->pad_tail, &d);
+			if (hs < 0) {
+				p->host_status[i] = hs;
+				continue;
+			}
+			uint32_t blen = g.rows << g.level;
+			uint64_t in_hi = (g.in_off + g.in_len + 15u) & ~(uint64_t)15u;
+			uint64_t o_hi = g.out_off + (((uint64_t)g.total_values * opts->wordlen + 15u) & ~(uint64_t)15u);
+			p->blob_room = std::max(p->blob_room, in_hi);
+			sg.blob_lo = std::min(sg.blob_lo, g.in_off & ~(uint64_t)15u);
+			sg.blob_hi = std::max(sg.blob_hi, in_hi);
+			sg.out_lo = std::min(sg.out_lo, g.out_off);
+			sg.out_hi = std::max(sg.out_hi, o_hi);
+			if (opts->kernel != 1 && fast_eligible(g, opts)) {
+				fast.push_back(d);
+			} else {
+				gen.push_back(d);
+				max_blen = std::max(max_blen, blen);
+				max_cols = std::max(max_cols, 1u << g.level);
+			}
+		}
+		if (sg.blob_lo > sg.blob_hi)
+			sg.blob_lo = sg.blob_hi = 0;
+		if (sg.out_lo > sg.out_hi)
+			sg.out_lo = sg.out_hi = 0;
+		/* longest first: the work queues hand out streams in this order (LPT) */
 		auto by_len = [](const DevStream &a, const DevStream &b) {
 			if (a.n_attempt != b.n_attempt)
 				return a.n_attempt > b.n_attempt;
@@ -285,17 +347,22 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 			return a.index < b.index;
 		};
 		std::sort(gen.begin(), gen.end(), by_work);
+		sg.fast_first = all.size();
+		sg.n_fast = fast.size();
+		all.insert(all.end(), fast.begin(), fast.end());
+		sg.gen_first = all.size();
+		sg.n_gen = gen.size();
+		all.insert(all.end(), gen.begin(), gen.end());
+		p->n_fast += sg.n_fast;
+		p->n_generic += sg.n_gen;
+		max_fast = std::max(max_fast, sg.n_fast);
+		max_gen = std::max(max_gen, sg.n_gen);
 	}
-	p->n_fast = fast.size();
-	p->n_generic = gen.size();
-	p->n_dev = p->n_fast + p->n_generic;
+	p->n_dev = all.size();
 
 	CU(cudaMalloc(&p->d_streams, (p->n_dev + 1) * sizeof(DevStream)));
-	if (p->n_fast)
-		CU(cudaMemcpy(p->d_streams, fast.data(), p->n_fast * sizeof(DevStream), cudaMemcpyHostToDevice));
-	if (p->n_generic)
-		CU(cudaMemcpy(p->d_streams + p->n_fast, gen.data(), p->n_generic * sizeof(DevStream),
-			      cudaMemcpyHostToDevice));
+	if (p->n_dev)
+		CU(cudaMemcpy(p->d_streams, all.data(), p->n_dev * sizeof(DevStream), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&p->d_status, (n + 1) * sizeof(int32_t)));
 	CU(cudaMalloc(&p->d_words, (n + 1) * sizeof(uint32_t)));
 	CU(cudaMalloc(&p->d_cks, (n + 1) * sizeof(unsigned long long)));
@@ -305,29 +372,39 @@ extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n
 	acm_tables_build(&host_tab);
 	CU(cudaMalloc(&p->d_tables, sizeof(acm_tables)));
 	CU(cudaMemcpy(p->d_tables, &host_tab, sizeof(acm_tables), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&p->d_counters, 64));
+	CU(cudaMalloc(&p->d_counters, (4 * p->seg.size() + 4) * sizeof(uint32_t)));
 	CU(cudaEventCreate(&p->ev0));
 	CU(cudaEventCreate(&p->ev1));
 
-	if (p->n_fast) {
-		uint64_t per = (uint64_t)fast_slots_per_cta();
-		uint64_t groups = (p->n_fast + per - 1) / per;
-		p->fast_ctas = (uint64_t)p->sm_count < groups ? p->sm_count : (int)groups;
-		CU(cudaMalloc(&p->d_hist, (size_t)p->fast_ctas * fast_hist_words_per_cta() * 4));
-	}
-	if (p->n_generic) {
-		size_t stride = generic_scratch_words(max_blen, max_cols);
-		size_t budget = (size_t)4 << 30; /* bytes of scratch we are willing to hold */
-		int ctas = p->sm_count * 4;
-		if ((uint64_t)ctas > p->n_generic)
-			ctas = (int)p->n_generic;
-		while (ctas > 1 && (size_t)ctas * stride * 4 > budget)
-			ctas /= 2;
-		p->generic_ctas = ctas;
-		p->scratch.stride = stride;
-		p->scratch.max_blen = max_blen;
-		p->scratch.max_cols = max_cols;
-		CU(cudaMalloc(&p->scratch.buf, (size_t)ctas * stride * 4));
+	{
+		const uint64_t per = (uint64_t)fast_slots_per_cta();
+		const size_t stride = generic_scratch_words(max_blen, max_cols);
+		const size_t budget = ((size_t)4 << 30) / p->seg.size(); /* scratch bytes per segment */
+		size_t hist_words = 0, scratch_words = 0;
+		for (Segment &sg : p->seg) {
+			uint64_t groups = (sg.n_fast + per - 1) / per;
+			sg.fast_ctas = (uint64_t)p->sm_count < groups ? p->sm_count : (int)groups;
+			sg.hist_off = hist_words;
+			hist_words += (size_t)sg.fast_ctas * fast_hist_words_per_cta();
+			int ctas = p->sm_count * 4;
+			if ((uint64_t)ctas > sg.n_gen)
+				ctas = (int)sg.n_gen;
+			while (ctas > 1 && (size_t)ctas * stride * 4 > budget)
+				ctas /= 2;
+			sg.gen_ctas = ctas;
+			sg.scratch_off = scratch_words;
+			scratch_words += (size_t)ctas * stride;
+			p->fast_ctas = std::max(p->fast_ctas, sg.fast_ctas);
+			p->generic_ctas = std::max(p->generic_ctas, sg.gen_ctas);
+		}
+		if (max_fast)
+			CU(cudaMalloc(&p->d_hist, hist_words * 4 + 16));
+		if (max_gen) {
+			p->scratch.stride = stride;
+			p->scratch.max_blen = max_blen;
+			p->scratch.max_cols = max_cols;
+			CU(cudaMalloc(&p->scratch.buf, scratch_words * 4 + 16));
+		}
 	}
 	if (err_out)
 		*err_out = ACM_OK;
@@ -339,43 +416,63 @@ fail:
 	return nullptr;
 }
 
-extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out, void *cuda_stream)
+extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n,
+					     const acm_gpu_opts *opts, int *err_out)
 {
-	cudaStream_t st = (cudaStream_t)cuda_stream;
+	return plan_create(s, n, opts, 1, err_out);
+}
+
+/* launch the kernels of one segment on `st`; the cursors must have been zeroed on that stream */
+static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void *d_out, cudaStream_t st)
+{
+	const Segment &sg = p->seg[g];
 	KernelArgs a;
-	g_err[0] = 0;
-	CU(cudaSetDevice(p->device));
-	CU(cudaMemsetAsync(p->d_counters, 0, 64, st));
-	CU(cudaEventRecord(p->ev0, st));
-	if (((uintptr_t)d_blob & 15u) || ((uintptr_t)d_out & 15u)) {
-		acm_set_error("acm_gpu_plan_run: blob and out must be 16-byte aligned");
-		return ACM_ERR_OTHER;
-	}
 	a.blob = (const uint8_t *)d_blob;
 	a.blob_room = p->blob_room;
-	a.errflag = p->d_counters + 2;
+	a.errflag = p->d_counters + 4 * p->seg.size();
 	a.out = (uint8_t *)d_out;
 	a.status = p->d_status;
 	a.words = p->d_words;
 	a.cks = p->d_cks;
 	a.tables = p->d_tables;
 	a.fmt = p->fmt;
-	a.hist = p->d_hist;
+	a.hist = p->d_hist ? p->d_hist + sg.hist_off : nullptr;
 	a.resume_hist = nullptr;
 	a.resume_stride = 0;
 	a.end_pos = nullptr;
-	if (p->n_fast) {
-		a.streams = p->d_streams;
-		a.count = (uint32_t)p->n_fast;
-		a.counter = p->d_counters;
-		CU(launch_fast(a, p->fast_ctas, st));
+	if (sg.n_fast) {
+		a.streams = p->d_streams + sg.fast_first;
+		a.count = (uint32_t)sg.n_fast;
+		a.counter = p->d_counters + 4 * g;
+		CU(launch_fast(a, sg.fast_ctas, st));
 	}
-	if (p->n_generic) {
-		a.streams = p->d_streams + p->n_fast;
-		a.count = (uint32_t)p->n_generic;
-		a.counter = p->d_counters + 1;
-		CU(launch_generic(a, p->scratch, p->generic_ctas, st));
+	if (sg.n_gen) {
+		GenericScratch sc = p->scratch;
+		sc.buf += sg.scratch_off;
+		a.streams = p->d_streams + sg.gen_first;
+		a.count = (uint32_t)sg.n_gen;
+		a.counter = p->d_counters + 4 * g + 1;
+		CU(launch_generic(a, sc, sg.gen_ctas, st));
 	}
+	return ACM_OK;
+fail:
+	return ACM_ERR_OTHER;
+}
+
+extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out, void *cuda_stream)
+{
+	cudaStream_t st = (cudaStream_t)cuda_stream;
+	g_err[0] = 0;
+	if (((uintptr_t)d_blob & 15u) || ((uintptr_t)d_out & 15u)) {
+		acm_set_error("acm_gpu_plan_run: blob and out must be 16-byte aligned");
+		return ACM_ERR_OTHER;
+	}
+	CU(cudaSetDevice(p->device));
+	CU(cudaMemsetAsync(p->d_counters, 0, (4 * p->seg.size() + 4) * sizeof(uint32_t), st));
+	CU(cudaEventRecord(p->ev0, st));
+	for (size_t g = 0; g < p->seg.size(); g++)
+		if (plan_run_segment(p, g, d_blob, d_out, st) < 0)
+			return ACM_ERR_OTHER;
 	CU(cudaEventRecord(p->ev1, st));
 	p->timed = true;
 	return ACM_OK;
@@ -393,9 +490,9 @@ extern "C" int acm_gpu_plan_fetch(acm_gpu_plan *p, acm_gpu_stream *s, void *cuda
 	g_err[0] = 0;
 	CU(cudaSetDevice(p->device));
 	CU(cudaStreamSynchronize(st));
-	CU(cudaMemcpy(&flag, p->d_counters + 2, sizeof(flag), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(&flag, p->d_counters + 4 * p->seg.size(), sizeof(flag), cudaMemcpyDeviceToHost));
 	if (flag) {
-		acm_set_error("decode kernel reported internal failure %u (bulk-copy timeout)", flag);
+		acm_set_error("decode kernel reported internal failure %u", flag);
 		return ACM_ERR_OTHER;
 	}
 	if (p->n) {
@@ -421,7 +518,10 @@ fail:
 
 extern "C" int acm_gpu_plan_launches(const acm_gpu_plan *p)
 {
-	return (p->n_fast ? 1 : 0) + (p->n_generic ? 1 : 0);
+	int k = 0;
+	for (const Segment &sg : p->seg)
+		k += (sg.n_fast ? 1 : 0) + (sg.n_gen ? 1 : 0);
+	return k;
 }
 
 extern "C" void acm_gpu_plan_split(const acm_gpu_plan *p, uint64_t *n_fast, uint64_t *n_generic)
@@ -448,16 +548,146 @@ extern "C" void acm_gpu_plan_destroy(acm_gpu_plan *p) { plan_free(p); }
 
 /* ------------------------------------------------------------------ one-shot */
 
+namespace {
+
+/* device staging buffers and streams of the host path, kept between calls (one set per device) */
+constexpr unsigned MAX_SEG = 8;
+
+struct Workspace {
+	uint8_t *d_blob = nullptr, *d_out = nullptr;
+	size_t blob_cap = 0, out_cap = 0;
+	cudaStream_t s_in = nullptr, s_out = nullptr;
+	cudaStream_t s_k[MAX_SEG] = {};
+};
+std::mutex g_ws_mutex;
+Workspace g_ws[16];
+
+int ws_reserve(Workspace &w, size_t blob_bytes, size_t out_bytes)
+{
+	if (!w.s_in) {
+		CU(cudaStreamCreateWithFlags(&w.s_in, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&w.s_out, cudaStreamNonBlocking));
+		for (unsigned k = 0; k < MAX_SEG; k++)
+			CU(cudaStreamCreateWithFlags(&w.s_k[k], cudaStreamNonBlocking));
+	}
+	if (w.blob_cap < blob_bytes) {
+		cudaFree(w.d_blob);
+		w.d_blob = nullptr;
+		w.blob_cap = 0;
+		CU(cudaMalloc(&w.d_blob, blob_bytes));
+		w.blob_cap = blob_bytes;
+	}
+	if (w.out_cap < out_bytes) {
+		cudaFree(w.d_out);
+		w.d_out = nullptr;
+		w.out_cap = 0;
+		CU(cudaMalloc(&w.d_out, out_bytes));
+		w.out_cap = out_bytes;
+	}
+	return ACM_OK;
+fail:
+	return ACM_ERR_OTHER;
+}
+
+} // namespace
+
+extern "C" void acm_gpu_release_workspace(void)
+{
+	std::lock_guard<std::mutex> lock(g_ws_mutex);
+	int cur = 0;
+	cudaGetDevice(&cur);
+	for (int d = 0; d < 16; d++) {
+		Workspace &w = g_ws[d];
+		if (!w.s_in && !w.d_blob && !w.d_out)
+			continue;
+		cudaSetDevice(d);
+		cudaFree(w.d_blob);
+		cudaFree(w.d_out);
+		if (w.s_in) {
+			cudaStreamDestroy(w.s_in);
+			cudaStreamDestroy(w.s_out);
+			for (unsigned k = 0; k < MAX_SEG; k++)
+				if (w.s_k[k])
+					cudaStreamDestroy(w.s_k[k]);
+		}
+		w = Workspace();
+	}
+	cudaSetDevice(cur);
+}
+
+#define CUR(call)                                                                     \
+	do {                                                                          \
+		cudaError_t e_ = (call);                                              \
+		if (e_ != cudaSuccess) {                                              \
+			acm_set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call,     \
+				      cudaGetErrorString(e_));                        \
+			return ACM_ERR_OTHER;                                         \
+		}                                                                     \
+	} while (0)
+
+/* copy-in / decode / copy-out of every segment, overlapped on the workspace's three streams */
+static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w,
+			std::vector<cudaEvent_t> &ev_in, std::vector<cudaEvent_t> &ev_k)
+{
+	const uint8_t *blob_dev = (const uint8_t *)b->blob;
+	uint8_t *out_dev = (uint8_t *)b->out;
+	const size_t ns = plan->seg.size();
+	if (ws_reserve(w, b->blob_on_device ? 0 : ((b->blob_len + 15u) & ~(uint64_t)15u) + 64,
+		       b->out_on_device ? 0 : b->out_len + 64) < 0)
+		return ACM_ERR_OTHER;
+	if (!b->blob_on_device)
+		blob_dev = w.d_blob;
+	if (!b->out_on_device)
+		out_dev = w.d_out;
+	if (((uintptr_t)blob_dev & 15u) || ((uintptr_t)out_dev & 15u)) {
+		acm_set_error("acm_gpu_decode_batch: device blob and out must be 16-byte aligned");
+		return ACM_ERR_OTHER;
+	}
+	ev_in.assign(ns, nullptr);
+	ev_k.assign(ns, nullptr);
+	for (size_t g = 0; g < ns; g++) {
+		CUR(cudaEventCreateWithFlags(&ev_in[g], cudaEventDisableTiming));
+		CUR(cudaEventCreateWithFlags(&ev_k[g], cudaEventDisableTiming));
+	}
+	/* the cursors are zeroed before anything else is queued: the copy-in stream waits for it */
+	CUR(cudaMemsetAsync(plan->d_counters, 0, (4 * ns + 4) * sizeof(uint32_t), w.s_in));
+	for (size_t g = 0; g < ns; g++) {
+		const Segment &sg = plan->seg[g];
+		cudaStream_t sk = w.s_k[g % MAX_SEG];
+		if (!b->blob_on_device && sg.blob_hi > sg.blob_lo) {
+			uint64_t hi = sg.blob_hi < b->blob_len ? sg.blob_hi : b->blob_len;
+			CUR(cudaMemcpyAsync(w.d_blob + sg.blob_lo, (const uint8_t *)b->blob + sg.blob_lo,
+					    hi - sg.blob_lo, cudaMemcpyHostToDevice, w.s_in));
+		}
+		CUR(cudaEventRecord(ev_in[g], w.s_in));
+		CUR(cudaStreamWaitEvent(sk, ev_in[g], 0));
+		if (plan_run_segment(plan, g, blob_dev, out_dev, sk) < 0)
+			return ACM_ERR_OTHER;
+		CUR(cudaEventRecord(ev_k[g], sk));
+		if (!b->out_on_device && sg.out_hi > sg.out_lo) {
+			uint64_t hi = sg.out_hi < b->out_len ? sg.out_hi : b->out_len;
+			CUR(cudaStreamWaitEvent(w.s_out, ev_k[g], 0));
+			CUR(cudaMemcpyAsync((uint8_t *)b->out + sg.out_lo, w.d_out + sg.out_lo, hi - sg.out_lo,
+					    cudaMemcpyDeviceToHost, w.s_out));
+		}
+	}
+	for (size_t g = 0; g < ns; g++)
+		CUR(cudaEventSynchronize(ev_k[g]));
+	if (acm_gpu_plan_fetch(plan, b->streams, w.s_in) < 0)
+		return ACM_ERR_OTHER;
+	CUR(cudaStreamSynchronize(w.s_out));
+	CUR(cudaGetLastError());
+	return ACM_OK;
+}
+
 extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *opts)
 {
 	acm_gpu_opts defaults;
 	acm_gpu_plan *plan = nullptr;
-	uint8_t *d_blob = nullptr, *d_out = nullptr;
-	const uint8_t *blob_dev;
-	uint8_t *out_dev;
-	cudaStream_t st = nullptr;
-	int err = ACM_ERR_OTHER, perr = 0;
-	bool need_probe = false;
+	std::vector<cudaEvent_t> ev_in, ev_k;
+	int err = ACM_ERR_OTHER, perr = 0, dev = 0;
+	bool need_probe = false, host_io, monotonic = true;
+	unsigned nseg = 1;
 
 	g_err[0] = 0;
 	if (!b || (!b->streams && b->n)) {
@@ -483,40 +713,36 @@ extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *
 			acm_set_error("stream %llu does not fit its blob/out range", (unsigned long long)i);
 			return ACM_ERR_OTHER;
 		}
+		if (i && (g.in_off < b->streams[i - 1].in_off || g.out_off < b->streams[i - 1].out_off))
+			monotonic = false;
 	}
-	plan = acm_gpu_plan_create(b->streams, b->n, opts, &perr);
+	host_io = !b->blob_on_device || !b->out_on_device;
+	/* host buffers: cut the batch into segments and pipeline copy-in / decode / copy-out, provided the
+	 * caller's order is also the byte order of blob and out (acm_gpu_layout's order) */
+	if (host_io && monotonic && b->out_len >= ((uint64_t)32 << 20) && b->n >= 64)
+		nseg = MAX_SEG;
+	plan = plan_create(b->streams, b->n, opts, nseg, &perr);
 	if (!plan)
 		return perr ? perr : ACM_ERR_OTHER;
-
-	CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-	if (b->blob_on_device) {
-		blob_dev = (const uint8_t *)b->blob;
-	} else {
-		CU(cudaMalloc(&d_blob, b->blob_len + 64));
-		CU(cudaMemcpyAsync(d_blob, b->blob, b->blob_len, cudaMemcpyHostToDevice, st));
-		blob_dev = d_blob;
+	{
+		std::lock_guard<std::mutex> lock(g_ws_mutex);
+		if (cudaGetDevice(&dev) == cudaSuccess) {
+			Workspace &w = g_ws[dev & 15];
+			err = run_segments(plan, b, w, ev_in, ev_k);
+			if (w.s_in) {
+				cudaStreamSynchronize(w.s_in);
+				cudaStreamSynchronize(w.s_out);
+				for (unsigned k = 0; k < MAX_SEG; k++)
+					cudaStreamSynchronize(w.s_k[k]);
+			}
+		}
 	}
-	if (b->out_on_device) {
-		out_dev = (uint8_t *)b->out;
-	} else {
-		CU(cudaMalloc(&d_out, b->out_len + 64));
-		out_dev = d_out;
-	}
-	if (acm_gpu_plan_run(plan, blob_dev, out_dev, st) < 0)
-		goto fail;
-	if (!b->out_on_device && b->out_len)
-		CU(cudaMemcpyAsync(b->out, d_out, b->out_len, cudaMemcpyDeviceToHost, st));
-	if (acm_gpu_plan_fetch(plan, b->streams, st) < 0)
-		goto fail;
-	CU(cudaGetLastError());
-	err = ACM_OK;
-fail:
-	if (st) {
-		cudaStreamSynchronize(st);
-		cudaStreamDestroy(st);
-	}
-	cudaFree(d_blob);
-	cudaFree(d_out);
+	for (cudaEvent_t e : ev_in)
+		if (e)
+			cudaEventDestroy(e);
+	for (cudaEvent_t e : ev_k)
+		if (e)
+			cudaEventDestroy(e);
 	acm_gpu_plan_destroy(plan);
 	return err;
 }

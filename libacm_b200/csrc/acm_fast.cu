@@ -69,7 +69,7 @@ constexpr int STAGE_BYTES = (BLEN + 4 * 32 - X0_WORDS) * 4; /* 4608: a whole blo
 constexpr int STAGE_CHUNKS = STAGE_BYTES / 16;
 constexpr int RING_WORDS = 64;           /* 16 chunks of 16 bytes per scan lane */
 constexpr int RING_LEAD = 8;             /* chunks kept ahead of the read position */
-constexpr int SCAN_PERIOD = 8;           /* walk iterations between two ring top-ups */
+constexpr int SCAN_PERIOD = 4;           /* walk iterations between two ring top-ups (<= 16 bytes consumed) */
 constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [128,192) X2 tail [192,256) */
 
 enum { ENT_IDLE = -100 };
@@ -127,11 +127,11 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
  * the top of every iteration; when fewer remain, ring word `widx` (read unconditionally
  * at the top of the iteration, next to the table lookups) is spliced in above them.
  *
- * topup() runs for all lanes together every SCAN_PERIOD iterations: it stores the (at most
- * two) 16-byte chunks requested by the previous top-up into the ring -- zeroing everything
- * at and past the end of the file, which is the reference's "one zero byte, then nothing"
- * (decode.c:57-61) -- and requests the next ones so that RING_LEAD chunks stay ahead of
- * the read position.  SCAN_PERIOD iterations consume at most 32 bytes = the two chunks a
+ * topup() runs for all lanes together every SCAN_PERIOD iterations: it stores the 16-byte
+ * chunk requested by the previous top-up into the ring -- zeroing everything at and past
+ * the end of the file, which is the reference's "one zero byte, then nothing"
+ * (decode.c:57-61) -- and requests the next one while fewer than RING_LEAD chunks are ahead
+ * of the read position.  SCAN_PERIOD iterations consume at most 16 bytes = the chunk a
  * top-up can add, so the ring never runs dry and nothing ever waits on a load.
  */
 struct ScanReader {
@@ -142,8 +142,8 @@ struct ScanReader {
 	uint32_t lo, mid, hi, avail; /* bits [0, avail) of hi:mid:lo are the stream at the read position */
 	uint32_t widx;        /* stream word that will be spliced in next */
 	uint32_t fill;        /* chunks stored so far = index of the next chunk to store */
-	uint32_t npend;       /* chunks requested at the last top-up (0..2) */
-	uint4 pa, pb;
+	uint32_t npend;       /* chunks requested at the last top-up (0..1) */
+	uint4 pa;
 
 	__device__ __forceinline__ uint4 load_chunk(uint32_t c) const
 	{
@@ -178,7 +178,7 @@ struct ScanReader {
 		avail = 96;
 		fill = 0x40000000u; /* never asks for data */
 		npend = 0;
-		pa = pb = make_uint4(0u, 0u, 0u, 0u);
+		pa = make_uint4(0u, 0u, 0u, 0u);
 	}
 	/* new stream: fill the ring synchronously once, position the window on bit P0 */
 	__device__ __forceinline__ void start(const uint8_t *src, uint64_t room, uint32_t file_end, uint32_t P0)
@@ -203,17 +203,12 @@ struct ScanReader {
 	}
 	__device__ __forceinline__ void topup()
 	{
-		if (npend >= 1)
+		if (npend)
 			store_chunk(fill, pa);
-		if (npend >= 2)
-			store_chunk(fill + 1, pb);
 		fill += npend;
-		const int want = (int)((widx >> 2) + RING_LEAD) - (int)fill;
-		npend = want <= 0 ? 0u : (want >= 2 ? 2u : 1u);
-		if (npend >= 1)
+		npend = (widx >> 2) + RING_LEAD > fill ? 1u : 0u;
+		if (npend)
 			pa = load_chunk(fill);
-		if (npend >= 2)
-			pb = load_chunk(fill + 1);
 	}
 	__device__ __forceinline__ uint32_t peek() const { return lo; }
 	__device__ __forceinline__ uint32_t next_word() const { return ring[widx & (RING_WORDS - 1)]; }
@@ -283,12 +278,16 @@ __device__ __forceinline__ uint32_t make_info(uint32_t kind)
  * two ring top-ups, and the loop condition is a warp vote: the 32 lanes execute ONE
  * instruction stream however their column types differ.
  */
+enum { SCAN_RUNNING = 2 }; /* besides SCAN_OK (1), SCAN_EOF (0) and the negative error codes */
+
 struct ScanState {
 	uint32_t P, rem, pend, col, kbase;
-	int status;
-	bool done;
+	int st; /* SCAN_RUNNING while walking, then the verdict */
 };
 
+/* NEAR = false: no lane of the warp can reach its limit within this period (a step is <= 32
+ * bits), so the end-of-file verdicts are compiled out; a bad selector is still caught. */
+template <bool NEAR>
 __device__ __forceinline__ void scan_step(ScanReader &br, ScanState &s, uint32_t limit, uint16_t *&cp,
 					  uint32_t pblock, const uint16_t *sel13, const uint8_t *kstep)
 {
@@ -298,11 +297,13 @@ __device__ __forceinline__ void scan_step(ScanReader &br, ScanState &s, uint32_t
 	const uint32_t es = sel13[w & 0x1FFFu];
 	const uint32_t ek = kstep[s.kbase + umin32(s.rem, 7u) * 256u + (w & 255u)];
 	const uint32_t adv_s = es & 511u, hi7 = es >> 9, rem_s = hi7 & 15u;
-	const bool run = !s.done;
+	const bool run = s.st == SCAN_RUNNING;
 	/* selector: GET_BITS_EXPECT_EOF decode.c:496, then f_bad decode.c:190-194 */
-	const bool eof = run && at_sel && (s.P + 5u > limit);
-	const bool bad = run && at_sel && !eof && hi7 == 0x70u;
-	const bool go = run && !eof && !bad;
+	const bool sel_try = run && at_sel;
+	const bool eof = NEAR && sel_try && (s.P + 5u > limit);
+	const bool bad = sel_try && hi7 == 0x70u;
+	s.st = eof ? (int)SCAN_EOF : (bad ? -6 : s.st);
+	const bool go = s.st == SCAN_RUNNING;
 	const bool sel = go && at_sel;
 	if (sel)
 		*cp = (uint16_t)(s.P - pblock);
@@ -318,10 +319,9 @@ __device__ __forceinline__ void scan_step(ScanReader &br, ScanState &s, uint32_t
 	s.P += step;
 	br.consume(step, cand);
 	const bool fin = go && (s.rem | s.pend) == 0u;
-	const bool over = fin && s.P > limit; /* a GET_BITS inside the payload ran dry: decode.c:146-152 */
+	const bool over = NEAR && fin && s.P > limit; /* a GET_BITS inside the payload ran dry: decode.c:146-152 */
 	s.col = over ? s.col - 1u : s.col;    /* its selector was consumed, its payload did not complete */
-	s.status = eof ? (int)SCAN_EOF : (bad ? -6 : (over ? -7 : s.status));
-	s.done = s.done || eof || bad || over || (fin && s.col == (uint32_t)COLS);
+	s.st = over ? -7 : ((fin && s.col == (uint32_t)COLS) ? (int)SCAN_OK : s.st);
 }
 
 __device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P, uint32_t limit,
@@ -333,26 +333,32 @@ __device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P
 	uint16_t *cp = coloff;
 	s.P = P;
 	s.rem = s.pend = s.col = s.kbase = 0;
-	s.status = SCAN_OK;
-	s.done = !active;
+	s.st = active ? (int)SCAN_RUNNING : (int)SCAN_OK;
 	r.val = 0;
 	if (active) {
 		if (P + 20 > limit) { /* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
-			s.status = SCAN_EOF;
-			s.done = true;
+			s.st = SCAN_EOF;
 		} else {
 			r.val = (int)((br.peek() >> 4) & 0xFFFFu);
 			s.P = P + 20;
 			br.consume(20u, br.next_word());
 		}
 	}
-	while (__any_sync(0xFFFFFFFFu, !s.done)) {
+	while (__any_sync(0xFFFFFFFFu, s.st == SCAN_RUNNING)) {
 		br.topup();
+		/* SCAN_PERIOD steps move at most 32*SCAN_PERIOD bits; +13 for the lookup window */
+		const bool near = s.st == SCAN_RUNNING && s.P + 32u * SCAN_PERIOD + 16u > limit;
+		if (__any_sync(0xFFFFFFFFu, near)) {
 #pragma unroll
-		for (int k = 0; k < SCAN_PERIOD; k++)
-			scan_step(br, s, limit, cp, P, sel13, kstep);
+			for (int k = 0; k < SCAN_PERIOD; k++)
+				scan_step<true>(br, s, limit, cp, P, sel13, kstep);
+		} else {
+#pragma unroll
+			for (int k = 0; k < SCAN_PERIOD; k++)
+				scan_step<false>(br, s, limit, cp, P, sel13, kstep);
+		}
 	}
-	r.status = s.status;
+	r.status = s.st;
 	r.ncols = s.col;
 	r.end = s.P;
 	return r;
@@ -578,7 +584,9 @@ juggle_and_store(uint32_t *xs, uint32_t *gh, bool first, int lane, int val, uint
 				if (w == 3) {
 					const int q = (t - 64) >> 3;
 					if (full) {
-						dst[q] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+						/* streaming store: PCM is written once and must not evict the
+						 * L2-resident history and the compressed bytes still to be staged */
+						__stcs(dst + q, make_uint4(pk[0], pk[1], pk[2], pk[3]));
 					} else {
 						/* last block of a stream: word-granular tail */
 						uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + q);
@@ -805,7 +813,12 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 				if (!ok || bad || last) {
 					/* finalise: results + zero padding of the undelivered tail */
 					uint8_t *p0 = a.out + d.out_off + (size_t)pos * a.fmt.wordlen;
-					size_t nb = d.pad_words > pos ? (size_t)(d.pad_words - pos) * a.fmt.wordlen : 0;
+					/* up to the 16-byte boundary that ends this stream's slot (out_off is 16-byte
+					 * aligned), so that alignment gaps never carry stale bytes */
+					size_t nb = d.pad_words >= pos && d.pad_words
+							    ? (((size_t)d.pad_words * a.fmt.wordlen + 15u) & ~(size_t)15u) -
+								      (size_t)pos * a.fmt.wordlen
+							    : 0;
 					for (size_t i = lane; i < nb; i += 32)
 						p0[i] = 0;
 					__syncwarp();

@@ -147,7 +147,11 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 		/* zero padding of the undelivered tail (acmtool.c:293-310) */
 		{
 			uint8_t *p = out + (size_t)pos * a.fmt.wordlen;
-			size_t nbytes = d.pad_words > pos ? (size_t)(d.pad_words - pos) * a.fmt.wordlen : 0;
+			/* up to the 16-byte boundary that ends this stream's slot: no stale bytes in the gaps */
+			size_t nbytes = d.pad_words >= pos && d.pad_words
+						? (((size_t)d.pad_words * a.fmt.wordlen + 15u) & ~(size_t)15u) -
+							  (size_t)pos * a.fmt.wordlen
+						: 0;
 			for (size_t i = tid; i < nbytes; i += GEN_THREADS)
 				p[i] = 0;
 		}

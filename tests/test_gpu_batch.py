@@ -121,3 +121,23 @@ def test_fallout_batch_checksums_and_roundtrip_properties(checker):
     s2, _ = gu.decode_device([imgs[i] for i in perm], want_checksums=1)
     assert np.array_equal(s2["checksum"], s["checksum"][perm])
     assert np.all(s["status"] == 0) and np.array_equal(s["words"], s["total_values"])
+
+
+def test_host_path_segmented_pipeline_matches_resident(checker):
+    """A batch large enough (>= 32 MB of PCM) for acm_gpu_decode_batch to cut it into segments
+    whose copy-in / decode / copy-out overlap: same bytes as the single-launch resident path."""
+    imgs = corpus.images(corpus.fallout_params(420, seed=21) + corpus.stress_params(max_values=20_000)[::11])
+    s1, out1 = gu.decode_host(imgs, want_checksums=1)
+    s2, out2 = gu.decode_device(imgs, want_checksums=1)
+    assert out1.size >= (32 << 20)
+    assert np.array_equal(s1["status"], s2["status"]) and np.array_equal(s1["words"], s2["words"])
+    assert np.array_equal(s1["checksum"], s2["checksum"])
+    for i in range(len(imgs)):
+        o, nb = int(s1["out_off"][i]), int(s1["total_values"][i]) * 2
+        assert np.array_equal(out1[o:o + nb], out2[o:o + nb]), i
+        gap = out1[o + nb:o + ((nb + 15) & ~15)]
+        assert not gap.any()            # alignment gaps are zeroed by the kernels, never stale
+    assert gu.compare(imgs[::37], s1[::37], out1, checker, checksums=True) == []
+    # second call reuses the cached workspace
+    s3, out3 = gu.decode_host(imgs[:200], want_checksums=1)
+    assert np.array_equal(s3["checksum"], s1["checksum"][:200])
