@@ -58,7 +58,7 @@ constexpr int COLS = 128;
 constexpr int ROWS = 16;
 constexpr int BLEN = COLS * ROWS;        /* 2048 */
 constexpr int NSCAN = 2;                 /* scan warps */
-constexpr int W = 13;                    /* worker warps; 15 warps = 480 threads -> 128 regs/thread */
+constexpr int W = 14;                    /* worker warps; 16 warps = 512 threads -> 128 regs/thread */
 constexpr int S = 32 * NSCAN;            /* stream slots per CTA */
 constexpr int THREADS = 32 * (W + NSCAN);
 constexpr int OFF_PITCH = S + 2;         /* u16 per column row of the offset table (bank spread) */
