@@ -95,7 +95,7 @@ struct Smem {
 	Entry ent[2][S];
 	unsigned long long cks[S];
 	uint32_t pos[S];
-	uint32_t dead[S];
+	uint32_t dead[2][S];         /* [round parity][slot]: desc+1 of a stream a worker finalised early */
 	uint32_t info[32];
 	uint16_t t[ACM_T_SIZE];
 	int more[2][NSCAN];
@@ -625,7 +625,8 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 	if (tid < 32)
 		sm.info[tid] = make_info(a.tables->kind[tid]);
 	for (int i = tid; i < S; i += THREADS) {
-		sm.dead[i] = 0;
+		sm.dead[0][i] = 0;
+		sm.dead[1][i] = 0;
 		sm.pos[i] = 0;
 		sm.cks[i] = 0ull;
 	}
@@ -653,7 +654,8 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 			e.pblock = 0; e.pend = 0; e.desc = 0; e.blk = 0; e.ncols = 0; e.val = 0; e.pad = 0;
 			if (warp == W && lane == 0)
 				sm.next_slot[buf] = 0; /* the workers drain this queue next round */
-			if (active && sm.dead[myslot] == cur + 1u)
+			/* written by a worker in the previous round (other parity: no concurrent writer) */
+			if (active && sm.dead[buf ^ 1][myslot] == cur + 1u)
 				active = false; /* a worker found a corrupt t-code: abandon the stream */
 			if (!active) {
 				uint32_t idx = atomicAdd(a.counter, 1u);
@@ -727,12 +729,11 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					if (lane == 0) {
 						sm.pos[slot] = 0u;
 						sm.cks[slot] = 0ull;
-						sm.dead[slot] = 0u;
 					}
 					__syncwarp();
 				}
-				if (sm.dead[slot] == e.desc + 1u)
-					continue; /* stream already finalised by a corrupt code */
+				if (sm.dead[0][slot] == e.desc + 1u || sm.dead[1][slot] == e.desc + 1u)
+					continue; /* stream already finalised by a corrupt code (descriptor ids are unique) */
 				const uint32_t limit_w = d.file_end + 8u;
 				const bool ok = e.status == SCAN_OK;
 				const uint32_t ncheck = ok ? (uint32_t)COLS : e.ncols + (e.status == -7 ? 1u : 0u);
@@ -826,7 +827,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 						a.status[d.index] = st;
 						a.words[d.index] = pos;
 						a.cks[d.index] = a.fmt.checksums ? sm.cks[slot] : 0ull;
-						sm.dead[slot] = e.desc + 1u;
+						sm.dead[buf][slot] = e.desc + 1u;
 					}
 				}
 				__syncwarp();
