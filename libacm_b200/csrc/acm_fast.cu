@@ -228,16 +228,14 @@ struct ScanReader {
 	}
 };
 
-/* Worker view of the staged block: stream words [w_lo, w_lo + n) in shared memory, EOF
- * already patched in at staging time; anything outside reads as zero. */
+/* Worker view of the staged block: stream words [w_lo, ...) in shared memory, EOF already
+ * patched in at staging time.  No bounds check: the staging area (STAGE_BYTES = 4608) always
+ * holds the whole block (<= 33 428 bits) plus the 96 bits the decoders read ahead, and for a
+ * block that failed in the scan the walk stopped at most 261 bits past the stream's limit. */
 struct StageReader {
 	const uint32_t *st;
-	uint32_t w_lo, n;
-	__device__ __forceinline__ uint32_t word(uint32_t i) const
-	{
-		const uint32_t k = i - w_lo;
-		return k < n ? st[k] : 0u;
-	}
+	uint32_t w_lo;
+	__device__ __forceinline__ uint32_t word(uint32_t i) const { return st[i - w_lo]; }
 };
 
 /* ------------------------------------------------------------------ scan */
@@ -413,17 +411,21 @@ __device__ __forceinline__ int unpack_column(const StageReader &sr, uint32_t P, 
 			const unsigned long long win =
 				(unsigned long long)__funnelshift_r(w0, w1, sh) |
 				((unsigned long long)__funnelshift_r(w1, w2, sh) << 32);
+			/* codes the reference gets to read before the stream runs dry: all of them,
+			 * except in the last block of a truncated stream */
+			const uint32_t nread = P + ncodes * width <= limit ? ncodes : (limit > P ? (limit - P) / width : 0u);
+			uint32_t seen = 0u;
 #pragma unroll
 			for (int q = 0; q < 8; q++) {
 				if ((uint32_t)q < ncodes) {
 					const uint32_t e = tab[(uint32_t)(win >> (q * width)) & cmask];
-					if (P + (q + 1) * width <= limit && (e & 0x8000u))
-						bad = 1;
+					seen |= (uint32_t)q < nread ? e : 0u;
 					const unsigned long long vv = (unsigned long long)(e & vmask) << (4u * q * per);
 					a0 |= (uint32_t)vv;
 					a1 |= (uint32_t)(vv >> 32);
 				}
 			}
+			bad = (seen & 0x8000u) != 0u;
 		}
 #pragma unroll
 		for (int r = 0; r < ROWS; r++)
@@ -770,7 +772,6 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast_kernel(KernelArgs 
 					StageReader sr;
 					sr.st = stage;
 					sr.w_lo = c_lo * 4u;
-					sr.n = (c_hi - c_lo) * 4u;
 					/* ---- unpack: lane = column */
 					const uint16_t *offs = sm.coloff[pb] + slot;
 #pragma unroll 1
@@ -857,27 +858,27 @@ cudaError_t launch_fast(const KernelArgs &a, int n_ctas, cudaStream_t st)
 {
 	if (a.count == 0)
 		return cudaSuccess;
-	static bool configured[2] = { false, false };
+	/* the opt-in shared-memory size is a per-device function attribute */
+	static bool configured[2][64] = {};
 	const size_t smem = sizeof(fast::Smem);
-	if (a.fmt.checksums) {
-		if (!configured[1]) {
-			cudaError_t e = cudaFuncSetAttribute(fast::acm_decode_fast_kernel<true>,
-							     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e != cudaSuccess)
-				return e;
-			configured[1] = true;
-		}
-		fast::acm_decode_fast_kernel<true><<<n_ctas, fast::THREADS, smem, st>>>(a);
-	} else {
-		if (!configured[0]) {
-			cudaError_t e = cudaFuncSetAttribute(fast::acm_decode_fast_kernel<false>,
-							     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e != cudaSuccess)
-				return e;
-			configured[0] = true;
-		}
-		fast::acm_decode_fast_kernel<false><<<n_ctas, fast::THREADS, smem, st>>>(a);
+	const int v = a.fmt.checksums ? 1 : 0;
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (!configured[v][dev & 63]) {
+		e = v ? cudaFuncSetAttribute(fast::acm_decode_fast_kernel<true>,
+					     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+		      : cudaFuncSetAttribute(fast::acm_decode_fast_kernel<false>,
+					     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+		configured[v][dev & 63] = true;
 	}
+	if (v)
+		fast::acm_decode_fast_kernel<true><<<n_ctas, fast::THREADS, smem, st>>>(a);
+	else
+		fast::acm_decode_fast_kernel<false><<<n_ctas, fast::THREADS, smem, st>>>(a);
 	return cudaGetLastError();
 }
 

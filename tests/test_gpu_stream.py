@@ -192,3 +192,38 @@ def test_open_file_and_strerror(libs, tmp_path):
         assert L.acm_open_file(C.byref(s), b"/nonexistent/file.acm", 0) == -2
         outs.append(tuple(L.acm_strerror(e) for e in range(1, -11, -1)))
     assert outs[0] == outs[2] and outs[1] == outs[3]
+
+
+@pytest.mark.parametrize("level,rows", [(7, 16), (10, 2)])
+def test_config5_full_size_long_stream(libs, level, rows):
+    """BASELINE configs[4] at full size: >= 5 min of 44 100 Hz stereo (26.46 M words), read with 4 KiB
+    buffers around every seek target, formats s16le/s16be/u16le/u16be, forward and backward seeks."""
+    total = 44100 * 2 * 300 + 2
+    img = gen.make_stream(level=level, rows=rows, channels=2, rate=44100, total_values=total, seed=100 + level)
+    a, b = _pair(libs, img)
+    assert a.err == b.err == 0 and a.getters() == b.getters()
+    pcm_total = b.getters()["pcm_total"]
+    assert pcm_total >= 44100 * 300
+    fmts = [(0, 1), (1, 1), (0, 0), (1, 0)]
+    targets = [0, 5, pcm_total // 3, pcm_total // 2, pcm_total - 1, pcm_total, pcm_total + 100,
+               pcm_total // 2 + 7, 5, pcm_total // 3, 0]
+    for k, t in enumerate(targets):
+        assert a.seek(t) == b.seek(t), t
+        be, sg = fmts[k % 4]
+        for _ in range(6):
+            x, y = a.read(4096, be=be, sgned=sg), b.read(4096, be=be, sgned=sg)
+            assert x == y, (t, be, sg)
+        x, y = a.read(64, be=be, sgned=sg), b.read(64, be=be, sgned=sg)
+        assert x == y
+        x, y = a.read(1024, loop=True), b.read(1024, loop=True)
+        assert x == y
+        assert a.state()["stream_pos"] == b.state()["stream_pos"]
+    # a long sequential run through acm_read_loop, then to the very end
+    assert a.seek(pcm_total - 300_000) == b.seek(pcm_total - 300_000)
+    while True:
+        x, y = a.read(65536, loop=True), b.read(65536, loop=True)
+        assert x == y
+        if x[0] <= 0:
+            break
+    assert a.getters()["pcm_tell"] == b.getters()["pcm_tell"] == pcm_total
+    a.close(), b.close()

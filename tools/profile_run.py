@@ -19,9 +19,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--streams", type=int, default=2000)
 ap.add_argument("--runs", type=int, default=2)
 ap.add_argument("--kernel", type=int, default=0)
+ap.add_argument("--workload", default="config2")
 args = ap.parse_args()
 
-blob, offs, lens = bench.build_corpus(args.streams, 0)
+blob, offs, lens = bench.build_corpus(args.streams, 0, workload=args.workload)
 opts = api.make_opts(device=0, kernel=args.kernel)
 s = api.new_streams(offs, lens)
 d_blob = torch.from_numpy(blob).cuda()
