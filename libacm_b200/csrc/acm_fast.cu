@@ -69,7 +69,8 @@ constexpr int STAGE_BYTES = (BLEN + 4 * 32 - X0_WORDS) * 4; /* 4608: a whole blo
 constexpr int STAGE_CHUNKS = STAGE_BYTES / 16;
 constexpr int RING_WORDS = 64;           /* 16 chunks of 16 bytes per scan lane */
 constexpr int RING_LEAD = 8;             /* chunks kept ahead of the read position */
-constexpr int SCAN_PERIOD = 4;           /* walk iterations between two ring top-ups (<= 16 bytes consumed) */
+constexpr int SCAN_UNROLL = 4;           /* unrolled walk steps (keeps the loop body inside the L0 I-cache) */
+constexpr int SCAN_PERIOD = 8;           /* walk steps between two ring top-ups (<= 32 bytes consumed) */
 constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [128,192) X2 tail [192,256) */
 
 enum { ENT_IDLE = -100 };
@@ -127,12 +128,13 @@ __device__ __forceinline__ void prefetch_l1(const void *p)
  * the top of every iteration; when fewer remain, ring word `widx` (read unconditionally
  * at the top of the iteration, next to the table lookups) is spliced in above them.
  *
- * topup() runs for all lanes together every SCAN_PERIOD iterations: it stores the 16-byte
- * chunk requested by the previous top-up into the ring -- zeroing everything at and past
- * the end of the file, which is the reference's "one zero byte, then nothing"
- * (decode.c:57-61) -- and requests the next one while fewer than RING_LEAD chunks are ahead
- * of the read position.  SCAN_PERIOD iterations consume at most 16 bytes = the chunk a
- * top-up can add, so the ring never runs dry and nothing ever waits on a load.
+ * topup() runs for all lanes together every SCAN_PERIOD iterations: it stores the (at most
+ * two) 16-byte chunks requested by the previous top-up into the ring -- zeroing everything
+ * at and past the end of the file, which is the reference's "one zero byte, then nothing"
+ * (decode.c:57-61) -- and requests the next ones so that RING_LEAD chunks stay ahead of
+ * the read position.  SCAN_PERIOD iterations consume at most 32 bytes = the two chunks a
+ * top-up can add, so the ring never runs dry; the ~1500+ cycles between two top-ups cover a
+ * scattered load that misses to DRAM, so nothing waits on a load either.
  */
 struct ScanReader {
 	const uint4 *base16;  /* stream base (16-byte aligned) */
@@ -142,8 +144,8 @@ struct ScanReader {
 	uint32_t lo, mid, hi, avail; /* bits [0, avail) of hi:mid:lo are the stream at the read position */
 	uint32_t widx;        /* stream word that will be spliced in next */
 	uint32_t fill;        /* chunks stored so far = index of the next chunk to store */
-	uint32_t npend;       /* chunks requested at the last top-up (0..1) */
-	uint4 pa;
+	uint32_t npend;       /* chunks requested at the last top-up (0..2) */
+	uint4 pa, pb;
 
 	__device__ __forceinline__ uint4 load_chunk(uint32_t c) const
 	{
@@ -178,7 +180,7 @@ struct ScanReader {
 		avail = 96;
 		fill = 0x40000000u; /* never asks for data */
 		npend = 0;
-		pa = make_uint4(0u, 0u, 0u, 0u);
+		pa = pb = make_uint4(0u, 0u, 0u, 0u);
 	}
 	/* new stream: fill the ring synchronously once, position the window on bit P0 */
 	__device__ __forceinline__ void start(const uint8_t *src, uint64_t room, uint32_t file_end, uint32_t P0)
@@ -203,12 +205,17 @@ struct ScanReader {
 	}
 	__device__ __forceinline__ void topup()
 	{
-		if (npend)
+		if (npend >= 1)
 			store_chunk(fill, pa);
+		if (npend >= 2)
+			store_chunk(fill + 1, pb);
 		fill += npend;
-		npend = (widx >> 2) + RING_LEAD > fill ? 1u : 0u;
-		if (npend)
+		const int want = (int)((widx >> 2) + RING_LEAD) - (int)fill;
+		npend = want <= 0 ? 0u : (want >= 2 ? 2u : 1u);
+		if (npend >= 1)
 			pa = load_chunk(fill);
+		if (npend >= 2)
+			pb = load_chunk(fill + 1);
 	}
 	__device__ __forceinline__ uint32_t peek() const { return lo; }
 	__device__ __forceinline__ uint32_t next_word() const { return ring[widx & (RING_WORDS - 1)]; }
@@ -347,13 +354,19 @@ __device__ __forceinline__ ScanResult scan_block_flat(ScanReader &br, uint32_t P
 		/* SCAN_PERIOD steps move at most 32*SCAN_PERIOD bits; +13 for the lookup window */
 		const bool near = s.st == SCAN_RUNNING && s.P + 32u * SCAN_PERIOD + 16u > limit;
 		if (__any_sync(0xFFFFFFFFu, near)) {
+#pragma unroll 1
+			for (int h = 0; h < SCAN_PERIOD / SCAN_UNROLL; h++) {
 #pragma unroll
-			for (int k = 0; k < SCAN_PERIOD; k++)
-				scan_step<true>(br, s, limit, cp, P, sel13, kstep);
+				for (int k = 0; k < SCAN_UNROLL; k++)
+					scan_step<true>(br, s, limit, cp, P, sel13, kstep);
+			}
 		} else {
+#pragma unroll 1
+			for (int h = 0; h < SCAN_PERIOD / SCAN_UNROLL; h++) {
 #pragma unroll
-			for (int k = 0; k < SCAN_PERIOD; k++)
-				scan_step<false>(br, s, limit, cp, P, sel13, kstep);
+				for (int k = 0; k < SCAN_UNROLL; k++)
+					scan_step<false>(br, s, limit, cp, P, sel13, kstep);
+			}
 		}
 	}
 	r.status = s.st;
