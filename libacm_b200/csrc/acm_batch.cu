@@ -171,6 +171,7 @@ struct Segment {
 	uint64_t out_lo, out_hi;
 	int fast_ctas, gen_ctas;          /* grid sizes; segments may run concurrently, so each has */
 	size_t hist_off, scratch_off;     /* its own history / scratch region (offsets in words) */
+	size_t ring_off;                  /* block-record rings of the fast kernel (offset in bytes) */
 };
 
 struct acm_gpu_plan {
@@ -190,6 +191,9 @@ struct acm_gpu_plan {
 	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue; [4*nseg] error flag */
 	GenericScratch scratch;
 	uint32_t *d_hist;    /* fast kernel history, fast_ctas * fast_hist_words_per_cta() words */
+	uint8_t *d_ring;     /* fast kernel 2 block-record rings (inside d_ring_alloc) */
+	uint8_t *d_ring_alloc;
+	int fast_gen;        /* 2: acm_fast2.cu (default), 1: acm_fast.cu (opts->kernel == 2) */
 	int fast_ctas;
 	int generic_ctas;
 	int sm_count;
@@ -209,6 +213,7 @@ static void plan_free(acm_gpu_plan *p)
 	cudaFree(p->d_counters);
 	cudaFree(p->scratch.buf);
 	cudaFree(p->d_hist);
+	cudaFree(p->d_ring_alloc);
 	if (p->ev0)
 		cudaEventDestroy(p->ev0);
 	if (p->ev1)
@@ -255,6 +260,9 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	p->d_streams = nullptr; p->d_status = nullptr; p->d_words = nullptr; p->d_cks = nullptr;
 	p->d_tables = nullptr; p->d_counters = nullptr; p->ev0 = nullptr; p->ev1 = nullptr;
 	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
+	p->d_ring = nullptr;
+	p->d_ring_alloc = nullptr;
+	p->fast_gen = opts->kernel == 2 ? 1 : 2;
 	p->device = dev;
 	p->n = n;
 	p->n_fast = p->n_generic = 0;
@@ -377,15 +385,19 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	CU(cudaEventCreate(&p->ev1));
 
 	{
-		const uint64_t per = (uint64_t)fast_slots_per_cta();
+		const uint64_t per = (uint64_t)(p->fast_gen == 2 ? fast2_slots_per_cta() : fast_slots_per_cta());
+		const size_t hist_per_cta = p->fast_gen == 2 ? fast2_hist_words_per_cta() : fast_hist_words_per_cta();
 		const size_t stride = generic_scratch_words(max_blen, max_cols);
 		const size_t budget = ((size_t)4 << 30) / p->seg.size(); /* scratch bytes per segment */
-		size_t hist_words = 0, scratch_words = 0;
+		size_t hist_words = 0, scratch_words = 0, ring_bytes = 0;
 		for (Segment &sg : p->seg) {
 			uint64_t groups = (sg.n_fast + per - 1) / per;
 			sg.fast_ctas = (uint64_t)p->sm_count < groups ? p->sm_count : (int)groups;
 			sg.hist_off = hist_words;
-			hist_words += (size_t)sg.fast_ctas * fast_hist_words_per_cta();
+			hist_words += (size_t)sg.fast_ctas * hist_per_cta;
+			sg.ring_off = ring_bytes;
+			if (p->fast_gen == 2)
+				ring_bytes += (size_t)sg.fast_ctas * fast2_ring_bytes_per_cta();
 			int ctas = p->sm_count * 4;
 			if ((uint64_t)ctas > sg.n_gen)
 				ctas = (int)sg.n_gen;
@@ -399,6 +411,21 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		}
 		if (max_fast)
 			CU(cudaMalloc(&p->d_hist, hist_words * 4 + 16));
+		if (max_fast && ring_bytes) {
+			/* the scan lanes advance only the low half of a record address (acm_fast2.cu):
+			 * place the rings so that they do not straddle a 4 GiB boundary */
+			CU(cudaMalloc(&p->d_ring_alloc, ring_bytes + 512));
+			uintptr_t lo = ((uintptr_t)p->d_ring_alloc + 255u) & ~(uintptr_t)255u;
+			if ((lo >> 32) != ((lo + ring_bytes) >> 32)) {
+				cudaFree(p->d_ring_alloc);
+				p->d_ring_alloc = nullptr;
+				CU(cudaMalloc(&p->d_ring_alloc, 2 * ring_bytes + 512));
+				lo = ((uintptr_t)p->d_ring_alloc + 255u) & ~(uintptr_t)255u;
+				if ((lo >> 32) != ((lo + ring_bytes) >> 32))
+					lo = ((lo + ring_bytes) >> 32) << 32;
+			}
+			p->d_ring = (uint8_t *)lo;
+		}
 		if (max_gen) {
 			p->scratch.stride = stride;
 			p->scratch.max_blen = max_blen;
@@ -437,6 +464,7 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 	a.tables = p->d_tables;
 	a.fmt = p->fmt;
 	a.hist = p->d_hist ? p->d_hist + sg.hist_off : nullptr;
+	a.ring = p->d_ring ? p->d_ring + sg.ring_off : nullptr;
 	a.resume_hist = nullptr;
 	a.resume_stride = 0;
 	a.end_pos = nullptr;
@@ -444,7 +472,10 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 		a.streams = p->d_streams + sg.fast_first;
 		a.count = (uint32_t)sg.n_fast;
 		a.counter = p->d_counters + 4 * g;
-		CU(launch_fast(a, sg.fast_ctas, st));
+		if (p->fast_gen == 2)
+			CU(launch_fast2(a, sg.fast_ctas, st));
+		else
+			CU(launch_fast(a, sg.fast_ctas, st));
 	}
 	if (sg.n_gen) {
 		GenericScratch sc = p->scratch;

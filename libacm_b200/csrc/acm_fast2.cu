@@ -1,0 +1,922 @@
+/*
+ * acm_fast2.cu -- the throughput kernel for the common block shape: level 7 (128 columns),
+ * 16 rows, 2048 words per block (the shape of BASELINE configs 1, 2, 4), second generation.
+ *
+ * What bounds this path: a stream's bitstream is serial -- where column
+ * c+1 starts is only known once column c has been walked -- so the makespan of a
+ * batch is at least (blocks of the longest stream) x (walk steps per block) x (latency of one
+ * step).  Everything else is parallel and has to keep up with the walk.  Hence:
+ *
+ *  - SCAN warps (the two highest warp ids of the CTA: the SM's warp arbiter prefers high warp
+ *    ids, so the latency-critical walk issues first) walk column LENGTHS only, one stream per
+ *    lane (64 stream slots per CTA).  A step is: fetch the 32 bits at bit position P from the
+ *    lane's shared-memory ring (two conflict-free LDS + one funnel shift), one table lookup
+ *    (sel13: selector + first prefix-code step, or the whole advance of a fixed-size column;
+ *    kstep: one further prefix-code step with the row cap folded in), P += advance.  Every
+ *    update is a select on the lane's state, so the 32 lanes run ONE instruction stream
+ *    however their column types differ.  The ring (128 words per lane, word-interleaved across
+ *    lanes) is filled with 4-byte cp.async copies issued for all lanes at the same time every
+ *    SCAN_PERIOD steps and awaited one period later, so no step ever waits on global memory;
+ *    the end-of-file rule (one zero byte, decode.c:57-61) is the zero-fill of cp.async's
+ *    src-size operand.
+ *  - The scan is DECOUPLED from the decode: every walked block becomes a 288-byte record (128
+ *    column offsets + header facts) in a per-slot ring of RING_D records in global memory (L2
+ *    resident), published through a shared-memory counter.  Scan lanes run up to RING_D blocks
+ *    ahead of the decode, so neither side waits for the other at a per-round barrier: the
+ *    kernel's time is max(longest walk, decode throughput), not their sum.
+ *  - WORKER warps claim a slot that has records pending, and decode its blocks in order:
+ *      stage    the block's compressed bytes (<= 4.2 KB) into shared memory, coalesced;
+ *      sort     the 128 columns by filler class (ballot + popc) into per-class work lists, so
+ *               that every unpack pass runs one straight-line routine on 32 busy lanes;
+ *      unpack   prefix-coded columns: 96-bit shift register, one 64-bit table entry per step
+ *               (up to 8 values + bit and row counts), 16 nibbles accumulated in two registers,
+ *               no row cap (rows past the 16th shift out); radix-coded columns: all codes from
+ *               one 64-bit window; linear columns: sliding window.  A column leaves as sixteen
+ *               int16 indices in two 128-bit shared-memory stores (48-byte column pitch:
+ *               conflict-free for the transform's 128-bit loads);
+ *      juggle   dequantise (idx*val) on load; lifting stages 1-2 (C=64,32) in registers with
+ *               lane j owning every word m = j mod 32; one transpose through shared memory;
+ *               stages 3-7 (C=16..1) in registers over a recomputed 62-word halo;
+ *      output   >>7, low 16 bits, byte order / sign bias folded into one PRMT (+LOP), eight
+ *               128-bit streaming stores per lane: the block leaves as 4 KiB of PCM.
+ *    The reference's wrapbuf (decode.c:803, 2*cols-2 = 254 words) is 256 words of per-slot
+ *    history (last 128 X0, 64 X1, 64 X2 words) in an L2-resident global array.
+ *  - Streams are handed out by an atomic cursor in longest-first order.
+ *
+ * Bit-exactness: same arithmetic as the generic kernel (uint32 wrap-around, arithmetic shift,
+ * truncation), same table-driven symbol decode, same status rules.
+ */
+#include "acm_fast2_core.cuh"
+#include "acm_kernels.cuh"
+
+namespace acm {
+
+namespace fast2 {
+
+constexpr int LEVEL = 7;
+constexpr int COLS = 128;
+constexpr int BLEN = COLS * ROWS;        /* 2048 */
+constexpr int NSCAN = 2;                 /* scan warps (the highest warp ids) */
+constexpr int W = 14;                    /* worker warps */
+constexpr int S = 32 * NSCAN;            /* stream slots per CTA */
+constexpr int THREADS = 32 * (W + NSCAN);
+constexpr int RING_D = 8;                /* block records a scan lane may be ahead of the decode */
+constexpr int REC_BYTES = 288;           /* 128 x u16 column offsets + 32-byte Rec */
+constexpr int RW = 64;                   /* ring words per scan lane (+3 duplicates of words 0..2) */
+constexpr int LEAD = 14;                 /* 16-byte chunks requested ahead of the read position */
+constexpr int SCAN_PERIOD = 16;          /* walk steps between two top-ups */
+constexpr int XPRE = 68;                 /* chunk -1: the previous block's last 64 X2 words (+4 pad) */
+constexpr int XWORDS = XPRE + BLEN + 4 * 32; /* transpose layout: 4 pad words per 64 */
+constexpr int CPITCH = 8;                /* words per unpacked column (16 x int16), halves swizzled */
+constexpr int X0_W = COLS * CPITCH;      /* 1024 */
+constexpr int STAGE_W = 1088;            /* 4352 bytes: a whole block (<= 4179 B) + alignment + read-ahead */
+constexpr int LIST_W = 256;              /* listA (k from the front, t from the back), listB (linear) */
+constexpr int WB_WORDS = X0_W + STAGE_W + LIST_W;
+constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [128,192) X2 tail [192,256) */
+constexpr int KMAX = 4;                  /* blocks a worker decodes per slot claim */
+
+static_assert(WB_WORDS >= XWORDS, "transform layout must fit the worker buffer");
+
+
+struct Rec {
+	uint32_t pblock; /* P of the block header */
+	uint32_t pend;   /* P where the scan stopped (block end when status == SCAN_OK) */
+	uint32_t desc;   /* index into the kernel's descriptor slice */
+	uint32_t blk;    /* block number, bit 31 = last record of the stream */
+	int32_t status;  /* SCAN_OK / SCAN_EOF / ACM_ERR_* */
+	uint32_t ncols;
+	int32_t val;
+	uint32_t pad;
+};
+
+struct Smem {
+	uint64_t k8w[ACM_K8_SIZE];
+	uint16_t uni16[ACM_UNI_PAGES * 128];
+	uint32_t nib2w[256];
+	uint32_t ring[NSCAN][(RW + 3) * 32]; /* [word][lane] */
+	uint32_t wb[W][WB_WORDS];
+	unsigned long long cks[S];
+	uint32_t prod[S];  /* records published per slot (scan lane writes) */
+	uint32_t cons[S];  /* records consumed per slot (owning worker writes) */
+	uint32_t busy[S];  /* slot claimed by a worker */
+	uint32_t pos[S];   /* words delivered so far of the slot's current stream */
+	uint32_t dead[S];  /* desc+1 of a stream a worker finalised early */
+	uint32_t info[32];
+	uint16_t t[ACM_T_SIZE];
+	uint32_t scan_done;
+};
+
+/* ------------------------------------------------------------------ helpers */
+
+__device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
+{
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+		     : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async4z(uint32_t saddr, const void *g, uint32_t n)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t vol_ld(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void vol_st(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+/* selector facts: bit 16 prefix-coded (k), bit 17 bad, bit 18 t, bit 19 linear, bits 20..23 sub-type */
+enum { INF_K = 1u << 16, INF_BAD = 1u << 17, INF_T = 1u << 18, INF_LIN = 1u << 19 };
+
+__device__ __forceinline__ uint32_t make_info(uint32_t kind)
+{
+	const uint32_t cls = kind & 7u, sub = kind >> 3;
+	uint32_t v = sub << 20;
+	if (cls == ACM_CLS_LINEAR)
+		v |= INF_LIN;
+	else if (cls == ACM_CLS_T)
+		v |= INF_T;
+	else if (cls == ACM_CLS_K)
+		v |= INF_K;
+	else if (cls == ACM_CLS_BAD)
+		v |= INF_BAD;
+	return v;
+}
+
+/* ------------------------------------------------------------------ scan */
+
+/*
+ * A scan lane's view of its stream: RW ring words in shared memory, word i of the stream
+ * (32-bit words from the 16-byte aligned stream base) at ring[(i % RW) * 32 + lane], plus a
+ * copy of ring word 0 at index RW so that the pair (i, i+1) is always (slot, slot + 32).
+ * Chunks (16 bytes) [.., fill) have been requested; words [.., ready_w) have landed.
+ */
+struct ScanRing {
+	uint32_t saddr;       /* shared-space address of this lane's ring word 0 */
+	const uint32_t *rw;   /* the same, generic */
+	const uint8_t *base;  /* stream base (16-byte aligned) */
+	uint32_t room16;      /* 16-byte chunks readable at base */
+	uint32_t fe_byte;     /* bytes of the stream that exist (relative to base) */
+	uint32_t fill, fill_prev, ready_w;
+
+	__device__ __forceinline__ void idle()
+	{
+		base = nullptr;
+		room16 = 0;
+		fe_byte = 0;
+		fill = fill_prev = 0x0FFFFFF0u; /* never asks for data */
+		ready_w = 0;
+	}
+	__device__ __forceinline__ void start(const uint8_t *src, uint64_t room, uint32_t file_end, uint32_t P0)
+	{
+		cp_async_wait_all(); /* copies of the slot's previous stream must not land after this one's */
+		base = src;
+		room16 = (uint32_t)(room >> 4);
+		fe_byte = file_end >> 3;
+		fill = fill_prev = P0 >> 7;
+		ready_w = 0; /* nothing readable yet: the lane idles until its first chunks land */
+	}
+	__device__ __forceinline__ void request(uint32_t c)
+	{
+		const uint32_t sa = saddr + ((c & (RW / 4 - 1)) << 9);
+		const uint8_t *g = base + (size_t)c * 16u;
+		if (c < room16 && c * 16u + 16u <= fe_byte) {
+			cp_async4(sa, g);
+			cp_async4(sa + 128, g + 4);
+			cp_async4(sa + 256, g + 8);
+			cp_async4(sa + 384, g + 12);
+			if ((c & (RW / 4 - 1)) == 0) {
+				cp_async4(saddr + RW * 128, g);
+				cp_async4(saddr + RW * 128 + 128, g + 4);
+				cp_async4(saddr + RW * 128 + 256, g + 8);
+			}
+		} else {
+			/* touches the end of the file (or of the blob): bytes at and past it read as zero,
+			 * which is the reference's "one zero byte, then nothing" (decode.c:57-61) */
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t at = c * 16u + 4u * k;
+				uint32_t n = 0;
+				if (c < room16 && at < fe_byte)
+					n = fe_byte - at < 4u ? fe_byte - at : 4u;
+				const void *src = n ? (const void *)(g + 4 * k) : (const void *)base;
+				cp_async4z(sa + 128 * k, src, n);
+				if (k < 3 && (c & (RW / 4 - 1)) == 0)
+					cp_async4z(saddr + RW * 128 + 128 * k, src, n);
+			}
+		}
+	}
+	/* all lanes together, every SCAN_PERIOD steps */
+	__device__ __forceinline__ void topup(uint32_t P)
+	{
+		const int want = (int)((P >> 7) + LEAD) - (int)fill;
+		const uint32_t f0 = fill;
+#pragma unroll 1
+		for (int j = 0; j < want; j++)
+			request(f0 + j);
+		fill = want > 0 ? f0 + want : f0;
+		cp_async_commit();
+		cp_async_wait1(); /* everything but the group just committed has landed */
+		ready_w = base ? fill_prev * 4u : 0u;
+		fill_prev = fill;
+	}
+};
+
+__device__ __forceinline__ void st_global_u16(uint32_t lo, uint32_t hi, uint32_t v)
+{
+	asm volatile("{\n\t.reg .b64 p;\n\tmov.b64 p, {%0, %1};\n\tst.global.u16 [p], %2;\n\t}" ::"r"(lo), "r"(hi),
+		     "h"((unsigned short)v)
+		     : "memory");
+}
+
+/*
+ * One walk step for all lanes of a scan warp.  The lane holds lo = the 32 stream bits at P, so
+ * the step's dependent chain is: one uni16 lookup with lo, then the next lo cut out of the four
+ * ring words at P (fetched at the top of the step, next to the lookup, not after it) at offset
+ * (P & 31) + advance.  That works for advances up to 64 bits; after a longer one (a wide linear
+ * column), at the start of a block, or when the words at P have not landed yet, the lane is
+ * STALE for one step: the lookup's result is ignored and lo is simply re-cut at P.  A stale step
+ * and a live step are the same instructions.  At a selector the column offset is noted; after
+ * the 128th column the lane moves to the HALT page (entries advance 0 bits and stay), which is
+ * also where finished and idle lanes sit.  No end-of-file checks here: bits past the end read
+ * as zero, and a block whose walk ends at or before the stream's limit cannot have read past
+ * it (the caller re-walks the rare other case with the reference's verdicts).  cp = low half
+ * of the global address of the next column offset (records do not straddle a 4 GiB boundary:
+ * see plan_create).
+ */
+__device__ __forceinline__ void fast_step(Walk &s, bool &stale, uint32_t &cp, uint32_t cph, uint32_t cpend,
+					  uint32_t pblock, const uint32_t *ringw, uint32_t ready_w,
+					  const unsigned char *uni)
+{
+	const uint32_t wi = s.P >> 5;
+	const uint32_t *rp = ringw + (wi & (RW - 1)) * 32u;
+	const uint32_t w0 = rp[0], w1 = rp[32], w2 = rp[64], w3 = rp[96];
+	const bool landed = wi + 4u <= ready_w;
+	const bool live = !stale;
+	if (live && s.msk == MSK_SEL) {
+		st_global_u16(cp, cph, s.P - pblock);
+		cp += 2u;
+	}
+	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s));
+	const uint32_t adv = live ? (e & 0xFFu) : 0u;
+	const uint32_t sh = (s.P & 31u) + adv;
+	const uint32_t f0 = fsr(w0, w1, sh), f1 = fsr(w1, w2, sh), f2 = fsr(w2, w3, sh);
+	s.lo = sh < 32u ? f0 : (sh < 64u ? f1 : f2);
+	s.P += adv;
+	if (live) {
+		walk_next(s, e);
+		if (s.s8 == 0u && cp == cpend) {
+			s.s8 = UNI_HALT8;
+			s.msk = MSK_K;
+		}
+	}
+	stale = !(landed && adv <= 64u);
+}
+
+/* ------------------------------------------------------------------ unpack */
+
+struct Stage {
+	const uint32_t *st;
+	uint32_t w_lo;
+	__device__ __forceinline__ uint32_t word(uint32_t i) const { return st[i - w_lo]; }
+};
+
+/* where column c's two halves live: 8 words per column, the halves swapped for columns with
+ * bit 2 set, so that the transform's 128-bit loads (lane = column mod 32) are conflict-free */
+__device__ __forceinline__ ColOut col_out(uint32_t *wb, uint32_t c)
+{
+	ColOut o;
+	const uint32_t swz = (c >> 2) & 1u;
+	o.h0 = wb + c * CPITCH + 4u * swz;
+	o.h1 = wb + c * CPITCH + 4u * (swz ^ 1u);
+	return o;
+}
+
+/* ------------------------------------------------------------------ transform + output */
+
+__device__ __forceinline__ uint32_t lift(uint32_t a, uint32_t p1, uint32_t p2, bool odd)
+{
+	/* decode.c:518-519 */
+	uint32_t s = a + p2;
+	return odd ? 2u * p1 - s : 2u * p1 + s;
+}
+
+/* pack two results into one 32-bit word of 16-bit PCM: (v >> 7) low 16 bits each */
+__device__ __forceinline__ uint32_t pack2(uint32_t a, uint32_t b, uint32_t sel, uint32_t flip)
+{
+	uint32_t lo = (uint32_t)((int32_t)a >> LEVEL); /* bytes 0,1 wanted */
+	uint32_t hi = b << (16 - LEVEL);               /* bytes 2,3 wanted */
+	return __byte_perm(lo, hi, sel) ^ flip;
+}
+
+/*
+ * Transform + output of one block by one warp.  wb[0 .. X0_W) holds the unpacked columns
+ * (column c: sixteen int16 at words [8c, 8c+8), see col_out); val is the block's multiplier; gh is the
+ * slot's history in global memory (first == true: all-zero history, decode.c:812).
+ * n = words to emit (<= 2048).  Returns this lane's checksum contribution.
+ */
+template <bool CKS>
+__device__ __forceinline__ unsigned long long
+juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint8_t *out, uint32_t pos0,
+		 uint32_t n, const Format fmt)
+{
+	uint32_t *xs = wb + XPRE;
+	uint32_t x[64];
+	unsigned long long cks = 0ull;
+
+	/* history of the previous block (L2 resident; .cg: never a stale L1 line) */
+	uint32_t hx[4], hy[2], hz[2];
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		hx[k] = first ? 0u : __ldcg(gh + 32 * k + lane);       /* X0[-128 + 32k + lane] */
+	hy[0] = first ? 0u : __ldcg(gh + 128 + lane);               /* X1[-64 + lane] */
+	hy[1] = first ? 0u : __ldcg(gh + 160 + lane);               /* X1[-32 + lane] */
+	hz[0] = first ? 0u : __ldcg(gh + 192 + lane);               /* X2[-64 + lane] */
+	hz[1] = first ? 0u : __ldcg(gh + 224 + lane);               /* X2[-32 + lane] */
+
+	/* ---- dequantise (decode.c:174-177, :591-600) and stages 1, 2 in registers:
+	 * lane owns m = 32*i + lane = row i/4, column 32*(i%4) + lane */
+#pragma unroll
+	for (int p = 0; p < 4; p++) {
+		const uint32_t swz = ((uint32_t)lane >> 2) & 1u;
+		const uint32_t *c = wb + (32 * p + lane) * CPITCH;
+		const uint4 q0 = *reinterpret_cast<const uint4 *>(c + 4u * swz);
+		const uint4 q1 = *reinterpret_cast<const uint4 *>(c + 4u * (swz ^ 1u));
+		const uint32_t ww[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+#pragma unroll
+		for (int j = 0; j < 8; j++) {
+			x[8 * j + p] = (uint32_t)((int)(short)(ww[j] & 0xFFFFu) * val);
+			x[8 * j + 4 + p] = (uint32_t)(((int)ww[j] >> 16) * val);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		__stcg(gh + 32 * k + lane, x[60 + k]);
+	const uint32_t one0 = lane == 0 ? 1u : 0u; /* decode.c:561-564: +1 where m % 64 == 0 */
+	uint32_t y[64];
+#pragma unroll
+	for (int i = 0; i < 64; i++) {
+		/* C = 64: m-64 -> i-2, m-128 -> i-4; row parity = (m/64)&1 = (i>>1)&1 */
+		uint32_t p1 = i >= 2 ? x[i - 2] : hx[i + 2];
+		uint32_t p2 = i >= 4 ? x[i - 4] : hx[i];
+		y[i] = lift(x[i], p1, p2, (i >> 1) & 1);
+		if ((i & 1) == 0)
+			y[i] += one0;
+	}
+	__stcg(gh + 128 + lane, y[62]);
+	__stcg(gh + 160 + lane, y[63]);
+	__syncwarp(); /* every lane has read its columns: the buffer can be overwritten */
+	/* chunk -1 = the previous block's last 64 X2 words */
+	xs[-XPRE + lane] = hz[0];
+	xs[-XPRE + 32 + lane] = hz[1];
+#pragma unroll
+	for (int i = 0; i < 64; i++) {
+		/* C = 32: m-32 -> i-1, m-64 -> i-2; row parity = i&1 */
+		uint32_t p1 = i >= 1 ? y[i - 1] : hy[1];
+		uint32_t p2 = i >= 2 ? y[i - 2] : hy[i];
+		uint32_t z = lift(y[i], p1, p2, i & 1);
+		/* transpose layout: word m lives at m + 4*(m/64); m/64 = i/2 for every lane */
+		xs[32 * i + lane + 4 * (i >> 1)] = z;
+		if (i == 62)
+			__stcg(gh + 192 + lane, z);
+		if (i == 63)
+			__stcg(gh + 224 + lane, z);
+	}
+	__syncwarp();
+
+	/* ---- stages 3..7 in registers: lane owns m in [64*lane, 64*lane+64) and walks the 128-word
+	 * window t = 0..127 made of the 64 words before it (the halo: the previous lane's chunk,
+	 * chunk -1 for lane 0: 68*(lane-1) = -XPRE) and its own 64 words, in 16-word pieces
+	 * k = 2..7 (t = 16k..16k+15).  A ROLLED loop: the body is ~4 KB of code that stays in the
+	 * instruction caches (the fully unrolled version was 40 KB and every worker warp streamed it
+	 * from L2, profiles/r01_ncu_fast2.md).  The stage-3 inputs of a piece come from shared
+	 * memory; what later stages need of the previous piece is carried in registers
+	 * (A3: its 16 stage-3 outputs, A4: its last 8 stage-4 outputs, A5: 4, A6: 2).  A stage is
+	 * only run where its inputs are complete: stage 3 from t = 32, stages 4-6 from t = 48,
+	 * stage 7 (= the output) from t = 64. */
+	const uint32_t sel = fmt.be ? 0x6701u : 0x7610u;
+	const uint32_t flip = fmt.bias ? (fmt.be ? 0x00800080u : 0x80008000u) : 0u;
+	const bool full = (uint32_t)(64 * lane + 64) <= n;
+	uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)pos0 + 64u * lane) * 2u);
+	const uint32_t *win = xs + 68 * (lane - 1);
+	uint32_t A3[16], A4[8], A5[4], A6[2];
+#pragma unroll
+	for (int j = 0; j < 16; j++)
+		A3[j] = 0u;
+#pragma unroll
+	for (int j = 0; j < 8; j++)
+		A4[j] = 0u;
+	A5[0] = A5[1] = A5[2] = A5[3] = 0u;
+	A6[0] = A6[1] = 0u;
+#pragma unroll 1
+	for (int k = 2; k < 8; k++) {
+		/* word t of the window lives at t + (t >= 64 ? 4 : 0) */
+		const uint4 *p0 = reinterpret_cast<const uint4 *>(win + 16 * k + (k >= 4 ? 4 : 0));
+		const uint4 *p1 = reinterpret_cast<const uint4 *>(win + 16 * (k - 1) + (k >= 5 ? 4 : 0));
+		const uint4 *p2 = reinterpret_cast<const uint4 *>(win + 16 * (k - 2) + (k >= 6 ? 4 : 0));
+		const uint32_t sgn = (k & 1) ? 0xFFFFFFFFu : 1u; /* row parity of stage 3 = (t >> 4) & 1 */
+		uint32_t a3[16];
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const uint4 c0 = p0[q], c1 = p1[q], c2 = p2[q];
+			/* C = 16 (decode.c:518-519): 2*in[t-16] +- (in[t] + in[t-32]) */
+			a3[4 * q + 0] = 2u * c1.x + sgn * (c0.x + c2.x);
+			a3[4 * q + 1] = 2u * c1.y + sgn * (c0.y + c2.y);
+			a3[4 * q + 2] = 2u * c1.z + sgn * (c0.z + c2.z);
+			a3[4 * q + 3] = 2u * c1.w + sgn * (c0.w + c2.w);
+		}
+		if (k >= 3) {
+			uint32_t a4[16], a5[16], a6[16];
+#pragma unroll
+			for (int j = 0; j < 16; j++) /* C = 8 */
+				a4[j] = lift(a3[j], j >= 8 ? a3[j - 8] : A3[j + 8], A3[j], (j >> 3) & 1);
+#pragma unroll
+			for (int j = 0; j < 16; j++) /* C = 4 */
+				a5[j] = lift(a4[j], j >= 4 ? a4[j - 4] : A4[j + 4], j >= 8 ? a4[j - 8] : A4[j], (j >> 2) & 1);
+#pragma unroll
+			for (int j = 0; j < 16; j++) /* C = 2 */
+				a6[j] = lift(a5[j], j >= 2 ? a5[j - 2] : A5[j + 2], j >= 4 ? a5[j - 4] : A5[j], (j >> 1) & 1);
+			if (k >= 4) {
+				uint32_t pk[8];
+#pragma unroll
+				for (int j = 0; j < 16; j += 2) { /* C = 1 */
+					const uint32_t v0 = lift(a6[j], j >= 1 ? a6[j - 1] : A6[1], j >= 2 ? a6[j - 2] : A6[0], 0);
+					const uint32_t v1 = lift(a6[j + 1], a6[j], j >= 1 ? a6[j - 1] : A6[1], 1);
+					pk[j >> 1] = pack2(v0, v1, sel, flip);
+					if (CKS) {
+						/* u_i as an unsigned 16-bit value, independent of byte order */
+						const uint32_t m = pos0 + 64u * lane + 16u * (uint32_t)(k - 4) + (uint32_t)j;
+						const uint32_t w0 = (((uint32_t)((int32_t)v0 >> LEVEL)) + fmt.bias) & 0xFFFFu;
+						const uint32_t w1 = (((uint32_t)((int32_t)v1 >> LEVEL)) + fmt.bias) & 0xFFFFu;
+						if (m - pos0 < n)
+							cks += (unsigned long long)(m + 1u) * (w0 + 1ull);
+						if (m + 1u - pos0 < n)
+							cks += (unsigned long long)(m + 2u) * (w1 + 1ull);
+					}
+				}
+				const int q = 2 * (k - 4);
+				if (full) {
+					/* streaming stores: PCM is written once and must not evict the L2-resident
+					 * history, records and compressed bytes */
+					__stcs(dst + q, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+					__stcs(dst + q + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+				} else {
+					/* last block of a stream: word-granular tail */
+					uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + q);
+#pragma unroll
+					for (int e = 0; e < 16; e++) {
+						const uint32_t m = 64u * lane + 8u * q + e;
+						if (m < n)
+							d16[e] = (uint16_t)(pk[e >> 1] >> (16 * (e & 1)));
+					}
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+				A4[j] = a4[8 + j];
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				A5[j] = a5[12 + j];
+			A6[0] = a6[14];
+			A6[1] = a6[15];
+		}
+#pragma unroll
+		for (int j = 0; j < 16; j++)
+			A3[j] = a3[j];
+	}
+	__syncwarp(); /* all shared-memory reads of this block are done */
+	return cks;
+}
+
+/* ------------------------------------------------------------------ worker: one block record */
+
+template <bool CKS>
+__device__ __forceinline__ void decode_record(Smem &sm, const KernelArgs &a, uint32_t *wb, int slot, int lane,
+					      const uint8_t *recbase, uint32_t *gh)
+{
+	Rec e;
+	{
+		const uint4 r0 = __ldcg(reinterpret_cast<const uint4 *>(recbase + 256));
+		const uint4 r1 = __ldcg(reinterpret_cast<const uint4 *>(recbase + 272));
+		e.pblock = r0.x; e.pend = r0.y; e.desc = r0.z; e.blk = r0.w;
+		e.status = (int32_t)r1.x; e.ncols = r1.y; e.val = (int32_t)r1.z; e.pad = r1.w;
+	}
+	const uint2 offs = __ldcg(reinterpret_cast<const uint2 *>(recbase) + lane); /* columns 4*lane .. +3 */
+	const DevStream d = a.streams[e.desc];
+	const uint32_t bno = e.blk & 0x7FFFFFFFu;
+	const bool last = (e.blk >> 31) != 0;
+	if (bno == 0) {
+		if (lane == 0) {
+			sm.pos[slot] = 0u;
+			sm.cks[slot] = 0ull;
+		}
+		__syncwarp();
+	}
+	if (vol_ld(&sm.dead[slot]) == e.desc + 1u)
+		return; /* stream already finalised by a corrupt code (descriptor ids are unique) */
+	const uint32_t limit_w = d.file_end + 8u;
+	const bool ok = e.status == SCAN_OK;
+	const uint32_t ncheck = ok ? (uint32_t)COLS : e.ncols + (e.status == -7 ? 1u : 0u);
+	int bad = 0;
+	if (ncheck) {
+		uint32_t *stage = wb + X0_W;
+		uint32_t *listA = wb + X0_W + STAGE_W, *listB = listA + 128;
+		/* ---- stage the block's bytes: 16-byte chunks [c_lo, c_hi) of the stream, with the
+		 * EOF rule applied (bits at and past file_end read as zero) */
+		const uint32_t c_lo = e.pblock >> 7;
+		uint32_t c_hi = (e.pend + 160u + 127u) >> 7;
+		if (c_hi > c_lo + (uint32_t)(STAGE_W / 4))
+			c_hi = c_lo + (uint32_t)(STAGE_W / 4);
+		const uint8_t *src = a.blob + d.base_off;
+		const uint64_t room = a.blob_room > d.base_off ? a.blob_room - d.base_off : 0;
+		const uint32_t fe_word = d.file_end >> 5, fe_tail = d.file_end & 31u;
+		for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
+			uint4 v = make_uint4(0u, 0u, 0u, 0u);
+			if ((uint64_t)c * 16u + 16u <= room)
+				v = ldg_nc_v4(src + (size_t)c * 16u);
+			if (4u * c + 3u >= fe_word) {
+				uint32_t q[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+				for (int j = 0; j < 4; j++) {
+					const uint32_t k = 4u * c + j;
+					if (k > fe_word || (k == fe_word && !fe_tail))
+						q[j] = 0u;
+					else if (k == fe_word)
+						q[j] &= (1u << fe_tail) - 1u;
+				}
+				v = make_uint4(q[0], q[1], q[2], q[3]);
+			}
+			reinterpret_cast<uint4 *>(stage)[c - c_lo] = v;
+		}
+		__syncwarp();
+		Stage sr;
+		sr.st = stage;
+		sr.w_lo = c_lo * 4u;
+		/* ---- sort the columns by filler class */
+		uint32_t nk = 0, nt = 0, nl = 0;
+		const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const uint32_t c = 4u * lane + j;
+			const uint32_t off = (j & 1) ? ((j & 2) ? offs.y : offs.x) >> 16 : ((j & 2) ? offs.y : offs.x) & 0xFFFFu;
+			uint32_t inf = 0u, ent = 0u;
+			if (c < ncheck) {
+				const uint32_t Pc = e.pblock + off, i = Pc >> 5;
+				const uint32_t ind = __funnelshift_r(sr.word(i), sr.word(i + 1), Pc) & 31u;
+				inf = sm.info[ind];
+				ent = c | (((inf & INF_LIN) ? ind : (inf >> 20)) << 8) | (off << 16);
+				if (ok && !(inf & (INF_K | INF_T | INF_LIN))) {
+					/* f_zero decode.c:181-188 */
+					uint4 *z = reinterpret_cast<uint4 *>(wb + c * CPITCH);
+					z[0] = make_uint4(0u, 0u, 0u, 0u);
+					z[1] = make_uint4(0u, 0u, 0u, 0u);
+				}
+			}
+			const uint32_t mk = __ballot_sync(0xFFFFFFFFu, (inf & INF_K) != 0u);
+			const uint32_t mt = __ballot_sync(0xFFFFFFFFu, (inf & INF_T) != 0u);
+			const uint32_t ml = __ballot_sync(0xFFFFFFFFu, (inf & INF_LIN) != 0u);
+			if (inf & INF_K)
+				listA[nk + __popc(mk & lt)] = ent;
+			if (inf & INF_T)
+				listA[127u - (nt + __popc(mt & lt))] = ent;
+			if (inf & INF_LIN)
+				listB[nl + __popc(ml & lt)] = ent;
+			nk += __popc(mk);
+			nt += __popc(mt);
+			nl += __popc(ml);
+		}
+		__syncwarp();
+		/* ---- unpack, one class at a time */
+		if (ok) {
+			for (uint32_t j = lane; j < nk; j += 32) {
+				const uint32_t ent = listA[j];
+				unpack_k(sr, e.pblock + (ent >> 16) + 5u, (ent >> 8) & 31u, col_out(wb, ent & 127u), sm.k8w,
+					 sm.nib2w);
+			}
+			for (uint32_t j = lane; j < nl; j += 32) {
+				const uint32_t ent = listB[j];
+				unpack_linear(sr, e.pblock + (ent >> 16) + 5u, (ent >> 8) & 31u, col_out(wb, ent & 127u));
+			}
+		}
+		for (uint32_t j = lane; j < nt; j += 32) {
+			const uint32_t ent = listA[127u - j];
+			bad |= unpack_t(sr, e.pblock + (ent >> 16) + 5u, limit_w, (ent >> 8) & 31u, col_out(wb, ent & 127u),
+					sm.t, sm.nib2w, ok);
+		}
+	}
+	bad = __any_sync(0xFFFFFFFFu, bad);
+	__syncwarp();
+	uint32_t pos = sm.pos[slot];
+	int st = 0;
+	if (bad)
+		st = -6;
+	else if (!ok)
+		st = e.status == SCAN_EOF ? 0 : e.status;
+	if (ok && !bad) {
+		uint32_t n = d.words_limit - pos;
+		if (n > (uint32_t)BLEN)
+			n = BLEN;
+		uint8_t *out = a.out + d.out_off;
+		unsigned long long c2 = juggle_and_store<CKS>(wb, gh, bno == 0, lane, e.val, out, pos, n, a.fmt);
+		pos += n;
+		if (CKS) {
+			for (int o = 16; o; o >>= 1)
+				c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+			if (lane == 0)
+				sm.cks[slot] += c2;
+		}
+		if (lane == 0)
+			sm.pos[slot] = pos;
+	}
+	if (!ok || bad || last) {
+		/* finalise: results + zero padding of the undelivered tail */
+		uint8_t *p0 = a.out + d.out_off + (size_t)pos * a.fmt.wordlen;
+		/* up to the 16-byte boundary that ends this stream's slot (out_off is 16-byte
+		 * aligned), so that alignment gaps never carry stale bytes */
+		size_t nb = d.pad_words >= pos && d.pad_words
+				    ? (((size_t)d.pad_words * a.fmt.wordlen + 15u) & ~(size_t)15u) -
+					      (size_t)pos * a.fmt.wordlen
+				    : 0;
+		for (size_t i = lane; i < nb; i += 32)
+			p0[i] = 0;
+		__syncwarp();
+		if (lane == 0) {
+			a.status[d.index] = st;
+			a.words[d.index] = pos;
+			a.cks[d.index] = a.fmt.checksums ? sm.cks[slot] : 0ull;
+			vol_st(&sm.dead[slot], e.desc + 1u);
+		}
+	}
+	__syncwarp();
+}
+
+/* ------------------------------------------------------------------ kernel */
+
+template <bool CKS>
+__global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs a)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+	for (int i = tid; i < ACM_K8_SIZE; i += THREADS)
+		sm.k8w[i] = a.tables->k8w[i];
+	for (int i = tid; i < ACM_UNI_PAGES * 128 / 2; i += THREADS)
+		reinterpret_cast<uint32_t *>(sm.uni16)[i] = reinterpret_cast<const uint32_t *>(a.tables->uni16)[i];
+	for (int i = tid; i < ACM_T_SIZE; i += THREADS)
+		sm.t[i] = a.tables->t[i];
+	for (int i = tid; i < 256; i += THREADS)
+		sm.nib2w[i] = a.tables->nib2w[i];
+	if (tid < 32)
+		sm.info[tid] = make_info(a.tables->kind[tid]);
+	for (int i = tid; i < S; i += THREADS) {
+		sm.prod[i] = 0;
+		sm.cons[i] = 0;
+		sm.busy[i] = 0;
+		sm.dead[i] = 0;
+		sm.pos[i] = 0;
+		sm.cks[i] = 0ull;
+	}
+	for (int i = tid; i < NSCAN * (RW + 3) * 32; i += THREADS)
+		(&sm.ring[0][0])[i] = 0u;
+	if (tid == 0)
+		sm.scan_done = 0;
+	__syncthreads();
+
+	uint8_t *const cta_ring = a.ring + (size_t)blockIdx.x * S * RING_D * REC_BYTES;
+	uint32_t *const cta_hist = a.hist + (size_t)blockIdx.x * S * HIST_WORDS;
+
+	if (warp >= W) {
+		/* ================= scan warps: lane = stream slot ================= */
+		const int sw = warp - W, slot = 32 * sw + lane;
+		uint8_t *const slot_ring = cta_ring + (size_t)slot * RING_D * REC_BYTES;
+		ScanRing ring;
+		ring.rw = &sm.ring[sw][lane];
+		ring.saddr = (uint32_t)__cvta_generic_to_shared(ring.rw);
+		ring.idle();
+		bool active = false, exhausted = false;
+		uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
+		for (;;) {
+			if (active && vol_ld(&sm.dead[slot]) == cur + 1u) {
+				active = false; /* a worker found a corrupt t-code: abandon the stream */
+				ring.idle();
+			}
+			if (!active && !exhausted) {
+				const uint32_t idx = atomicAdd(a.counter, 1u);
+				if (idx < a.count) {
+					const DevStream d = a.streams[idx];
+					cur = idx;
+					P = d.bit0;
+					blk = 0;
+					limit = d.file_end + 8u;
+					n_attempt = d.n_attempt;
+					ring.start(a.blob + d.base_off, a.blob_room > d.base_off ? a.blob_room - d.base_off : 0,
+						   d.file_end, P);
+					active = true;
+				} else {
+					exhausted = true;
+				}
+			}
+			const uint32_t lead = prodn - vol_ld(&sm.cons[slot]);
+			const bool can = active && lead < (uint32_t)RING_D;
+			if (!__any_sync(0xFFFFFFFFu, can)) {
+				if (!__any_sync(0xFFFFFFFFu, active))
+					break; /* every lane is out of streams */
+				__nanosleep(500);
+				continue;
+			}
+			if (!__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2))) {
+				__nanosleep(300); /* nobody is close to starving the decode: let lanes bunch up */
+				continue;
+			}
+			/* ---- one record per lane that can produce */
+			uint8_t *const recbase = slot_ring + (size_t)(prodn % RING_D) * REC_BYTES;
+			Rec e;
+			e.pblock = P; e.pend = P; e.desc = cur; e.blk = blk; e.status = SCAN_EOF; e.ncols = 0; e.val = 0; e.pad = 0;
+			Walk s;
+			s.P = P;
+			s.lo = 0u;
+			s.s8 = UNI_HALT8;
+			s.msk = MSK_K;
+			bool stale = true;
+			int mode = 0; /* 0 not walking (any more), 1 block header pending, 2 walking */
+			bool walk = false;
+			if (can) {
+				if (blk >= n_attempt) {
+					/* nothing (more) to attempt: clean end */
+					e.blk |= 0x80000000u;
+				} else {
+					walk = true;
+					mode = 1;
+				}
+			}
+			const unsigned long long rec64 = (unsigned long long)(uintptr_t)recbase;
+			uint32_t cp = (uint32_t)rec64;
+			const uint32_t cph = (uint32_t)(rec64 >> 32), cpend = cp + 2u * COLS;
+			bool hdr_eof = false;
+			while (__any_sync(0xFFFFFFFFu, mode != 0)) {
+				ring.topup(s.P);
+				if (mode == 1) {
+					/* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
+					const uint32_t wi = s.P >> 5;
+					if (s.P + 20u > limit) {
+						hdr_eof = true;
+						mode = 0;
+					} else if (wi + 2u <= ring.ready_w) {
+						const uint32_t *rp = ring.rw + (wi & (RW - 1)) * 32u;
+						const uint32_t w = fsr(rp[0], rp[32], s.P);
+						e.val = (int)((w >> 4) & 0xFFFFu);
+						s.P += 20u;
+						s.s8 = 0u;
+						s.msk = MSK_SEL;
+						stale = true;
+						mode = 2;
+					}
+				}
+#pragma unroll 4
+				for (int k = 0; k < SCAN_PERIOD; k++)
+					fast_step(s, stale, cp, cph, cpend, P, ring.rw, ring.ready_w,
+						  reinterpret_cast<const unsigned char *>(sm.uni16));
+				if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
+					mode = 0;
+			}
+			if (walk) {
+				if (hdr_eof) {
+					e.status = SCAN_EOF;
+				} else if (s.s8 == UNI_HALT8 && s.P <= limit) {
+					/* 128 columns, every read inside the stream */
+					e.status = SCAN_OK;
+					e.ncols = COLS;
+					e.pend = s.P;
+				} else {
+					/* bad selector, or the stream ended inside the block: walk it again with the
+					 * reference's verdicts (rare: at most once per stream) */
+					const DevStream d = a.streams[cur];
+					BitReader br;
+					br.init(reinterpret_cast<const uint32_t *>(a.blob + d.base_off), d.file_end);
+					const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS,
+									 reinterpret_cast<uint16_t *>(recbase), P, a.tables->kind,
+									 a.tables->k8);
+					e.status = sc.status;
+					e.ncols = sc.ncols;
+					e.pend = sc.end;
+					e.val = sc.val;
+					s.P = sc.end;
+				}
+				P = s.P;
+				blk++;
+				if (e.status != SCAN_OK || blk >= n_attempt)
+					e.blk |= 0x80000000u;
+			}
+			if (can) {
+				uint4 *rp = reinterpret_cast<uint4 *>(recbase + 256);
+				rp[0] = make_uint4(e.pblock, e.pend, e.desc, e.blk);
+				rp[1] = make_uint4((uint32_t)e.status, e.ncols, (uint32_t)e.val, 0u);
+				if (e.blk >> 31) {
+					active = false;
+					ring.idle();
+				}
+			}
+			__threadfence(); /* records reach L2 before they are announced */
+			if (can)
+				vol_st(&sm.prod[slot], ++prodn);
+		}
+		__threadfence_block();
+		if (lane == 0)
+			atomicAdd(&sm.scan_done, 1u);
+	} else {
+		/* ================= worker warps: claim a slot, decode its pending records ================= */
+		uint32_t *wb = sm.wb[warp];
+		uint32_t rot = (uint32_t)warp * 5u, nap = 64u;
+		for (;;) {
+			const bool done = vol_ld(&sm.scan_done) == (uint32_t)NSCAN;
+			__threadfence_block();
+			const bool r0 = vol_ld(&sm.prod[lane]) != vol_ld(&sm.cons[lane]) && !vol_ld(&sm.busy[lane]);
+			const bool r1 = vol_ld(&sm.prod[lane + 32]) != vol_ld(&sm.cons[lane + 32]) && !vol_ld(&sm.busy[lane + 32]);
+			const unsigned long long m = (unsigned long long)__ballot_sync(0xFFFFFFFFu, r0) |
+						     ((unsigned long long)__ballot_sync(0xFFFFFFFFu, r1) << 32);
+			if (!m) {
+				if (done)
+					break;
+				__nanosleep(nap); /* idle: back off, the scan warps need the issue slots */
+				nap = nap < 2048u ? nap * 2u : nap;
+				continue;
+			}
+			nap = 64u;
+			/* round robin from a rotating start so that every slot gets its turn */
+			rot &= 63u;
+			const unsigned long long mr = rot ? (m >> rot) | (m << (64u - rot)) : m;
+			const int slot = (int)((rot + (uint32_t)__ffsll((long long)mr) - 1u) & 63u);
+			rot = (uint32_t)slot + 1u;
+			uint32_t got = 0;
+			if (lane == 0)
+				got = atomicCAS(&sm.busy[slot], 0u, 1u) == 0u;
+			got = __shfl_sync(0xFFFFFFFFu, got, 0);
+			if (!got)
+				continue;
+			__threadfence_block();
+			uint32_t c = vol_ld(&sm.cons[slot]);
+			const uint32_t p = vol_ld(&sm.prod[slot]);
+			uint32_t nrec = p - c;
+			if (nrec > (uint32_t)KMAX)
+				nrec = KMAX;
+			const uint8_t *slot_ring = cta_ring + (size_t)slot * RING_D * REC_BYTES;
+			for (uint32_t k = 0; k < nrec; k++, c++)
+				decode_record<CKS>(sm, a, wb, slot, lane, slot_ring + (size_t)(c % RING_D) * REC_BYTES,
+						   cta_hist + slot * HIST_WORDS);
+			__threadfence_block();
+			if (lane == 0) {
+				vol_st(&sm.cons[slot], c);
+				__threadfence_block();
+				atomicExch(&sm.busy[slot], 0u);
+			}
+			__syncwarp();
+		}
+	}
+}
+
+} // namespace fast2
+
+size_t fast2_smem_bytes() { return sizeof(fast2::Smem); }
+
+int fast2_slots_per_cta() { return fast2::S; }
+
+size_t fast2_hist_words_per_cta() { return (size_t)fast2::S * fast2::HIST_WORDS; }
+
+size_t fast2_ring_bytes_per_cta() { return (size_t)fast2::S * fast2::RING_D * fast2::REC_BYTES; }
+
+cudaError_t launch_fast2(const KernelArgs &a, int n_ctas, cudaStream_t st)
+{
+	if (a.count == 0)
+		return cudaSuccess;
+	/* the opt-in shared-memory size is a per-device function attribute */
+	static bool configured[2][64] = {};
+	const size_t smem = sizeof(fast2::Smem);
+	const int v = a.fmt.checksums ? 1 : 0;
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (!configured[v][dev & 63]) {
+		e = v ? cudaFuncSetAttribute(fast2::acm_decode_fast2_kernel<true>,
+					     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+		      : cudaFuncSetAttribute(fast2::acm_decode_fast2_kernel<false>,
+					     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess)
+			return e;
+		configured[v][dev & 63] = true;
+	}
+	if (v)
+		fast2::acm_decode_fast2_kernel<true><<<n_ctas, fast2::THREADS, smem, st>>>(a);
+	else
+		fast2::acm_decode_fast2_kernel<false><<<n_ctas, fast2::THREADS, smem, st>>>(a);
+	return cudaGetLastError();
+}
+
+} // namespace acm

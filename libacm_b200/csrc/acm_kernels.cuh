@@ -24,6 +24,7 @@ struct KernelArgs {
 	uint32_t *counter;        /* work-queue cursor (zeroed before launch) */
 	uint32_t *errflag;        /* set non-zero on an internal failure (e.g. copy timeout) */
 	uint32_t *hist;           /* fast kernel: per-CTA, per-slot transform history (256 words each) */
+	uint8_t *ring;            /* fast kernel 2: per-CTA, per-slot ring of block records */
 	/* generic kernel, resumable decode (acm_stream.cu): when resume_hist != NULL stream i of the
 	 * slice starts from / leaves its per-stage history at resume_hist + i * resume_stride (2*cols
 	 * words); a stream whose DevStream::resume is 0 still starts from zero history.
@@ -57,6 +58,13 @@ size_t fast_smem_bytes();
 int fast_slots_per_cta();
 size_t fast_hist_words_per_cta();
 cudaError_t launch_fast(const KernelArgs &a, int n_ctas, cudaStream_t st);
+
+/* second generation of the same (acm_fast2.cu): scan decoupled from the decode */
+size_t fast2_smem_bytes();
+int fast2_slots_per_cta();
+size_t fast2_hist_words_per_cta();
+size_t fast2_ring_bytes_per_cta();
+cudaError_t launch_fast2(const KernelArgs &a, int n_ctas, cudaStream_t st);
 
 /* gathers the first 48 bytes of every image (header parse on the host) */
 cudaError_t launch_gather_headers(const uint8_t *blob, uint64_t blob_len, const uint64_t *in_off,

@@ -87,6 +87,90 @@ void acm_tables_build(acm_tables *t)
 			t->k8[kt * 256 + b] = e | (uint64_t)nv;
 		}
 	}
+	for (kt = 0; kt < 8; kt++) {
+		for (b = 0; b < 256; b++) {
+			uint64_t vals = 0;
+			int pos = 0, nv = 0;
+			for (;;) {
+				int count, value, len, k;
+				len = k_symbol(sel_of_kt[kt], b, pos, &count, &value);
+				if (!len || nv + count > 8)
+					break;
+				pos += len;
+				for (k = 0; k < count; k++, nv++)
+					vals |= (uint64_t)(value & 15) << (4 * nv);
+			}
+			t->k8w[kt * 256 + b] = vals | ((uint64_t)pos << 32) | ((uint64_t)(4 * nv) << 40);
+		}
+	}
+	/* the scan walk as one state machine */
+	for (b = 0; b < 128; b++) {
+		t->uni16[ACM_UNI_HALT * 128 + b] = (uint16_t)(ACM_UNI_HALT << 8);
+		t->uni16[ACM_UNI_BAD * 128 + b] = (uint16_t)(ACM_UNI_BAD << 8);
+		t->uni16[ACM_UNI_SKIP6 * 128 + b] = (uint16_t)(6u | (ACM_UNI_SEL << 8));
+	}
+	for (kt = 0; kt < 8; kt++) {
+		int rem;
+		for (rem = 1; rem <= 16; rem++) {
+			/* rem < 16: a prefix-code page, ACM_UNI_KBITS index bits.  rem == 16: the first step
+			 * of a column, taken from the selector page, 8 payload bits */
+			const unsigned nb = rem < 16 ? ACM_UNI_KBITS : 8;
+			for (b = 0; b < (1u << nb); b++) {
+				/* whole symbols of the nb bits b (k_symbol refuses symbols that reach bit 8, so
+				 * the window is shifted up to end at bit 8), until rem rows are covered */
+				int pos = 8 - (int)nb, rows = 0, next;
+				for (;;) {
+					int count, value, len;
+					len = k_symbol(sel_of_kt[kt], b << (8 - nb), pos, &count, &value);
+					if (!len)
+						break;
+					pos += len;
+					rows += count;
+					if (rows >= rem)
+						break;
+				}
+				pos -= 8 - (int)nb;
+				next = rows >= rem ? ACM_UNI_SEL : ACM_UNI_K0 + kt * 15 + (rem - rows - 1);
+				if (rem < 16) {
+					t->uni16[(ACM_UNI_K0 + kt * 15 + rem - 1) * 128 + b] = (uint16_t)(pos | (next << 8));
+				} else {
+					unsigned idx = ((unsigned)b << 5) | (unsigned)sel_of_kt[kt];
+					t->uni16[idx] = (uint16_t)((5 + pos) | (next << 8));
+				}
+			}
+		}
+	}
+	for (b = 0; b < 8192; b++) {
+		unsigned ind = b & 31u, adv, next = ACM_UNI_SEL;
+		if (ind == 0)
+			adv = 5;
+		else if (ind >= 3 && ind <= 16)
+			adv = 5 + 16 * ind;
+		else if (ind == 19)
+			adv = 5 + 30;
+		else if (ind == 22)
+			adv = 5 + 42;
+		else if (ind == 29)
+			adv = 5 + 56;
+		else if (ind == 17 || ind == 18 || ind == 20 || ind == 21 || ind == 23 || ind == 24 || ind == 26 ||
+			 ind == 27)
+			continue; /* filled above */
+		else {
+			adv = 0;
+			next = ACM_UNI_BAD;
+		}
+		if (adv > 255) {
+			adv -= 6;
+			next = ACM_UNI_SKIP6;
+		}
+		t->uni16[b] = (uint16_t)(adv | (next << 8));
+	}
+	for (b = 0; b < 256; b++) {
+		int lo = (int)(b & 15u), hi = (int)(b >> 4);
+		lo = lo >= 8 ? lo - 16 : lo;
+		hi = hi >= 8 ? hi - 16 : hi;
+		t->nib2w[b] = ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16);
+	}
 	for (b = 0; b < 128; b++) {
 		unsigned v;
 		/* t15 (selector 19): b < 27, digits base 3 minus 1 */

@@ -29,6 +29,23 @@
  *   kstep[kt][m][b]  scan-only: one prefix-code step with m = min(rows remaining, 7) and b = the
  *               next 8 stream bits.  8-bit entry: bits 0..3 bits consumed, bits 4..6 values
  *               produced (k8's nv and cum with the row cap already applied).
+ *   k8w[kt][b]  the unpack-side variant of k8 (fast kernel 2): every whole symbol that fits in
+ *               the 8 bits b while at most 8 rows are produced.  64-bit entry:
+ *                 bits  0..31  the (up to 8) values, 4-bit two's complement, value j in nibble j
+ *                 bits 32..35  bits consumed (1..8)
+ *                 bits 40..45  4 * rows produced (4..32)
+ *               No row cap: the caller accumulates 16 nibbles in a 64-bit register and lets
+ *               rows past the 16th shift out; where the column ends is known from the scan.
+ *   uni16[page][b]  the whole column-length walk of a 16-row block as ONE state machine: an entry
+ *               is (bits to advance) | (next page id << 8).  The state "at a column selector" is
+ *               the 8192-entry page 0 (index = 13 stream bits: selector + first payload byte);
+ *               "inside a prefix-coded column of type kt with rem rows to come" is page
+ *               ACM_UNI_K0 + kt*15 + rem-1 (index = 7 stream bits; whole symbols, row cap applied);
+ *               a fixed-size filler advances over its whole payload in one step (the 261 bits of a
+ *               16-bit linear column as 255 + the SKIP6 page); a bad selector (f_bad,
+ *               decode.c:190-194) leads to the BAD page; HALT and BAD entries advance 0 bits
+ *               and stay, so a lane that is done, parked or corrupt runs the same instructions.
+ *   nib2w[b]    b = two nibbles (rows r, r+1) -> (int16)lo | (int16)hi << 16.
  */
 #ifndef ACM_TABLES_H
 #define ACM_TABLES_H
@@ -38,6 +55,14 @@
 #define ACM_K8_TYPES 8
 #define ACM_K8_SIZE (ACM_K8_TYPES * 256)
 #define ACM_T_SIZE (3 * 128)
+/* uni16 page ids; a page = 128 entries = 256 bytes, so (id << 8) is the page's byte offset */
+#define ACM_UNI_SEL 0     /* ids 0..63: the 8192-entry selector page */
+#define ACM_UNI_K0 64     /* (kt, rem) -> 64 + kt * 15 + (rem - 1), rem = 1..15 */
+#define ACM_UNI_HALT 184
+#define ACM_UNI_BAD 185
+#define ACM_UNI_SKIP6 186
+#define ACM_UNI_PAGES 187
+#define ACM_UNI_KBITS 7   /* index width of the prefix-code pages */
 
 typedef struct acm_tables {
 	uint64_t k8[ACM_K8_SIZE];
@@ -46,6 +71,9 @@ typedef struct acm_tables {
 	uint8_t kstep[8 * 8 * 256];
 	uint8_t kind[32];  /* per selector: class | (subtype << 3); see ACM_CLS_* */
 	uint8_t pad[32];
+	uint64_t k8w[ACM_K8_SIZE]; /* worker-side prefix-code step, see above */
+	uint16_t uni16[ACM_UNI_PAGES * 128]; /* scan walk of fast kernel 2, see above */
+	uint32_t nib2w[256];       /* two 4-bit two's complement values -> two int16 in one word */
 } acm_tables;
 
 enum { ACM_CLS_ZERO = 0, ACM_CLS_LINEAR = 1, ACM_CLS_K = 2, ACM_CLS_T = 3, ACM_CLS_BAD = 4 };
