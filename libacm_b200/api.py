@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libacm_b200.so")
+LIB_PATH = os.environ.get("ACM_B200_LIB") or os.path.join(_HERE, "_lib", "libacm_b200.so")
+# (ACM_B200_LIB: a tuning build of the same library, tools/build_variants.py)
 
 ACM_OK, ACM_ERR_OTHER, ACM_ERR_OPEN, ACM_ERR_NOT_ACM = 0, -1, -2, -3
 ACM_ERR_READ_ERR, ACM_ERR_BADFMT, ACM_ERR_CORRUPT = -4, -5, -6

@@ -193,6 +193,7 @@ struct acm_gpu_plan {
 	uint32_t *d_hist;    /* fast kernel history, fast_ctas * fast_hist_words_per_cta() words */
 	uint8_t *d_ring;     /* fast kernel 2 block-record rings (inside d_ring_alloc) */
 	uint8_t *d_ring_alloc;
+	unsigned long long *d_prof; /* 64 counters of -DF2_PROF tuning builds */
 	int fast_gen;        /* 2: acm_fast2.cu (default), 1: acm_fast.cu (opts->kernel == 2) */
 	int fast_ctas;
 	int generic_ctas;
@@ -214,6 +215,7 @@ static void plan_free(acm_gpu_plan *p)
 	cudaFree(p->scratch.buf);
 	cudaFree(p->d_hist);
 	cudaFree(p->d_ring_alloc);
+	cudaFree(p->d_prof);
 	if (p->ev0)
 		cudaEventDestroy(p->ev0);
 	if (p->ev1)
@@ -262,6 +264,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
 	p->d_ring = nullptr;
 	p->d_ring_alloc = nullptr;
+	p->d_prof = nullptr;
 	p->fast_gen = opts->kernel == 2 ? 1 : 2;
 	p->device = dev;
 	p->n = n;
@@ -381,6 +384,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	CU(cudaMalloc(&p->d_tables, sizeof(acm_tables)));
 	CU(cudaMemcpy(p->d_tables, &host_tab, sizeof(acm_tables), cudaMemcpyHostToDevice));
 	CU(cudaMalloc(&p->d_counters, (4 * p->seg.size() + 4) * sizeof(uint32_t)));
+	CU(cudaMalloc(&p->d_prof, 64 * sizeof(unsigned long long)));
+	CU(cudaMemset(p->d_prof, 0, 64 * sizeof(unsigned long long)));
 	CU(cudaEventCreate(&p->ev0));
 	CU(cudaEventCreate(&p->ev1));
 
@@ -419,6 +424,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			if ((lo >> 32) != ((lo + ring_bytes) >> 32)) {
 				cudaFree(p->d_ring_alloc);
 				p->d_ring_alloc = nullptr;
+	p->d_prof = nullptr;
 				CU(cudaMalloc(&p->d_ring_alloc, 2 * ring_bytes + 512));
 				lo = ((uintptr_t)p->d_ring_alloc + 255u) & ~(uintptr_t)255u;
 				if ((lo >> 32) != ((lo + ring_bytes) >> 32))
@@ -465,6 +471,7 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 	a.fmt = p->fmt;
 	a.hist = p->d_hist ? p->d_hist + sg.hist_off : nullptr;
 	a.ring = p->d_ring ? p->d_ring + sg.ring_off : nullptr;
+	a.prof = p->d_prof;
 	a.resume_hist = nullptr;
 	a.resume_stride = 0;
 	a.end_pos = nullptr;
@@ -576,6 +583,16 @@ extern "C" float acm_gpu_plan_last_ms(acm_gpu_plan *p)
 }
 
 extern "C" void acm_gpu_plan_destroy(acm_gpu_plan *p) { plan_free(p); }
+
+/* tuning builds (-DF2_PROF): the 64 in-kernel cycle counters, accumulated over the plan's runs */
+extern "C" int acm_gpu_plan_debug_counters(acm_gpu_plan *p, unsigned long long *out64)
+{
+	if (!p || !p->d_prof)
+		return ACM_ERR_OTHER;
+	return cudaMemcpy(out64, p->d_prof, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess
+		       ? ACM_OK
+		       : ACM_ERR_OTHER;
+}
 
 /* ------------------------------------------------------------------ one-shot */
 

@@ -57,14 +57,32 @@ constexpr int LEVEL = 7;
 constexpr int COLS = 128;
 constexpr int BLEN = COLS * ROWS;        /* 2048 */
 constexpr int NSCAN = 2;                 /* scan warps (the highest warp ids) */
-constexpr int W = 14;                    /* worker warps */
+#ifndef F2_W
+#define F2_W 12
+#endif
+#ifndef F2_RING_D
+#define F2_RING_D 8
+#endif
+#ifndef F2_RW
+#define F2_RW 64
+#endif
+#ifndef F2_PERIOD
+#define F2_PERIOD 16
+#endif
+#ifndef F2_FENCE_GPU
+#define F2_FENCE_GPU 0 /* 1: publish records behind a device-scope fence (scan and decode share the SM: not needed) */
+#endif
+#ifndef F2_HYST
+#define F2_HYST 1      /* scan warp sleeps while every lane is at least RING_D/2 records ahead */
+#endif
+constexpr int W = F2_W;                  /* worker warps */
 constexpr int S = 32 * NSCAN;            /* stream slots per CTA */
 constexpr int THREADS = 32 * (W + NSCAN);
-constexpr int RING_D = 8;                /* block records a scan lane may be ahead of the decode */
+constexpr int RING_D = F2_RING_D;              /* block records a scan lane may be ahead of the decode */
 constexpr int REC_BYTES = 288;           /* 128 x u16 column offsets + 32-byte Rec */
-constexpr int RW = 64;                   /* ring words per scan lane (+3 duplicates of words 0..2) */
-constexpr int LEAD = 14;                 /* 16-byte chunks requested ahead of the read position */
-constexpr int SCAN_PERIOD = 16;          /* walk steps between two top-ups */
+constexpr int RW = F2_RW;               /* ring words per scan lane (+1 duplicate of word 0) */
+constexpr int LEAD = RW / 4 - 2;               /* 16-byte chunks requested ahead of the read position */
+constexpr int SCAN_PERIOD = F2_PERIOD;         /* walk steps between two top-ups */
 constexpr int XPRE = 68;                 /* chunk -1: the previous block's last 64 X2 words (+4 pad) */
 constexpr int XWORDS = XPRE + BLEN + 4 * 32; /* transpose layout: 4 pad words per 64 */
 constexpr int CPITCH = 8;                /* words per unpacked column (16 x int16), halves swizzled */
@@ -91,9 +109,9 @@ struct Rec {
 
 struct Smem {
 	uint64_t k8w[ACM_K8_SIZE];
-	uint16_t uni16[ACM_UNI_PAGES * 128];
+	uint16_t uni16[ACM_UNI_PAGES * ACM_UNI_PSIZE];
 	uint32_t nib2w[256];
-	uint32_t ring[NSCAN][(RW + 3) * 32]; /* [word][lane] */
+	uint32_t ring[NSCAN][(RW + 1) * 32]; /* [word][lane] */
 	uint32_t wb[W][WB_WORDS];
 	unsigned long long cks[S];
 	uint32_t prod[S];  /* records published per slot (scan lane writes) */
@@ -105,6 +123,21 @@ struct Smem {
 	uint16_t t[ACM_T_SIZE];
 	uint32_t scan_done;
 };
+
+#ifndef F2_PROF
+#define F2_PROF 0
+#endif
+#if F2_PROF
+#define PROF_DECL unsigned long long prof_t0 = clock64(), prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define PROF_MARK(k) do { const unsigned long long t_ = clock64(); prof_acc[k] += t_ - prof_t0; prof_t0 = t_; } while (0)
+#define PROF_FLUSH(base) do { if (lane == 0) for (int k_ = 0; k_ < 8; k_++) atomicAdd(a.prof + (base) + k_, prof_acc[k_]); } while (0)
+#else
+#define PROF_DECL do { } while (0)
+#define PROF_MARK(k) do { } while (0)
+#define PROF_FLUSH(base) do { } while (0)
+#endif
+
+static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt in to");
 
 /* ------------------------------------------------------------------ helpers */
 
@@ -155,23 +188,27 @@ __device__ __forceinline__ uint32_t make_info(uint32_t kind)
  * A scan lane's view of its stream: RW ring words in shared memory, word i of the stream
  * (32-bit words from the 16-byte aligned stream base) at ring[(i % RW) * 32 + lane], plus a
  * copy of ring word 0 at index RW so that the pair (i, i+1) is always (slot, slot + 32).
- * Chunks (16 bytes) [.., fill) have been requested; words [.., ready_w) have landed.
+ * Chunks (16 bytes) [.., fill) have been requested; words [.., ready_w) have landed, and
+ * a 32-bit fetch at P is safe while P < ready_p.
  */
 struct ScanRing {
 	uint32_t saddr;       /* shared-space address of this lane's ring word 0 */
 	const uint32_t *rw;   /* the same, generic */
 	const uint8_t *base;  /* stream base (16-byte aligned) */
 	uint32_t room16;      /* 16-byte chunks readable at base */
+	uint32_t full16;      /* chunks [0, full16) lie entirely inside the file and the blob */
 	uint32_t fe_byte;     /* bytes of the stream that exist (relative to base) */
-	uint32_t fill, fill_prev, ready_w;
+	uint32_t fill, fill_prev, ready_w, ready_p;
 
 	__device__ __forceinline__ void idle()
 	{
 		base = nullptr;
 		room16 = 0;
+		full16 = 0;
 		fe_byte = 0;
 		fill = fill_prev = 0x0FFFFFF0u; /* never asks for data */
 		ready_w = 0;
+		ready_p = 0;
 	}
 	__device__ __forceinline__ void start(const uint8_t *src, uint64_t room, uint32_t file_end, uint32_t P0)
 	{
@@ -179,23 +216,29 @@ struct ScanRing {
 		base = src;
 		room16 = (uint32_t)(room >> 4);
 		fe_byte = file_end >> 3;
-		fill = fill_prev = P0 >> 7;
-		ready_w = 0; /* nothing readable yet: the lane idles until its first chunks land */
+		full16 = fe_byte >> 4 < room16 ? fe_byte >> 4 : room16;
+		fill = P0 >> 7;
+		/* the first chunks are fetched synchronously (once per stream): the walk starts at once */
+		for (int j = 0; j < LEAD; j++)
+			request(fill + j);
+		fill += LEAD;
+		cp_async_commit();
+		cp_async_wait_all();
+		fill_prev = fill;
+		ready_w = fill * 4u;
+		ready_p = (ready_w - 1u) * 32u;
 	}
 	__device__ __forceinline__ void request(uint32_t c)
 	{
 		const uint32_t sa = saddr + ((c & (RW / 4 - 1)) << 9);
 		const uint8_t *g = base + (size_t)c * 16u;
-		if (c < room16 && c * 16u + 16u <= fe_byte) {
+		if (c < full16) {
 			cp_async4(sa, g);
 			cp_async4(sa + 128, g + 4);
 			cp_async4(sa + 256, g + 8);
 			cp_async4(sa + 384, g + 12);
-			if ((c & (RW / 4 - 1)) == 0) {
+			if ((c & (RW / 4 - 1)) == 0)
 				cp_async4(saddr + RW * 128, g);
-				cp_async4(saddr + RW * 128 + 128, g + 4);
-				cp_async4(saddr + RW * 128 + 256, g + 8);
-			}
 		} else {
 			/* touches the end of the file (or of the blob): bytes at and past it read as zero,
 			 * which is the reference's "one zero byte, then nothing" (decode.c:57-61) */
@@ -207,8 +250,8 @@ struct ScanRing {
 					n = fe_byte - at < 4u ? fe_byte - at : 4u;
 				const void *src = n ? (const void *)(g + 4 * k) : (const void *)base;
 				cp_async4z(sa + 128 * k, src, n);
-				if (k < 3 && (c & (RW / 4 - 1)) == 0)
-					cp_async4z(saddr + RW * 128 + 128 * k, src, n);
+				if (k == 0 && (c & (RW / 4 - 1)) == 0)
+					cp_async4z(saddr + RW * 128, src, n);
 			}
 		}
 	}
@@ -224,6 +267,7 @@ struct ScanRing {
 		cp_async_commit();
 		cp_async_wait1(); /* everything but the group just committed has landed */
 		ready_w = base ? fill_prev * 4u : 0u;
+		ready_p = ready_w ? (ready_w - 1u) * 32u : 0u;
 		fill_prev = fill;
 	}
 };
@@ -236,47 +280,32 @@ __device__ __forceinline__ void st_global_u16(uint32_t lo, uint32_t hi, uint32_t
 }
 
 /*
- * One walk step for all lanes of a scan warp.  The lane holds lo = the 32 stream bits at P, so
- * the step's dependent chain is: one uni16 lookup with lo, then the next lo cut out of the four
- * ring words at P (fetched at the top of the step, next to the lookup, not after it) at offset
- * (P & 31) + advance.  That works for advances up to 64 bits; after a longer one (a wide linear
- * column), at the start of a block, or when the words at P have not landed yet, the lane is
- * STALE for one step: the lookup's result is ignored and lo is simply re-cut at P.  A stale step
- * and a live step are the same instructions.  At a selector the column offset is noted; after
- * the 128th column the lane moves to the HALT page (entries advance 0 bits and stay), which is
- * also where finished and idle lanes sit.  No end-of-file checks here: bits past the end read
- * as zero, and a block whose walk ends at or before the stream's limit cannot have read past
- * it (the caller re-walks the rare other case with the reference's verdicts).  cp = low half
- * of the global address of the next column offset (records do not straddle a 4 GiB boundary:
- * see plan_create).
+ * One walk step for all lanes of a scan warp: fetch the 32 stream bits at P from the ring, note
+ * the column offset if the lane is at a selector, one uni16 lookup, apply it.  After the 128th
+ * column the lane moves to the HALT page (entries advance 0 bits and stay), which is also where
+ * finished and idle lanes sit: every lane runs the same instructions.  A lane whose bits have
+ * not landed yet (P >= ready_p) does nothing this step.  No end-of-file checks here: bits past
+ * the end read as zero, and a block whose walk ends at or before the stream's limit cannot
+ * have read past it (the caller re-walks the rare other case with the reference's verdicts).
+ * A single warp issues in order and the walk is one dependent chain, so the step costs about
+ * four cycles per instruction plus the two shared-memory latencies: it is kept to the minimum.
  */
-__device__ __forceinline__ void fast_step(Walk &s, bool &stale, uint32_t &cp, uint32_t cph, uint32_t cpend,
-					  uint32_t pblock, const uint32_t *ringw, uint32_t ready_w,
-					  const unsigned char *uni)
+__device__ __forceinline__ void fast_step(Walk &s, uint32_t &cp, uint32_t cph, uint32_t cpend, uint32_t pblock,
+					  const uint32_t *ringw, uint32_t ready_p, const unsigned char *uni)
 {
-	const uint32_t wi = s.P >> 5;
-	const uint32_t *rp = ringw + (wi & (RW - 1)) * 32u;
-	const uint32_t w0 = rp[0], w1 = rp[32], w2 = rp[64], w3 = rp[96];
-	const bool landed = wi + 4u <= ready_w;
-	const bool live = !stale;
-	if (live && s.msk == MSK_SEL) {
+	const uint32_t *rp = ringw + ((s.P >> 5) & (RW - 1)) * 32u;
+	const uint32_t w = fsr(rp[0], rp[32], s.P);
+	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s, w));
+	const bool have = s.P < ready_p;
+	if (have && s.msk == MSK_SEL) {
 		st_global_u16(cp, cph, s.P - pblock);
 		cp += 2u;
 	}
-	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s));
-	const uint32_t adv = live ? (e & 0xFFu) : 0u;
-	const uint32_t sh = (s.P & 31u) + adv;
-	const uint32_t f0 = fsr(w0, w1, sh), f1 = fsr(w1, w2, sh), f2 = fsr(w2, w3, sh);
-	s.lo = sh < 32u ? f0 : (sh < 64u ? f1 : f2);
-	s.P += adv;
-	if (live) {
-		walk_next(s, e);
-		if (s.s8 == 0u && cp == cpend) {
-			s.s8 = UNI_HALT8;
-			s.msk = MSK_K;
-		}
-	}
-	stale = !(landed && adv <= 64u);
+	const uint32_t ee = have ? e : (s.s8 >> (UNI_PSHIFT - 8u)); /* not landed: advance 0, same page */
+	const bool at_sel = walk_next(s, ee);
+	const bool done = at_sel && cp == cpend;
+	s.s8 = done ? UNI_HALT8 : s.s8;
+	s.msk = done ? MSK_K : s.msk;
 }
 
 /* ------------------------------------------------------------------ unpack */
@@ -498,7 +527,7 @@ juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint
 
 template <bool CKS>
 __device__ __forceinline__ void decode_record(Smem &sm, const KernelArgs &a, uint32_t *wb, int slot, int lane,
-					      const uint8_t *recbase, uint32_t *gh)
+					      const uint8_t *recbase, uint32_t *gh, DevStream &d, uint32_t &d_id)
 {
 	Rec e;
 	{
@@ -508,7 +537,10 @@ __device__ __forceinline__ void decode_record(Smem &sm, const KernelArgs &a, uin
 		e.status = (int32_t)r1.x; e.ncols = r1.y; e.val = (int32_t)r1.z; e.pad = r1.w;
 	}
 	const uint2 offs = __ldcg(reinterpret_cast<const uint2 *>(recbase) + lane); /* columns 4*lane .. +3 */
-	const DevStream d = a.streams[e.desc];
+	if (e.desc != d_id) { /* consecutive records of a slot mostly belong to one stream */
+		d = a.streams[e.desc];
+		d_id = e.desc;
+	}
 	const uint32_t bno = e.blk & 0x7FFFFFFFu;
 	const bool last = (e.blk >> 31) != 0;
 	if (bno == 0) {
@@ -667,7 +699,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 
 	for (int i = tid; i < ACM_K8_SIZE; i += THREADS)
 		sm.k8w[i] = a.tables->k8w[i];
-	for (int i = tid; i < ACM_UNI_PAGES * 128 / 2; i += THREADS)
+	for (int i = tid; i < ACM_UNI_PAGES * ACM_UNI_PSIZE / 2; i += THREADS)
 		reinterpret_cast<uint32_t *>(sm.uni16)[i] = reinterpret_cast<const uint32_t *>(a.tables->uni16)[i];
 	for (int i = tid; i < ACM_T_SIZE; i += THREADS)
 		sm.t[i] = a.tables->t[i];
@@ -683,7 +715,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 		sm.pos[i] = 0;
 		sm.cks[i] = 0ull;
 	}
-	for (int i = tid; i < NSCAN * (RW + 3) * 32; i += THREADS)
+	for (int i = tid; i < NSCAN * (RW + 1) * 32; i += THREADS)
 		(&sm.ring[0][0])[i] = 0u;
 	if (tid == 0)
 		sm.scan_done = 0;
@@ -702,7 +734,9 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 		ring.idle();
 		bool active = false, exhausted = false;
 		uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
+		PROF_DECL;
 		for (;;) {
+			PROF_MARK(0); /* 0: round tail (publish) */
 			if (active && vol_ld(&sm.dead[slot]) == cur + 1u) {
 				active = false; /* a worker found a corrupt t-code: abandon the stream */
 				ring.idle();
@@ -729,22 +763,25 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 				if (!__any_sync(0xFFFFFFFFu, active))
 					break; /* every lane is out of streams */
 				__nanosleep(500);
+				PROF_MARK(1); /* 1: blocked by flow control */
 				continue;
 			}
+#if F2_HYST
 			if (!__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2))) {
 				__nanosleep(300); /* nobody is close to starving the decode: let lanes bunch up */
+				PROF_MARK(2); /* 2: hysteresis sleep */
 				continue;
 			}
+#endif
+			PROF_MARK(3); /* 3: round head (retire / acquire) */
 			/* ---- one record per lane that can produce */
 			uint8_t *const recbase = slot_ring + (size_t)(prodn % RING_D) * REC_BYTES;
 			Rec e;
 			e.pblock = P; e.pend = P; e.desc = cur; e.blk = blk; e.status = SCAN_EOF; e.ncols = 0; e.val = 0; e.pad = 0;
 			Walk s;
 			s.P = P;
-			s.lo = 0u;
 			s.s8 = UNI_HALT8;
 			s.msk = MSK_K;
-			bool stale = true;
 			int mode = 0; /* 0 not walking (any more), 1 block header pending, 2 walking */
 			bool walk = false;
 			if (can) {
@@ -761,31 +798,32 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 			const uint32_t cph = (uint32_t)(rec64 >> 32), cpend = cp + 2u * COLS;
 			bool hdr_eof = false;
 			while (__any_sync(0xFFFFFFFFu, mode != 0)) {
+				PROF_MARK(4); /* 4: walk steps */
 				ring.topup(s.P);
 				if (mode == 1) {
 					/* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
-					const uint32_t wi = s.P >> 5;
 					if (s.P + 20u > limit) {
 						hdr_eof = true;
 						mode = 0;
-					} else if (wi + 2u <= ring.ready_w) {
-						const uint32_t *rp = ring.rw + (wi & (RW - 1)) * 32u;
+					} else if (s.P < ring.ready_p) {
+						const uint32_t *rp = ring.rw + ((s.P >> 5) & (RW - 1)) * 32u;
 						const uint32_t w = fsr(rp[0], rp[32], s.P);
 						e.val = (int)((w >> 4) & 0xFFFFu);
 						s.P += 20u;
 						s.s8 = 0u;
 						s.msk = MSK_SEL;
-						stale = true;
 						mode = 2;
 					}
 				}
+				PROF_MARK(5); /* 5: top-up + header */
 #pragma unroll 4
 				for (int k = 0; k < SCAN_PERIOD; k++)
-					fast_step(s, stale, cp, cph, cpend, P, ring.rw, ring.ready_w,
+					fast_step(s, cp, cph, cpend, P, ring.rw, ring.ready_p,
 						  reinterpret_cast<const unsigned char *>(sm.uni16));
 				if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
 					mode = 0;
 			}
+			PROF_MARK(4);
 			if (walk) {
 				if (hdr_eof) {
 					e.status = SCAN_EOF;
@@ -823,18 +861,31 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 					ring.idle();
 				}
 			}
-			__threadfence(); /* records reach L2 before they are announced */
+#if F2_FENCE_GPU
+			__threadfence();
+#else
+			/* records are complete before they are announced; producer and consumers run on the
+			 * same SM, so CTA scope orders the global stores for them */
+			__threadfence_block();
+#endif
 			if (can)
 				vol_st(&sm.prod[slot], ++prodn);
 		}
 		__threadfence_block();
+		PROF_FLUSH(0);
 		if (lane == 0)
 			atomicAdd(&sm.scan_done, 1u);
 	} else {
 		/* ================= worker warps: claim a slot, decode its pending records ================= */
+#ifdef F2_SKIPMASK
+		if ((F2_SKIPMASK >> warp) & 1)
+			return; /* tuning: leave this warp's issue slots to the scan warp of its SM sub-partition */
+#endif
 		uint32_t *wb = sm.wb[warp];
 		uint32_t rot = (uint32_t)warp * 5u, nap = 64u;
+		PROF_DECL;
 		for (;;) {
+			PROF_MARK(0); /* 8+0: decode */
 			const bool done = vol_ld(&sm.scan_done) == (uint32_t)NSCAN;
 			__threadfence_block();
 			const bool r0 = vol_ld(&sm.prod[lane]) != vol_ld(&sm.cons[lane]) && !vol_ld(&sm.busy[lane]);
@@ -842,10 +893,13 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 			const unsigned long long m = (unsigned long long)__ballot_sync(0xFFFFFFFFu, r0) |
 						     ((unsigned long long)__ballot_sync(0xFFFFFFFFu, r1) << 32);
 			if (!m) {
-				if (done)
+				if (done) {
+					PROF_FLUSH(8);
 					break;
+				}
 				__nanosleep(nap); /* idle: back off, the scan warps need the issue slots */
 				nap = nap < 2048u ? nap * 2u : nap;
+				PROF_MARK(1); /* 8+1: idle */
 				continue;
 			}
 			nap = 64u;
@@ -860,6 +914,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 			got = __shfl_sync(0xFFFFFFFFu, got, 0);
 			if (!got)
 				continue;
+			PROF_MARK(2); /* 8+2: claim */
 			__threadfence_block();
 			uint32_t c = vol_ld(&sm.cons[slot]);
 			const uint32_t p = vol_ld(&sm.prod[slot]);
@@ -867,9 +922,11 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 			if (nrec > (uint32_t)KMAX)
 				nrec = KMAX;
 			const uint8_t *slot_ring = cta_ring + (size_t)slot * RING_D * REC_BYTES;
+			DevStream d;
+			uint32_t d_id = 0xFFFFFFFFu;
 			for (uint32_t k = 0; k < nrec; k++, c++)
 				decode_record<CKS>(sm, a, wb, slot, lane, slot_ring + (size_t)(c % RING_D) * REC_BYTES,
-						   cta_hist + slot * HIST_WORDS);
+						   cta_hist + slot * HIST_WORDS, d, d_id);
 			__threadfence_block();
 			if (lane == 0) {
 				vol_st(&sm.cons[slot], c);

@@ -28,27 +28,32 @@ ACM_HD uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t sh)
 
 /* ------------------------------------------------------------------ walk */
 
-/* uni16 addressing in bytes: page id * 256; the selector page starts at 0 */
-constexpr uint32_t UNI_HALT8 = (uint32_t)ACM_UNI_HALT << 8;
-constexpr uint32_t UNI_BAD8 = (uint32_t)ACM_UNI_BAD << 8;
+/* uni16 addressing in bytes: page id << UNI_PSHIFT; the selector page starts at 0 */
+constexpr uint32_t UNI_PSHIFT = ACM_UNI_KBITS + 1;
+constexpr uint32_t UNI_HALT8 = (uint32_t)ACM_UNI_HALT << UNI_PSHIFT;
+constexpr uint32_t UNI_BAD8 = (uint32_t)ACM_UNI_BAD << UNI_PSHIFT;
 constexpr uint32_t MSK_SEL = 0x1FFFu, MSK_K = (1u << ACM_UNI_KBITS) - 1u;
 
 /*
- * State of one lane's column walk: P = bit position, lo = the 32 stream bits at P, s8 = byte
- * offset of the current page in uni16, msk = index mask of that page (13 bits at a selector,
- * ACM_UNI_KBITS inside a prefix-coded column).
+ * State of one lane's column walk: P = bit position, s8 = byte offset of the current page in
+ * uni16, msk = index mask of that page (13 bits at a selector, ACM_UNI_KBITS inside a
+ * prefix-coded column).  One step: w = the 32 stream bits at P; e = uni16 entry at
+ * walk_index(s, w); walk_next(s, e).
  */
 struct Walk {
-	uint32_t P, lo, s8, msk;
+	uint32_t P, s8, msk;
 };
 
-ACM_HD uint32_t walk_index(const Walk &s) { return s.s8 + ((s.lo & s.msk) << 1); }
+ACM_HD uint32_t walk_index(const Walk &s, uint32_t w) { return s.s8 + ((w & s.msk) << 1); }
 
-/* state part of applying entry e (P and lo are the caller's business) */
-ACM_HD void walk_next(Walk &s, uint32_t e)
+/* apply entry e; returns true when the lane is at a column selector afterwards */
+ACM_HD bool walk_next(Walk &s, uint32_t e)
 {
-	s.s8 = e & 0xFF00u;
-	s.msk = s.s8 == 0u ? MSK_SEL : MSK_K;
+	s.P += e & 0xFFu;
+	s.s8 = (e & 0xFF00u) << (UNI_PSHIFT - 8u);
+	const bool at_sel = s.s8 == 0u;
+	s.msk = at_sel ? MSK_SEL : MSK_K;
+	return at_sel;
 }
 
 /* ------------------------------------------------------------------ unpack */
@@ -139,7 +144,8 @@ ACM_HD int unpack_t(const SR &sr, uint32_t P, uint32_t limit, uint32_t sub, cons
 	return (seen & 0x8000u) != 0u;
 }
 
-/* f_linear (decode.c:196-206): sliding 64-bit window, branch-free refill */
+/* f_linear (decode.c:196-206): sliding 64-bit window; the word that the next refill will need
+ * is fetched one refill ahead, so that no value waits on a load */
 template <typename SR>
 ACM_HD void unpack_linear(const SR &sr, uint32_t P, uint32_t ind, const ColOut &o)
 {
@@ -147,7 +153,8 @@ ACM_HD void unpack_linear(const SR &sr, uint32_t P, uint32_t ind, const ColOut &
 	const int mid = 1 << (ind - 1);
 	const uint32_t i = P >> 5, sh = P & 31u;
 	unsigned long long win = (((unsigned long long)sr.word(i + 1) << 32) | sr.word(i)) >> sh;
-	uint32_t avail = 64u - sh, nx = i + 2;
+	uint32_t avail = 64u - sh, nx = i + 3;
+	uint32_t nextw = sr.word(i + 2);
 	uint32_t w[8];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -161,8 +168,9 @@ ACM_HD void unpack_linear(const SR &sr, uint32_t P, uint32_t ind, const ColOut &
 		win >>= ind;
 		avail -= ind;
 		if (avail <= 32u) {
-			win |= (unsigned long long)sr.word(nx) << avail;
+			win |= (unsigned long long)nextw << avail;
 			avail += 32u;
+			nextw = sr.word(nx);
 			nx++;
 		}
 	}

@@ -25,6 +25,7 @@ struct KernelArgs {
 	uint32_t *errflag;        /* set non-zero on an internal failure (e.g. copy timeout) */
 	uint32_t *hist;           /* fast kernel: per-CTA, per-slot transform history (256 words each) */
 	uint8_t *ring;            /* fast kernel 2: per-CTA, per-slot ring of block records */
+	unsigned long long *prof; /* 64 counters, only written by -DF2_PROF tuning builds */
 	/* generic kernel, resumable decode (acm_stream.cu): when resume_hist != NULL stream i of the
 	 * slice starts from / leaves its per-stage history at resume_hist + i * resume_stride (2*cols
 	 * words); a stream whose DevStream::resume is 0 still starts from zero history.

@@ -104,10 +104,10 @@ void acm_tables_build(acm_tables *t)
 		}
 	}
 	/* the scan walk as one state machine */
-	for (b = 0; b < 128; b++) {
-		t->uni16[ACM_UNI_HALT * 128 + b] = (uint16_t)(ACM_UNI_HALT << 8);
-		t->uni16[ACM_UNI_BAD * 128 + b] = (uint16_t)(ACM_UNI_BAD << 8);
-		t->uni16[ACM_UNI_SKIP6 * 128 + b] = (uint16_t)(6u | (ACM_UNI_SEL << 8));
+	for (b = 0; b < ACM_UNI_PSIZE; b++) {
+		t->uni16[ACM_UNI_HALT * ACM_UNI_PSIZE + b] = (uint16_t)(ACM_UNI_HALT << 8);
+		t->uni16[ACM_UNI_BAD * ACM_UNI_PSIZE + b] = (uint16_t)(ACM_UNI_BAD << 8);
+		t->uni16[ACM_UNI_SKIP6 * ACM_UNI_PSIZE + b] = (uint16_t)(6u | (ACM_UNI_SEL << 8));
 	}
 	for (kt = 0; kt < 8; kt++) {
 		int rem;
@@ -132,7 +132,7 @@ void acm_tables_build(acm_tables *t)
 				pos -= 8 - (int)nb;
 				next = rows >= rem ? ACM_UNI_SEL : ACM_UNI_K0 + kt * 15 + (rem - rows - 1);
 				if (rem < 16) {
-					t->uni16[(ACM_UNI_K0 + kt * 15 + rem - 1) * 128 + b] = (uint16_t)(pos | (next << 8));
+					t->uni16[(ACM_UNI_K0 + kt * 15 + rem - 1) * ACM_UNI_PSIZE + b] = (uint16_t)(pos | (next << 8));
 				} else {
 					unsigned idx = ((unsigned)b << 5) | (unsigned)sel_of_kt[kt];
 					t->uni16[idx] = (uint16_t)((5 + pos) | (next << 8));

@@ -40,7 +40,7 @@
  *               is (bits to advance) | (next page id << 8).  The state "at a column selector" is
  *               the 8192-entry page 0 (index = 13 stream bits: selector + first payload byte);
  *               "inside a prefix-coded column of type kt with rem rows to come" is page
- *               ACM_UNI_K0 + kt*15 + rem-1 (index = 7 stream bits; whole symbols, row cap applied);
+ *               ACM_UNI_K0 + kt*15 + rem-1 (index = ACM_UNI_KBITS stream bits; whole symbols, row cap applied);
  *               a fixed-size filler advances over its whole payload in one step (the 261 bits of a
  *               16-bit linear column as 255 + the SKIP6 page); a bad selector (f_bad,
  *               decode.c:190-194) leads to the BAD page; HALT and BAD entries advance 0 bits
@@ -55,14 +55,18 @@
 #define ACM_K8_TYPES 8
 #define ACM_K8_SIZE (ACM_K8_TYPES * 256)
 #define ACM_T_SIZE (3 * 128)
-/* uni16 page ids; a page = 128 entries = 256 bytes, so (id << 8) is the page's byte offset */
-#define ACM_UNI_SEL 0     /* ids 0..63: the 8192-entry selector page */
-#define ACM_UNI_K0 64     /* (kt, rem) -> 64 + kt * 15 + (rem - 1), rem = 1..15 */
-#define ACM_UNI_HALT 184
-#define ACM_UNI_BAD 185
-#define ACM_UNI_SKIP6 186
-#define ACM_UNI_PAGES 187
-#define ACM_UNI_KBITS 7   /* index width of the prefix-code pages */
+/* uni16 page ids; a page = 2^ACM_UNI_KBITS entries, so (id << (ACM_UNI_KBITS + 1)) is the page's
+ * byte offset */
+#ifndef ACM_UNI_KBITS
+#define ACM_UNI_KBITS 8   /* index width of the prefix-code pages (7 or 8) */
+#endif
+#define ACM_UNI_PSIZE (1 << ACM_UNI_KBITS)
+#define ACM_UNI_SEL 0                            /* the 8192-entry selector page: ids 0 .. K0-1 */
+#define ACM_UNI_K0 (8192 >> ACM_UNI_KBITS)       /* (kt, rem) -> K0 + kt * 15 + (rem - 1), rem = 1..15 */
+#define ACM_UNI_HALT (ACM_UNI_K0 + 120)
+#define ACM_UNI_BAD (ACM_UNI_K0 + 121)
+#define ACM_UNI_SKIP6 (ACM_UNI_K0 + 122)
+#define ACM_UNI_PAGES (ACM_UNI_K0 + 123)
 
 typedef struct acm_tables {
 	uint64_t k8[ACM_K8_SIZE];
@@ -72,7 +76,7 @@ typedef struct acm_tables {
 	uint8_t kind[32];  /* per selector: class | (subtype << 3); see ACM_CLS_* */
 	uint8_t pad[32];
 	uint64_t k8w[ACM_K8_SIZE]; /* worker-side prefix-code step, see above */
-	uint16_t uni16[ACM_UNI_PAGES * 128]; /* scan walk of fast kernel 2, see above */
+	uint16_t uni16[ACM_UNI_PAGES * ACM_UNI_PSIZE]; /* scan walk of fast kernel 2, see above */
 	uint32_t nib2w[256];       /* two 4-bit two's complement values -> two int16 in one word */
 } acm_tables;
 

@@ -35,5 +35,13 @@ for _ in range(args.runs):
     plan.run(d_blob, d_out, cs)
     torch.cuda.synchronize()
     print("ms", plan.last_ms(), "Msamples/s", s["total_values"].sum() / plan.last_ms() / 1e3)
+if os.environ.get("F2_PROF"):
+    import ctypes as C
+    buf = (C.c_uint64 * 64)()
+    api.lib().acm_gpu_plan_debug_counters.argtypes = [C.c_void_p, C.c_void_p]
+    api.lib().acm_gpu_plan_debug_counters(plan._h, buf)
+    v = [x / args.runs / 1e6 for x in buf]
+    print("scan  Mcycles/run (all warps): publish %.1f flow %.1f hyst %.1f head %.1f steps %.1f topup %.1f" % tuple(v[0:6]))
+    print("work  Mcycles/run (all warps): decode %.1f idle %.1f claim %.1f" % tuple(v[8:11]))
 plan.fetch(s, cs)
 assert np.all(s["status"] == 0)
