@@ -172,6 +172,8 @@ struct Segment {
 	int fast_ctas, gen_ctas;          /* grid sizes; segments may run concurrently, so each has */
 	size_t hist_off, scratch_off;     /* its own history / scratch region (offsets in words) */
 	size_t ring_off;                  /* block-record rings of the fast kernel (offset in bytes) */
+	size_t ctl_off;                   /* slot control words (offset in bytes) */
+	uint32_t n_scan, n_slots;         /* fast kernel 2 geometry: scan CTAs, slots in use */
 };
 
 struct acm_gpu_plan {
@@ -193,6 +195,8 @@ struct acm_gpu_plan {
 	uint32_t *d_hist;    /* fast kernel history, fast_ctas * fast_hist_words_per_cta() words */
 	uint8_t *d_ring;     /* fast kernel 2 block-record rings (inside d_ring_alloc) */
 	uint8_t *d_ring_alloc;
+	uint8_t *d_ctl;      /* fast kernel 2 slot control words */
+	size_t ctl_bytes;
 	unsigned long long *d_prof; /* 64 counters of -DF2_PROF tuning builds */
 	int fast_gen;        /* 2: acm_fast2.cu (default), 1: acm_fast.cu (opts->kernel == 2) */
 	int fast_ctas;
@@ -215,6 +219,7 @@ static void plan_free(acm_gpu_plan *p)
 	cudaFree(p->scratch.buf);
 	cudaFree(p->d_hist);
 	cudaFree(p->d_ring_alloc);
+	cudaFree(p->d_ctl);
 	cudaFree(p->d_prof);
 	if (p->ev0)
 		cudaEventDestroy(p->ev0);
@@ -264,6 +269,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
 	p->d_ring = nullptr;
 	p->d_ring_alloc = nullptr;
+	p->d_ctl = nullptr;
+	p->ctl_bytes = 0;
 	p->d_prof = nullptr;
 	p->fast_gen = opts->kernel == 2 ? 1 : 2;
 	p->device = dev;
@@ -390,19 +397,31 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	CU(cudaEventCreate(&p->ev1));
 
 	{
-		const uint64_t per = (uint64_t)(p->fast_gen == 2 ? fast2_slots_per_cta() : fast_slots_per_cta());
-		const size_t hist_per_cta = p->fast_gen == 2 ? fast2_hist_words_per_cta() : fast_hist_words_per_cta();
+		const uint64_t per = (uint64_t)fast_slots_per_cta();
 		const size_t stride = generic_scratch_words(max_blen, max_cols);
 		const size_t budget = ((size_t)4 << 30) / p->seg.size(); /* scratch bytes per segment */
-		size_t hist_words = 0, scratch_words = 0, ring_bytes = 0;
+		size_t hist_words = 0, scratch_words = 0, ring_bytes = 0, ctl_bytes = 0;
 		for (Segment &sg : p->seg) {
-			uint64_t groups = (sg.n_fast + per - 1) / per;
-			sg.fast_ctas = (uint64_t)p->sm_count < groups ? p->sm_count : (int)groups;
 			sg.hist_off = hist_words;
-			hist_words += (size_t)sg.fast_ctas * hist_per_cta;
 			sg.ring_off = ring_bytes;
-			if (p->fast_gen == 2)
-				ring_bytes += (size_t)sg.fast_ctas * fast2_ring_bytes_per_cta();
+			sg.ctl_off = ctl_bytes;
+			sg.n_scan = sg.n_slots = 0;
+			if (p->fast_gen == 2) {
+				uint32_t n_work = 0;
+				if (sg.n_fast) {
+					fast2_geometry(sg.n_fast, p->sm_count, &sg.n_scan, &n_work, &sg.n_slots);
+					sg.fast_ctas = (int)(sg.n_scan + n_work);
+				} else {
+					sg.fast_ctas = 0;
+				}
+				hist_words += (size_t)sg.n_slots * fast2_hist_words_per_slot();
+				ring_bytes += (size_t)sg.n_slots * fast2_ring_bytes_per_slot();
+				ctl_bytes += ((size_t)sg.n_slots * fast2_ctl_bytes_per_slot() + 255u) & ~(size_t)255u;
+			} else {
+				uint64_t groups = (sg.n_fast + per - 1) / per;
+				sg.fast_ctas = (uint64_t)p->sm_count < groups ? p->sm_count : (int)groups;
+				hist_words += (size_t)sg.fast_ctas * fast_hist_words_per_cta();
+			}
 			int ctas = p->sm_count * 4;
 			if ((uint64_t)ctas > sg.n_gen)
 				ctas = (int)sg.n_gen;
@@ -414,6 +433,10 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			p->fast_ctas = std::max(p->fast_ctas, sg.fast_ctas);
 			p->generic_ctas = std::max(p->generic_ctas, sg.gen_ctas);
 		}
+		if (max_fast && ctl_bytes) {
+			CU(cudaMalloc(&p->d_ctl, ctl_bytes));
+			p->ctl_bytes = ctl_bytes;
+		}
 		if (max_fast)
 			CU(cudaMalloc(&p->d_hist, hist_words * 4 + 16));
 		if (max_fast && ring_bytes) {
@@ -424,6 +447,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			if ((lo >> 32) != ((lo + ring_bytes) >> 32)) {
 				cudaFree(p->d_ring_alloc);
 				p->d_ring_alloc = nullptr;
+	p->d_ctl = nullptr;
+	p->ctl_bytes = 0;
 	p->d_prof = nullptr;
 				CU(cudaMalloc(&p->d_ring_alloc, 2 * ring_bytes + 512));
 				lo = ((uintptr_t)p->d_ring_alloc + 255u) & ~(uintptr_t)255u;
@@ -472,6 +497,10 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 	a.hist = p->d_hist ? p->d_hist + sg.hist_off : nullptr;
 	a.ring = p->d_ring ? p->d_ring + sg.ring_off : nullptr;
 	a.prof = p->d_prof;
+	a.slotctl = p->d_ctl ? p->d_ctl + sg.ctl_off : nullptr;
+	a.scan_done = p->d_counters + 4 * g + 2;
+	a.n_scan = sg.n_scan;
+	a.n_slots = sg.n_slots;
 	a.resume_hist = nullptr;
 	a.resume_stride = 0;
 	a.end_pos = nullptr;
@@ -507,6 +536,8 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 	}
 	CU(cudaSetDevice(p->device));
 	CU(cudaMemsetAsync(p->d_counters, 0, (4 * p->seg.size() + 4) * sizeof(uint32_t), st));
+	if (p->d_ctl)
+		CU(cudaMemsetAsync(p->d_ctl, 0, p->ctl_bytes, st));
 	CU(cudaEventRecord(p->ev0, st));
 	for (size_t g = 0; g < p->seg.size(); g++)
 		if (plan_run_segment(p, g, d_blob, d_out, st) < 0)
@@ -699,6 +730,8 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 	}
 	/* the cursors are zeroed before anything else is queued: the copy-in stream waits for it */
 	CUR(cudaMemsetAsync(plan->d_counters, 0, (4 * ns + 4) * sizeof(uint32_t), w.s_in));
+	if (plan->d_ctl)
+		CUR(cudaMemsetAsync(plan->d_ctl, 0, plan->ctl_bytes, w.s_in));
 	for (size_t g = 0; g < ns; g++) {
 		const Segment &sg = plan->seg[g];
 		cudaStream_t sk = w.s_k[g % MAX_SEG];

@@ -58,7 +58,10 @@ constexpr int COLS = 128;
 constexpr int BLEN = COLS * ROWS;        /* 2048 */
 constexpr int NSCAN = 2;                 /* scan warps (the highest warp ids) */
 #ifndef F2_W
-#define F2_W 12
+#define F2_W 16        /* worker warps of a decode CTA */
+#endif
+#ifndef F2_SW
+#define F2_SW 8        /* scan warps of a scan CTA */
 #endif
 #ifndef F2_RING_D
 #define F2_RING_D 8
@@ -69,15 +72,14 @@ constexpr int NSCAN = 2;                 /* scan warps (the highest warp ids) */
 #ifndef F2_PERIOD
 #define F2_PERIOD 16
 #endif
-#ifndef F2_FENCE_GPU
-#define F2_FENCE_GPU 0 /* 1: publish records behind a device-scope fence (scan and decode share the SM: not needed) */
-#endif
 #ifndef F2_HYST
 #define F2_HYST 1      /* scan warp sleeps while every lane is at least RING_D/2 records ahead */
 #endif
-constexpr int W = F2_W;                  /* worker warps */
-constexpr int S = 32 * NSCAN;            /* stream slots per CTA */
-constexpr int THREADS = 32 * (W + NSCAN);
+constexpr int W = F2_W;                  /* worker warps per decode CTA */
+constexpr int SW = F2_SW;                /* scan warps per scan CTA */
+constexpr int SLOTS = 32 * SW;           /* stream slots per scan CTA */
+constexpr int THREADS = 32 * W;
+constexpr int MAXOWN = 128;              /* slots a decode CTA can own */
 constexpr int RING_D = F2_RING_D;              /* block records a scan lane may be ahead of the decode */
 constexpr int REC_BYTES = 288;           /* 128 x u16 column offsets + 32-byte Rec */
 constexpr int RW = F2_RW;               /* ring words per scan lane (+1 duplicate of word 0) */
@@ -94,6 +96,7 @@ constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [1
 constexpr int KMAX = 4;                  /* blocks a worker decodes per slot claim */
 
 static_assert(WB_WORDS >= XWORDS, "transform layout must fit the worker buffer");
+static_assert(SW <= W, "scan CTAs are launched with the decode CTAs' thread count");
 
 
 struct Rec {
@@ -107,22 +110,34 @@ struct Rec {
 	uint32_t pad;
 };
 
-struct Smem {
-	uint64_t k8w[ACM_K8_SIZE];
+/* per-slot control words in global memory, shared by the slot's scan lane and the decode CTA
+ * that owns the slot */
+struct SlotCtl {
+	uint32_t prod; /* records published (scan lane writes) */
+	uint32_t cons; /* records consumed (decode CTA writes) */
+	uint32_t dead; /* desc+1 of a stream the decode side finalised early */
+	uint32_t pad;
+};
+
+struct SmemScan {
 	uint16_t uni16[ACM_UNI_PAGES * ACM_UNI_PSIZE];
+	uint32_t ring[SW][(RW + 1) * 32]; /* [word][lane] */
+};
+
+struct SmemWork {
+	uint64_t k8w[ACM_K8_SIZE];
 	uint32_t nib2w[256];
-	uint32_t ring[NSCAN][(RW + 1) * 32]; /* [word][lane] */
 	uint32_t wb[W][WB_WORDS];
-	unsigned long long cks[S];
-	uint32_t prod[S];  /* records published per slot (scan lane writes) */
-	uint32_t cons[S];  /* records consumed per slot (owning worker writes) */
-	uint32_t busy[S];  /* slot claimed by a worker */
-	uint32_t pos[S];   /* words delivered so far of the slot's current stream */
-	uint32_t dead[S];  /* desc+1 of a stream a worker finalised early */
+	unsigned long long cks[MAXOWN];
+	uint32_t cons[MAXOWN]; /* records consumed per owned slot */
+	uint32_t busy[MAXOWN]; /* slot claimed by a worker warp */
+	uint32_t pos[MAXOWN];  /* words delivered so far of the slot's current stream */
+	uint32_t dead[MAXOWN]; /* local copy of SlotCtl::dead */
 	uint32_t info[32];
 	uint16_t t[ACM_T_SIZE];
-	uint32_t scan_done;
 };
+
+constexpr size_t SMEM_BYTES = sizeof(SmemScan) > sizeof(SmemWork) ? sizeof(SmemScan) : sizeof(SmemWork);
 
 #ifndef F2_PROF
 #define F2_PROF 0
@@ -137,7 +152,7 @@ struct Smem {
 #define PROF_FLUSH(base) do { } while (0)
 #endif
 
-static_assert(sizeof(Smem) <= 232448, "Smem exceeds the 227 KB a CTA can opt in to");
+static_assert(SMEM_BYTES <= 232448, "shared memory exceeds the 227 KB a CTA can opt in to");
 
 /* ------------------------------------------------------------------ helpers */
 
@@ -526,8 +541,9 @@ juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint
 /* ------------------------------------------------------------------ worker: one block record */
 
 template <bool CKS>
-__device__ __forceinline__ void decode_record(Smem &sm, const KernelArgs &a, uint32_t *wb, int slot, int lane,
-					      const uint8_t *recbase, uint32_t *gh, DevStream &d, uint32_t &d_id)
+__device__ __forceinline__ void decode_record(SmemWork &sm, const KernelArgs &a, uint32_t *wb, int slot, int lane,
+					      const uint8_t *recbase, uint32_t *gh, DevStream &d, uint32_t &d_id,
+					      SlotCtl *ctl)
 {
 	Rec e;
 	{
@@ -683,6 +699,7 @@ __device__ __forceinline__ void decode_record(Smem &sm, const KernelArgs &a, uin
 			a.words[d.index] = pos;
 			a.cks[d.index] = a.fmt.checksums ? sm.cks[slot] : 0ull;
 			vol_st(&sm.dead[slot], e.desc + 1u);
+			vol_st(&ctl->dead, e.desc + 1u); /* the slot's scan lane stops walking this stream */
 		}
 	}
 	__syncwarp();
@@ -690,263 +707,344 @@ __device__ __forceinline__ void decode_record(Smem &sm, const KernelArgs &a, uin
 
 /* ------------------------------------------------------------------ kernel */
 
+/*
+ * Scan CTA: SW scan warps, lane = stream slot (global slot id g = blockIdx * SLOTS + 32 * warp +
+ * lane, slots >= a.n_slots stay empty).  A scan CTA has no decode work on its SM: the walk is a
+ * dependent chain of shared-memory lookups, and sharing the SM's load/store pipe and issue slots
+ * with decode warps doubled its step time (profiles/r01_ncu_fast2.md).
+ */
+__device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int warp, int lane)
+{
+	const uint32_t g = (uint32_t)blockIdx.x * SLOTS + 32u * (uint32_t)warp + (uint32_t)lane;
+	const bool enabled = g < a.n_slots;
+	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl) + g;
+	uint8_t *const slot_ring = a.ring + (size_t)g * RING_D * REC_BYTES;
+	ScanRing ring;
+	ring.rw = &sm.ring[warp][lane];
+	ring.saddr = (uint32_t)__cvta_generic_to_shared(ring.rw);
+	ring.idle();
+	bool active = false, exhausted = !enabled;
+	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
+	PROF_DECL;
+	for (;;) {
+		PROF_MARK(0); /* 0: round tail (publish) */
+		uint32_t cons = 0, dead = 0;
+		if (enabled) {
+			const uint4 c4 = __ldcv(reinterpret_cast<const uint4 *>(ctl)); /* never a stale line */
+			cons = c4.y;
+			dead = c4.z;
+		}
+		if (active && dead == cur + 1u) {
+			active = false; /* the decode side found a corrupt t-code: abandon the stream */
+			ring.idle();
+		}
+		if (!active && !exhausted) {
+			const uint32_t idx = atomicAdd(a.counter, 1u);
+			if (idx < a.count) {
+				const DevStream d = a.streams[idx];
+				cur = idx;
+				P = d.bit0;
+				blk = 0;
+				limit = d.file_end + 8u;
+				n_attempt = d.n_attempt;
+				ring.start(a.blob + d.base_off, a.blob_room > d.base_off ? a.blob_room - d.base_off : 0,
+					   d.file_end, P);
+				active = true;
+			} else {
+				exhausted = true;
+			}
+		}
+		const uint32_t lead = prodn - cons;
+		const bool can = active && lead < (uint32_t)RING_D;
+		if (!__any_sync(0xFFFFFFFFu, can)) {
+			if (!__any_sync(0xFFFFFFFFu, active))
+				break; /* every lane is out of streams */
+			__nanosleep(500);
+			PROF_MARK(1); /* 1: blocked by flow control */
+			continue;
+		}
+#if F2_HYST
+		if (!__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2))) {
+			__nanosleep(300); /* nobody is close to starving the decode: let lanes bunch up */
+			PROF_MARK(2); /* 2: hysteresis sleep */
+			continue;
+		}
+#endif
+		PROF_MARK(3); /* 3: round head (retire / acquire) */
+		/* ---- one record per lane that can produce */
+		uint8_t *const recbase = slot_ring + (size_t)(prodn % RING_D) * REC_BYTES;
+		Rec e;
+		e.pblock = P; e.pend = P; e.desc = cur; e.blk = blk; e.status = SCAN_EOF; e.ncols = 0; e.val = 0; e.pad = 0;
+		Walk s;
+		s.P = P;
+		s.s8 = UNI_HALT8;
+		s.msk = MSK_K;
+		int mode = 0; /* 0 not walking (any more), 1 block header pending, 2 walking */
+		bool walk = false;
+		if (can) {
+			if (blk >= n_attempt) {
+				/* nothing (more) to attempt: clean end */
+				e.blk |= 0x80000000u;
+			} else {
+				walk = true;
+				mode = 1;
+			}
+		}
+		const unsigned long long rec64 = (unsigned long long)(uintptr_t)recbase;
+		uint32_t cp = (uint32_t)rec64;
+		const uint32_t cph = (uint32_t)(rec64 >> 32), cpend = cp + 2u * COLS;
+		bool hdr_eof = false;
+		while (__any_sync(0xFFFFFFFFu, mode != 0)) {
+			PROF_MARK(4); /* 4: walk steps */
+			ring.topup(s.P);
+			if (mode == 1) {
+				/* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
+				if (s.P + 20u > limit) {
+					hdr_eof = true;
+					mode = 0;
+				} else if (s.P < ring.ready_p) {
+					const uint32_t *rp = ring.rw + ((s.P >> 5) & (RW - 1)) * 32u;
+					const uint32_t w = fsr(rp[0], rp[32], s.P);
+					e.val = (int)((w >> 4) & 0xFFFFu);
+					s.P += 20u;
+					s.s8 = 0u;
+					s.msk = MSK_SEL;
+					mode = 2;
+				}
+			}
+			PROF_MARK(5); /* 5: top-up + header */
+#pragma unroll 4
+			for (int k = 0; k < SCAN_PERIOD; k++)
+				fast_step(s, cp, cph, cpend, P, ring.rw, ring.ready_p,
+					  reinterpret_cast<const unsigned char *>(sm.uni16));
+			if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
+				mode = 0;
+		}
+		PROF_MARK(4);
+		if (walk) {
+			if (hdr_eof) {
+				e.status = SCAN_EOF;
+			} else if (s.s8 == UNI_HALT8 && s.P <= limit) {
+				/* 128 columns, every read inside the stream */
+				e.status = SCAN_OK;
+				e.ncols = COLS;
+				e.pend = s.P;
+			} else {
+				/* bad selector, or the stream ended inside the block: walk it again with the
+				 * reference's verdicts (rare: at most once per stream) */
+				const DevStream d = a.streams[cur];
+				BitReader br;
+				br.init(reinterpret_cast<const uint32_t *>(a.blob + d.base_off), d.file_end);
+				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS,
+								 reinterpret_cast<uint16_t *>(recbase), P, a.tables->kind,
+								 a.tables->k8);
+				e.status = sc.status;
+				e.ncols = sc.ncols;
+				e.pend = sc.end;
+				e.val = sc.val;
+				s.P = sc.end;
+			}
+			P = s.P;
+			blk++;
+			if (e.status != SCAN_OK || blk >= n_attempt)
+				e.blk |= 0x80000000u;
+		}
+		if (can) {
+			uint4 *rp = reinterpret_cast<uint4 *>(recbase + 256);
+			rp[0] = make_uint4(e.pblock, e.pend, e.desc, e.blk);
+			rp[1] = make_uint4((uint32_t)e.status, e.ncols, (uint32_t)e.val, 0u);
+			if (e.blk >> 31) {
+				active = false;
+				ring.idle();
+			}
+		}
+		/* the records are in L2 before they are announced to the decode CTA (another SM) */
+		__threadfence();
+		if (can)
+			vol_st(&ctl->prod, ++prodn);
+	}
+	__threadfence();
+	PROF_FLUSH(0);
+	if (lane == 0)
+		atomicAdd(a.scan_done, 1u);
+}
+
+/*
+ * Decode CTA number w of n_work owns the slots g = w, w + n_work, w + 2 n_work, ... (local
+ * index j).  Its worker warps claim an owned slot that has records pending and decode them in
+ * order.
+ */
+template <bool CKS>
+__device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int warp, int lane)
+{
+	const uint32_t w = (uint32_t)blockIdx.x - a.n_scan, n_work = (uint32_t)gridDim.x - a.n_scan;
+	const uint32_t J = a.n_slots > w ? (a.n_slots - w + n_work - 1u) / n_work : 0u; /* owned slots */
+	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl);
+	uint32_t *wb = sm.wb[warp];
+	uint32_t rot = (uint32_t)warp * 5u, nap = 64u;
+	PROF_DECL;
+	for (;;) {
+		PROF_MARK(0); /* 8+0: decode */
+		const bool done = *reinterpret_cast<volatile uint32_t *>(a.scan_done) == a.n_scan * (uint32_t)SW;
+		__threadfence();
+		uint32_t rdy = 0; /* bit k: owned slot lane + 32 k has records pending and is not claimed */
+#pragma unroll
+		for (int k = 0; k < MAXOWN / 32; k++) {
+			const uint32_t j = (uint32_t)lane + 32u * k;
+			if (j < J && !vol_ld(&sm.busy[j]) && vol_ld(&ctl[w + n_work * j].prod) != vol_ld(&sm.cons[j]))
+				rdy |= 1u << k;
+		}
+		uint32_t m[MAXOWN / 32];
+		uint32_t any = 0;
+#pragma unroll
+		for (int k = 0; k < MAXOWN / 32; k++) {
+			m[k] = __ballot_sync(0xFFFFFFFFu, (rdy >> k) & 1u);
+			any |= m[k];
+		}
+		if (!any) {
+			if (done) {
+				PROF_FLUSH(8);
+				break;
+			}
+			__nanosleep(nap); /* idle: back off */
+			nap = nap < 2048u ? nap * 2u : nap;
+			PROF_MARK(1); /* 8+1: idle */
+			continue;
+		}
+		nap = 64u;
+		/* round robin from a rotating start so that every slot gets its turn */
+		int slot = -1;
+		rot &= (uint32_t)(MAXOWN - 1);
+#pragma unroll
+		for (int t = 0; t <= MAXOWN / 32; t++) {
+			const uint32_t k = ((rot >> 5) + (uint32_t)t) & (MAXOWN / 32 - 1);
+			uint32_t mk = m[0];
+#pragma unroll
+			for (int q = 1; q < MAXOWN / 32; q++)
+				mk = k == (uint32_t)q ? m[q] : mk;
+			if (t == 0)
+				mk &= ~0u << (rot & 31u); /* first group: only at or after the start position */
+			if (slot < 0 && mk)
+				slot = (int)(32u * k) + __ffs((int)mk) - 1;
+		}
+		if (slot < 0) { /* only bits before the start position in its group: wrap around */
+			rot = 0;
+			continue;
+		}
+		rot = (uint32_t)slot + 1u;
+		uint32_t got = 0;
+		if (lane == 0)
+			got = atomicCAS(&sm.busy[slot], 0u, 1u) == 0u;
+		got = __shfl_sync(0xFFFFFFFFu, got, 0);
+		if (!got)
+			continue;
+		PROF_MARK(2); /* 8+2: claim */
+		__threadfence_block();
+		const uint32_t g = w + n_work * (uint32_t)slot;
+		uint32_t c = vol_ld(&sm.cons[slot]);
+		const uint32_t p = vol_ld(&ctl[g].prod);
+		__threadfence(); /* acquire: the records behind prod */
+		uint32_t nrec = p - c;
+		if (nrec > (uint32_t)KMAX)
+			nrec = KMAX;
+		const uint8_t *slot_ring = a.ring + (size_t)g * RING_D * REC_BYTES;
+		DevStream d;
+		uint32_t d_id = 0xFFFFFFFFu;
+		for (uint32_t k = 0; k < nrec; k++, c++)
+			decode_record<CKS>(sm, a, wb, slot, lane, slot_ring + (size_t)(c % RING_D) * REC_BYTES,
+					   a.hist + (size_t)g * HIST_WORDS, d, d_id, ctl + g);
+		__threadfence(); /* the records have been read before the scan lane may overwrite them */
+		if (lane == 0) {
+			vol_st(&sm.cons[slot], c);
+			vol_st(&ctl[g].cons, c);
+			__threadfence_block();
+			atomicExch(&sm.busy[slot], 0u);
+		}
+		__syncwarp();
+	}
+}
+
 template <bool CKS>
 __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs a)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-	for (int i = tid; i < ACM_K8_SIZE; i += THREADS)
-		sm.k8w[i] = a.tables->k8w[i];
-	for (int i = tid; i < ACM_UNI_PAGES * ACM_UNI_PSIZE / 2; i += THREADS)
-		reinterpret_cast<uint32_t *>(sm.uni16)[i] = reinterpret_cast<const uint32_t *>(a.tables->uni16)[i];
-	for (int i = tid; i < ACM_T_SIZE; i += THREADS)
-		sm.t[i] = a.tables->t[i];
-	for (int i = tid; i < 256; i += THREADS)
-		sm.nib2w[i] = a.tables->nib2w[i];
-	if (tid < 32)
-		sm.info[tid] = make_info(a.tables->kind[tid]);
-	for (int i = tid; i < S; i += THREADS) {
-		sm.prod[i] = 0;
-		sm.cons[i] = 0;
-		sm.busy[i] = 0;
-		sm.dead[i] = 0;
-		sm.pos[i] = 0;
-		sm.cks[i] = 0ull;
-	}
-	for (int i = tid; i < NSCAN * (RW + 1) * 32; i += THREADS)
-		(&sm.ring[0][0])[i] = 0u;
-	if (tid == 0)
-		sm.scan_done = 0;
-	__syncthreads();
-
-	uint8_t *const cta_ring = a.ring + (size_t)blockIdx.x * S * RING_D * REC_BYTES;
-	uint32_t *const cta_hist = a.hist + (size_t)blockIdx.x * S * HIST_WORDS;
-
-	if (warp >= W) {
-		/* ================= scan warps: lane = stream slot ================= */
-		const int sw = warp - W, slot = 32 * sw + lane;
-		uint8_t *const slot_ring = cta_ring + (size_t)slot * RING_D * REC_BYTES;
-		ScanRing ring;
-		ring.rw = &sm.ring[sw][lane];
-		ring.saddr = (uint32_t)__cvta_generic_to_shared(ring.rw);
-		ring.idle();
-		bool active = false, exhausted = false;
-		uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
-		PROF_DECL;
-		for (;;) {
-			PROF_MARK(0); /* 0: round tail (publish) */
-			if (active && vol_ld(&sm.dead[slot]) == cur + 1u) {
-				active = false; /* a worker found a corrupt t-code: abandon the stream */
-				ring.idle();
-			}
-			if (!active && !exhausted) {
-				const uint32_t idx = atomicAdd(a.counter, 1u);
-				if (idx < a.count) {
-					const DevStream d = a.streams[idx];
-					cur = idx;
-					P = d.bit0;
-					blk = 0;
-					limit = d.file_end + 8u;
-					n_attempt = d.n_attempt;
-					ring.start(a.blob + d.base_off, a.blob_room > d.base_off ? a.blob_room - d.base_off : 0,
-						   d.file_end, P);
-					active = true;
-				} else {
-					exhausted = true;
-				}
-			}
-			const uint32_t lead = prodn - vol_ld(&sm.cons[slot]);
-			const bool can = active && lead < (uint32_t)RING_D;
-			if (!__any_sync(0xFFFFFFFFu, can)) {
-				if (!__any_sync(0xFFFFFFFFu, active))
-					break; /* every lane is out of streams */
-				__nanosleep(500);
-				PROF_MARK(1); /* 1: blocked by flow control */
-				continue;
-			}
-#if F2_HYST
-			if (!__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2))) {
-				__nanosleep(300); /* nobody is close to starving the decode: let lanes bunch up */
-				PROF_MARK(2); /* 2: hysteresis sleep */
-				continue;
-			}
-#endif
-			PROF_MARK(3); /* 3: round head (retire / acquire) */
-			/* ---- one record per lane that can produce */
-			uint8_t *const recbase = slot_ring + (size_t)(prodn % RING_D) * REC_BYTES;
-			Rec e;
-			e.pblock = P; e.pend = P; e.desc = cur; e.blk = blk; e.status = SCAN_EOF; e.ncols = 0; e.val = 0; e.pad = 0;
-			Walk s;
-			s.P = P;
-			s.s8 = UNI_HALT8;
-			s.msk = MSK_K;
-			int mode = 0; /* 0 not walking (any more), 1 block header pending, 2 walking */
-			bool walk = false;
-			if (can) {
-				if (blk >= n_attempt) {
-					/* nothing (more) to attempt: clean end */
-					e.blk |= 0x80000000u;
-				} else {
-					walk = true;
-					mode = 1;
-				}
-			}
-			const unsigned long long rec64 = (unsigned long long)(uintptr_t)recbase;
-			uint32_t cp = (uint32_t)rec64;
-			const uint32_t cph = (uint32_t)(rec64 >> 32), cpend = cp + 2u * COLS;
-			bool hdr_eof = false;
-			while (__any_sync(0xFFFFFFFFu, mode != 0)) {
-				PROF_MARK(4); /* 4: walk steps */
-				ring.topup(s.P);
-				if (mode == 1) {
-					/* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
-					if (s.P + 20u > limit) {
-						hdr_eof = true;
-						mode = 0;
-					} else if (s.P < ring.ready_p) {
-						const uint32_t *rp = ring.rw + ((s.P >> 5) & (RW - 1)) * 32u;
-						const uint32_t w = fsr(rp[0], rp[32], s.P);
-						e.val = (int)((w >> 4) & 0xFFFFu);
-						s.P += 20u;
-						s.s8 = 0u;
-						s.msk = MSK_SEL;
-						mode = 2;
-					}
-				}
-				PROF_MARK(5); /* 5: top-up + header */
-#pragma unroll 4
-				for (int k = 0; k < SCAN_PERIOD; k++)
-					fast_step(s, cp, cph, cpend, P, ring.rw, ring.ready_p,
-						  reinterpret_cast<const unsigned char *>(sm.uni16));
-				if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
-					mode = 0;
-			}
-			PROF_MARK(4);
-			if (walk) {
-				if (hdr_eof) {
-					e.status = SCAN_EOF;
-				} else if (s.s8 == UNI_HALT8 && s.P <= limit) {
-					/* 128 columns, every read inside the stream */
-					e.status = SCAN_OK;
-					e.ncols = COLS;
-					e.pend = s.P;
-				} else {
-					/* bad selector, or the stream ended inside the block: walk it again with the
-					 * reference's verdicts (rare: at most once per stream) */
-					const DevStream d = a.streams[cur];
-					BitReader br;
-					br.init(reinterpret_cast<const uint32_t *>(a.blob + d.base_off), d.file_end);
-					const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS,
-									 reinterpret_cast<uint16_t *>(recbase), P, a.tables->kind,
-									 a.tables->k8);
-					e.status = sc.status;
-					e.ncols = sc.ncols;
-					e.pend = sc.end;
-					e.val = sc.val;
-					s.P = sc.end;
-				}
-				P = s.P;
-				blk++;
-				if (e.status != SCAN_OK || blk >= n_attempt)
-					e.blk |= 0x80000000u;
-			}
-			if (can) {
-				uint4 *rp = reinterpret_cast<uint4 *>(recbase + 256);
-				rp[0] = make_uint4(e.pblock, e.pend, e.desc, e.blk);
-				rp[1] = make_uint4((uint32_t)e.status, e.ncols, (uint32_t)e.val, 0u);
-				if (e.blk >> 31) {
-					active = false;
-					ring.idle();
-				}
-			}
-#if F2_FENCE_GPU
-			__threadfence();
-#else
-			/* records are complete before they are announced; producer and consumers run on the
-			 * same SM, so CTA scope orders the global stores for them */
-			__threadfence_block();
-#endif
-			if (can)
-				vol_st(&sm.prod[slot], ++prodn);
-		}
-		__threadfence_block();
-		PROF_FLUSH(0);
-		if (lane == 0)
-			atomicAdd(&sm.scan_done, 1u);
+	if (blockIdx.x < a.n_scan) {
+		SmemScan &sm = *reinterpret_cast<SmemScan *>(smem_raw);
+		for (int i = tid; i < ACM_UNI_PAGES * ACM_UNI_PSIZE / 2; i += THREADS)
+			reinterpret_cast<uint32_t *>(sm.uni16)[i] = reinterpret_cast<const uint32_t *>(a.tables->uni16)[i];
+		for (int i = tid; i < SW * (RW + 1) * 32; i += THREADS)
+			(&sm.ring[0][0])[i] = 0u;
+		__syncthreads();
+		if (warp < SW)
+			scan_cta(a, sm, warp, lane);
 	} else {
-		/* ================= worker warps: claim a slot, decode its pending records ================= */
-#ifdef F2_SKIPMASK
-		if ((F2_SKIPMASK >> warp) & 1)
-			return; /* tuning: leave this warp's issue slots to the scan warp of its SM sub-partition */
-#endif
-		uint32_t *wb = sm.wb[warp];
-		uint32_t rot = (uint32_t)warp * 5u, nap = 64u;
-		PROF_DECL;
-		for (;;) {
-			PROF_MARK(0); /* 8+0: decode */
-			const bool done = vol_ld(&sm.scan_done) == (uint32_t)NSCAN;
-			__threadfence_block();
-			const bool r0 = vol_ld(&sm.prod[lane]) != vol_ld(&sm.cons[lane]) && !vol_ld(&sm.busy[lane]);
-			const bool r1 = vol_ld(&sm.prod[lane + 32]) != vol_ld(&sm.cons[lane + 32]) && !vol_ld(&sm.busy[lane + 32]);
-			const unsigned long long m = (unsigned long long)__ballot_sync(0xFFFFFFFFu, r0) |
-						     ((unsigned long long)__ballot_sync(0xFFFFFFFFu, r1) << 32);
-			if (!m) {
-				if (done) {
-					PROF_FLUSH(8);
-					break;
-				}
-				__nanosleep(nap); /* idle: back off, the scan warps need the issue slots */
-				nap = nap < 2048u ? nap * 2u : nap;
-				PROF_MARK(1); /* 8+1: idle */
-				continue;
-			}
-			nap = 64u;
-			/* round robin from a rotating start so that every slot gets its turn */
-			rot &= 63u;
-			const unsigned long long mr = rot ? (m >> rot) | (m << (64u - rot)) : m;
-			const int slot = (int)((rot + (uint32_t)__ffsll((long long)mr) - 1u) & 63u);
-			rot = (uint32_t)slot + 1u;
-			uint32_t got = 0;
-			if (lane == 0)
-				got = atomicCAS(&sm.busy[slot], 0u, 1u) == 0u;
-			got = __shfl_sync(0xFFFFFFFFu, got, 0);
-			if (!got)
-				continue;
-			PROF_MARK(2); /* 8+2: claim */
-			__threadfence_block();
-			uint32_t c = vol_ld(&sm.cons[slot]);
-			const uint32_t p = vol_ld(&sm.prod[slot]);
-			uint32_t nrec = p - c;
-			if (nrec > (uint32_t)KMAX)
-				nrec = KMAX;
-			const uint8_t *slot_ring = cta_ring + (size_t)slot * RING_D * REC_BYTES;
-			DevStream d;
-			uint32_t d_id = 0xFFFFFFFFu;
-			for (uint32_t k = 0; k < nrec; k++, c++)
-				decode_record<CKS>(sm, a, wb, slot, lane, slot_ring + (size_t)(c % RING_D) * REC_BYTES,
-						   cta_hist + slot * HIST_WORDS, d, d_id);
-			__threadfence_block();
-			if (lane == 0) {
-				vol_st(&sm.cons[slot], c);
-				__threadfence_block();
-				atomicExch(&sm.busy[slot], 0u);
-			}
-			__syncwarp();
+		SmemWork &sm = *reinterpret_cast<SmemWork *>(smem_raw);
+		for (int i = tid; i < ACM_K8_SIZE; i += THREADS)
+			sm.k8w[i] = a.tables->k8w[i];
+		for (int i = tid; i < ACM_T_SIZE; i += THREADS)
+			sm.t[i] = a.tables->t[i];
+		for (int i = tid; i < 256; i += THREADS)
+			sm.nib2w[i] = a.tables->nib2w[i];
+		if (tid < 32)
+			sm.info[tid] = make_info(a.tables->kind[tid]);
+		for (int i = tid; i < MAXOWN; i += THREADS) {
+			sm.cons[i] = 0;
+			sm.busy[i] = 0;
+			sm.dead[i] = 0;
+			sm.pos[i] = 0;
+			sm.cks[i] = 0ull;
 		}
+		__syncthreads();
+		work_cta<CKS>(a, sm, warp, lane);
 	}
 }
 
 } // namespace fast2
 
-size_t fast2_smem_bytes() { return sizeof(fast2::Smem); }
+size_t fast2_smem_bytes() { return fast2::SMEM_BYTES; }
 
-int fast2_slots_per_cta() { return fast2::S; }
+/*
+ * Grid geometry for `count` streams on a device with `sms` SMs: n_scan scan CTAs (fast2::SLOTS
+ * stream slots each) followed by n_work decode CTAs (one CTA per SM at most: all CTAs of a
+ * launch must be resident together, decode CTAs wait for records).  n_slots = slots in use.
+ */
+void fast2_geometry(uint64_t count, int sms, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots)
+{
+#ifndef F2_SCAN_PCT
+#define F2_SCAN_PCT 27
+#endif
+	uint64_t want_scan = (count + fast2::SLOTS - 1) / fast2::SLOTS;
+	uint32_t cap_scan = (uint32_t)((sms * F2_SCAN_PCT + 50) / 100);
+	if (cap_scan < 1)
+		cap_scan = 1;
+	if (cap_scan > (uint32_t)sms - 1)
+		cap_scan = sms > 1 ? (uint32_t)sms - 1 : 1;
+	uint32_t ns = want_scan < cap_scan ? (uint32_t)want_scan : cap_scan;
+	if (ns < 1)
+		ns = 1;
+	uint64_t slots = (uint64_t)ns * fast2::SLOTS;
+	if (slots > count)
+		slots = (count + 31) / 32 * 32; /* whole warps */
+	/* one decode CTA per ~16 slots, at least one, at most what is left of the device */
+	uint64_t want_work = (slots + 15) / 16;
+	uint32_t cap_work = sms > (int)ns ? (uint32_t)sms - ns : 1;
+	uint32_t nw = want_work < cap_work ? (uint32_t)want_work : cap_work;
+	if (nw < 1)
+		nw = 1;
+	if (slots > (uint64_t)nw * fast2::MAXOWN)
+		slots = (uint64_t)nw * fast2::MAXOWN;
+	*n_scan = ns;
+	*n_work = nw;
+	*n_slots = (uint32_t)slots;
+}
 
-size_t fast2_hist_words_per_cta() { return (size_t)fast2::S * fast2::HIST_WORDS; }
+size_t fast2_hist_words_per_slot() { return fast2::HIST_WORDS; }
 
-size_t fast2_ring_bytes_per_cta() { return (size_t)fast2::S * fast2::RING_D * fast2::REC_BYTES; }
+size_t fast2_ring_bytes_per_slot() { return (size_t)fast2::RING_D * fast2::REC_BYTES; }
+
+size_t fast2_ctl_bytes_per_slot() { return sizeof(fast2::SlotCtl); }
 
 cudaError_t launch_fast2(const KernelArgs &a, int n_ctas, cudaStream_t st)
 {
@@ -954,7 +1052,7 @@ cudaError_t launch_fast2(const KernelArgs &a, int n_ctas, cudaStream_t st)
 		return cudaSuccess;
 	/* the opt-in shared-memory size is a per-device function attribute */
 	static bool configured[2][64] = {};
-	const size_t smem = sizeof(fast2::Smem);
+	const size_t smem = fast2::SMEM_BYTES;
 	const int v = a.fmt.checksums ? 1 : 0;
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
