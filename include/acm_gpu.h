@@ -62,7 +62,7 @@ typedef struct acm_gpu_opts {
 	int32_t force_chans;    /* as acm_open_decoder */
 	int32_t want_checksums; /* compute acm_gpu_stream.checksum on the device */
 	int32_t pad_tail;       /* zero-fill words [words, total_values) of every stream */
-	int32_t kernel;         /* 0 auto; 1 force the generic kernel, 2 the first-generation fast kernel (testing) */
+	int32_t kernel;         /* 0 auto; 1 force the generic kernel (testing) */
 	int32_t reserved[8];
 } acm_gpu_opts;
 

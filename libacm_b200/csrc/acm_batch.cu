@@ -173,7 +173,7 @@ struct Segment {
 	size_t hist_off, scratch_off;     /* its own history / scratch region (offsets in words) */
 	size_t ring_off;                  /* block-record rings of the fast kernel (offset in bytes) */
 	size_t ctl_off;                   /* slot control words (offset in bytes) */
-	uint32_t n_scan, n_slots;         /* fast kernel 2 geometry: scan CTAs, slots in use */
+	uint32_t n_scan, n_slots;         /* fast kernel geometry: scan CTAs, slots in use */
 };
 
 struct acm_gpu_plan {
@@ -192,13 +192,12 @@ struct acm_gpu_plan {
 	acm_tables *d_tables;
 	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue; [4*nseg] error flag */
 	GenericScratch scratch;
-	uint32_t *d_hist;    /* fast kernel history, fast_ctas * fast_hist_words_per_cta() words */
-	uint8_t *d_ring;     /* fast kernel 2 block-record rings (inside d_ring_alloc) */
-	uint8_t *d_ring_alloc;
-	uint8_t *d_ctl;      /* fast kernel 2 slot control words */
+	uint32_t *d_hist;    /* fast kernel history, 256 words per stream slot */
+	uint8_t *d_ring;     /* fast kernel block-record rings */
+	uint8_t *d_pool;     /* the one device allocation all of the above point into (null: arena) */
+	uint8_t *d_ctl;      /* fast kernel slot control words */
 	size_t ctl_bytes;
 	unsigned long long *d_prof; /* 64 counters of -DF2_PROF tuning builds */
-	int fast_gen;        /* 2: acm_fast2.cu (default), 1: acm_fast.cu (opts->kernel == 2) */
 	int fast_ctas;
 	int generic_ctas;
 	int sm_count;
@@ -210,22 +209,21 @@ static void plan_free(acm_gpu_plan *p)
 {
 	if (!p)
 		return;
-	cudaFree(p->d_streams);
-	cudaFree(p->d_status);
-	cudaFree(p->d_words);
-	cudaFree(p->d_cks);
-	cudaFree(p->d_tables);
-	cudaFree(p->d_counters);
-	cudaFree(p->scratch.buf);
-	cudaFree(p->d_hist);
-	cudaFree(p->d_ring_alloc);
-	cudaFree(p->d_ctl);
-	cudaFree(p->d_prof);
+	cudaFree(p->d_pool); /* null when the plan lives in a caller's arena */
 	if (p->ev0)
 		cudaEventDestroy(p->ev0);
 	if (p->ev1)
 		cudaEventDestroy(p->ev1);
 	delete p;
+}
+
+/* the code tables, built once per process */
+static const acm_tables *host_tables()
+{
+	static acm_tables tab;
+	static std::once_flag once;
+	std::call_once(once, [] { acm_tables_build(&tab); });
+	return &tab;
 }
 
 static bool fast_eligible(const acm_gpu_stream &g, const acm_gpu_opts *o)
@@ -235,14 +233,19 @@ static bool fast_eligible(const acm_gpu_stream &g, const acm_gpu_opts *o)
 	return o->wordlen == 2 && fast_shape(g.level, g.rows);
 }
 
+/* device memory kept between calls by the host path (grown, never shrunk) */
+struct DevArena {
+	uint8_t *base = nullptr;
+	size_t cap = 0;
+};
+
 static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_gpu_opts *opts,
-				 unsigned nseg, int *err_out)
+				 unsigned nseg, DevArena *arena, int *err_out)
 {
 	acm_gpu_opts defaults;
 	acm_gpu_plan *p = nullptr;
 	std::vector<DevStream> all;
-	acm_tables host_tab;
-	cudaDeviceProp prop;
+	int sm_count = 0, max_ctas = 0;
 	int err = ACM_ERR_OTHER, dev = 0;
 	uint32_t max_blen = 1, max_cols = 1;
 	uint64_t max_fast = 0, max_gen = 0;
@@ -260,7 +263,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	if (use_device(opts) < 0)
 		goto fail;
 	CU(cudaGetDevice(&dev));
-	CU(cudaGetDeviceProperties(&prop, dev));
+	CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
 
 	p = new acm_gpu_plan();
 	memset(&p->scratch, 0, sizeof(p->scratch));
@@ -268,15 +271,14 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	p->d_tables = nullptr; p->d_counters = nullptr; p->ev0 = nullptr; p->ev1 = nullptr;
 	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
 	p->d_ring = nullptr;
-	p->d_ring_alloc = nullptr;
+	p->d_pool = nullptr;
 	p->d_ctl = nullptr;
 	p->ctl_bytes = 0;
 	p->d_prof = nullptr;
-	p->fast_gen = opts->kernel == 2 ? 1 : 2;
 	p->device = dev;
 	p->n = n;
 	p->n_fast = p->n_generic = 0;
-	p->sm_count = prop.multiProcessorCount;
+	p->sm_count = sm_count;
 	p->timed = false;
 	p->fmt.wordlen = opts->wordlen;
 	p->fmt.be = opts->bigendianp ? 1 : 0;
@@ -289,6 +291,10 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		nseg = 1;
 	if (nseg > n)
 		nseg = n ? (unsigned)n : 1;
+	/* segments of the host path run concurrently (copy-in / decode / copy-out pipeline): a
+	 * segment's launch is latency-bound by its longest stream, so each gets a share of the SMs
+	 * and up to four of them are resident together */
+	max_ctas = nseg > 1 ? sm_count / (int)(nseg < 4 ? nseg : 4) : sm_count;
 	{
 		/* segment boundaries: equal shares of the output words */
 		uint64_t total = 0, acc = 0, first = 0;
@@ -378,26 +384,12 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	}
 	p->n_dev = all.size();
 
-	CU(cudaMalloc(&p->d_streams, (p->n_dev + 1) * sizeof(DevStream)));
-	if (p->n_dev)
-		CU(cudaMemcpy(p->d_streams, all.data(), p->n_dev * sizeof(DevStream), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&p->d_status, (n + 1) * sizeof(int32_t)));
-	CU(cudaMalloc(&p->d_words, (n + 1) * sizeof(uint32_t)));
-	CU(cudaMalloc(&p->d_cks, (n + 1) * sizeof(unsigned long long)));
-	CU(cudaMemset(p->d_status, 0, (n + 1) * sizeof(int32_t)));
-	CU(cudaMemset(p->d_words, 0, (n + 1) * sizeof(uint32_t)));
-	CU(cudaMemset(p->d_cks, 0, (n + 1) * sizeof(unsigned long long)));
-	acm_tables_build(&host_tab);
-	CU(cudaMalloc(&p->d_tables, sizeof(acm_tables)));
-	CU(cudaMemcpy(p->d_tables, &host_tab, sizeof(acm_tables), cudaMemcpyHostToDevice));
-	CU(cudaMalloc(&p->d_counters, (4 * p->seg.size() + 4) * sizeof(uint32_t)));
-	CU(cudaMalloc(&p->d_prof, 64 * sizeof(unsigned long long)));
-	CU(cudaMemset(p->d_prof, 0, 64 * sizeof(unsigned long long)));
 	CU(cudaEventCreate(&p->ev0));
 	CU(cudaEventCreate(&p->ev1));
-
 	{
-		const uint64_t per = (uint64_t)fast_slots_per_cta();
+		/* ---- geometry of every segment, then ONE device allocation for the whole plan (or a
+		 * slice of the caller's arena: the host path of acm_gpu_decode_batch keeps one
+		 * between calls, cudaMalloc / cudaFree synchronise the device) */
 		const size_t stride = generic_scratch_words(max_blen, max_cols);
 		const size_t budget = ((size_t)4 << 30) / p->seg.size(); /* scratch bytes per segment */
 		size_t hist_words = 0, scratch_words = 0, ring_bytes = 0, ctl_bytes = 0;
@@ -406,22 +398,15 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			sg.ring_off = ring_bytes;
 			sg.ctl_off = ctl_bytes;
 			sg.n_scan = sg.n_slots = 0;
-			if (p->fast_gen == 2) {
+			sg.fast_ctas = 0;
+			if (sg.n_fast) {
 				uint32_t n_work = 0;
-				if (sg.n_fast) {
-					fast2_geometry(sg.n_fast, p->sm_count, &sg.n_scan, &n_work, &sg.n_slots);
-					sg.fast_ctas = (int)(sg.n_scan + n_work);
-				} else {
-					sg.fast_ctas = 0;
-				}
-				hist_words += (size_t)sg.n_slots * fast2_hist_words_per_slot();
-				ring_bytes += (size_t)sg.n_slots * fast2_ring_bytes_per_slot();
-				ctl_bytes += ((size_t)sg.n_slots * fast2_ctl_bytes_per_slot() + 255u) & ~(size_t)255u;
-			} else {
-				uint64_t groups = (sg.n_fast + per - 1) / per;
-				sg.fast_ctas = (uint64_t)p->sm_count < groups ? p->sm_count : (int)groups;
-				hist_words += (size_t)sg.fast_ctas * fast_hist_words_per_cta();
+				fast2_geometry(sg.n_fast, p->sm_count, max_ctas, &sg.n_scan, &n_work, &sg.n_slots);
+				sg.fast_ctas = (int)(sg.n_scan + n_work);
 			}
+			hist_words += (size_t)sg.n_slots * fast2_hist_words_per_slot();
+			ring_bytes += (size_t)sg.n_slots * fast2_ring_bytes_per_slot();
+			ctl_bytes += ((size_t)sg.n_slots * fast2_ctl_bytes_per_slot() + 255u) & ~(size_t)255u;
 			int ctas = p->sm_count * 4;
 			if ((uint64_t)ctas > sg.n_gen)
 				ctas = (int)sg.n_gen;
@@ -433,36 +418,57 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			p->fast_ctas = std::max(p->fast_ctas, sg.fast_ctas);
 			p->generic_ctas = std::max(p->generic_ctas, sg.gen_ctas);
 		}
-		if (max_fast && ctl_bytes) {
-			CU(cudaMalloc(&p->d_ctl, ctl_bytes));
-			p->ctl_bytes = ctl_bytes;
-		}
-		if (max_fast)
-			CU(cudaMalloc(&p->d_hist, hist_words * 4 + 16));
-		if (max_fast && ring_bytes) {
-			/* the scan lanes advance only the low half of a record address (acm_fast2.cu):
-			 * place the rings so that they do not straddle a 4 GiB boundary */
-			CU(cudaMalloc(&p->d_ring_alloc, ring_bytes + 512));
-			uintptr_t lo = ((uintptr_t)p->d_ring_alloc + 255u) & ~(uintptr_t)255u;
-			if ((lo >> 32) != ((lo + ring_bytes) >> 32)) {
-				cudaFree(p->d_ring_alloc);
-				p->d_ring_alloc = nullptr;
-	p->d_ctl = nullptr;
-	p->ctl_bytes = 0;
-	p->d_prof = nullptr;
-				CU(cudaMalloc(&p->d_ring_alloc, 2 * ring_bytes + 512));
-				lo = ((uintptr_t)p->d_ring_alloc + 255u) & ~(uintptr_t)255u;
-				if ((lo >> 32) != ((lo + ring_bytes) >> 32))
-					lo = ((lo + ring_bytes) >> 32) << 32;
+		size_t total = 0;
+		auto carve = [&total](size_t bytes) {
+			const size_t at = total;
+			total += (bytes + 255u) & ~(size_t)255u;
+			return at;
+		};
+		const size_t o_streams = carve((p->n_dev + 1) * sizeof(DevStream));
+		const size_t o_results = carve((n + 1) * 16); /* status (4) | words (4) | checksums (8) */
+		const size_t o_tables = carve(sizeof(acm_tables));
+		const size_t o_counters = carve((4 * p->seg.size() + 4) * sizeof(uint32_t));
+		const size_t o_prof = carve(64 * sizeof(unsigned long long));
+		const size_t o_ctl = carve(ctl_bytes);
+		const size_t o_hist = carve(hist_words * 4 + 16);
+		const size_t o_ring = carve(ring_bytes + 16);
+		const size_t o_scratch = carve(max_gen ? scratch_words * 4 + 16 : 0);
+		uint8_t *base = nullptr;
+		if (arena) {
+			if (arena->cap < total) {
+				cudaFree(arena->base);
+				arena->base = nullptr;
+				arena->cap = 0;
+				CU(cudaMalloc(&arena->base, total + total / 4));
+				arena->cap = total + total / 4;
 			}
-			p->d_ring = (uint8_t *)lo;
+			base = arena->base;
+		} else {
+			CU(cudaMalloc(&p->d_pool, total));
+			base = p->d_pool;
 		}
+		p->d_streams = reinterpret_cast<DevStream *>(base + o_streams);
+		p->d_cks = reinterpret_cast<unsigned long long *>(base + o_results);
+		p->d_status = reinterpret_cast<int32_t *>(base + o_results + (n + 1) * 8);
+		p->d_words = reinterpret_cast<uint32_t *>(base + o_results + (n + 1) * 12);
+		p->d_tables = reinterpret_cast<acm_tables *>(base + o_tables);
+		p->d_counters = reinterpret_cast<uint32_t *>(base + o_counters);
+		p->d_prof = reinterpret_cast<unsigned long long *>(base + o_prof);
+		p->d_ctl = base + o_ctl;
+		p->ctl_bytes = ctl_bytes;
+		p->d_hist = reinterpret_cast<uint32_t *>(base + o_hist);
+		p->d_ring = base + o_ring;
 		if (max_gen) {
 			p->scratch.stride = stride;
 			p->scratch.max_blen = max_blen;
 			p->scratch.max_cols = max_cols;
-			CU(cudaMalloc(&p->scratch.buf, scratch_words * 4 + 16));
+			p->scratch.buf = reinterpret_cast<uint32_t *>(base + o_scratch);
 		}
+		if (p->n_dev)
+			CU(cudaMemcpy(p->d_streams, all.data(), p->n_dev * sizeof(DevStream), cudaMemcpyHostToDevice));
+		CU(cudaMemset(base + o_results, 0, (n + 1) * 16));
+		CU(cudaMemset(p->d_prof, 0, 64 * sizeof(unsigned long long)));
+		CU(cudaMemcpy(p->d_tables, host_tables(), sizeof(acm_tables), cudaMemcpyHostToDevice));
 	}
 	if (err_out)
 		*err_out = ACM_OK;
@@ -477,7 +483,7 @@ fail:
 extern "C" acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *s, uint64_t n,
 					     const acm_gpu_opts *opts, int *err_out)
 {
-	return plan_create(s, n, opts, 1, err_out);
+	return plan_create(s, n, opts, 1, nullptr, err_out);
 }
 
 /* launch the kernels of one segment on `st`; the cursors must have been zeroed on that stream */
@@ -508,10 +514,7 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 		a.streams = p->d_streams + sg.fast_first;
 		a.count = (uint32_t)sg.n_fast;
 		a.counter = p->d_counters + 4 * g;
-		if (p->fast_gen == 2)
-			CU(launch_fast2(a, sg.fast_ctas, st));
-		else
-			CU(launch_fast(a, sg.fast_ctas, st));
+		CU(launch_fast2(a, sg.fast_ctas, st));
 	}
 	if (sg.n_gen) {
 		GenericScratch sc = p->scratch;
@@ -637,6 +640,7 @@ struct Workspace {
 	size_t blob_cap = 0, out_cap = 0;
 	cudaStream_t s_in = nullptr, s_out = nullptr;
 	cudaStream_t s_k[MAX_SEG] = {};
+	DevArena arena; /* the plans' descriptor tables, rings, history */
 };
 std::mutex g_ws_mutex;
 Workspace g_ws[16];
@@ -677,11 +681,12 @@ extern "C" void acm_gpu_release_workspace(void)
 	cudaGetDevice(&cur);
 	for (int d = 0; d < 16; d++) {
 		Workspace &w = g_ws[d];
-		if (!w.s_in && !w.d_blob && !w.d_out)
+		if (!w.s_in && !w.d_blob && !w.d_out && !w.arena.base)
 			continue;
 		cudaSetDevice(d);
 		cudaFree(w.d_blob);
 		cudaFree(w.d_out);
+		cudaFree(w.arena.base);
 		if (w.s_in) {
 			cudaStreamDestroy(w.s_in);
 			cudaStreamDestroy(w.s_out);
@@ -802,20 +807,22 @@ extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *
 	 * caller's order is also the byte order of blob and out (acm_gpu_layout's order) */
 	if (host_io && monotonic && b->out_len >= ((uint64_t)32 << 20) && b->n >= 64)
 		nseg = MAX_SEG;
-	plan = plan_create(b->streams, b->n, opts, nseg, &perr);
-	if (!plan)
-		return perr ? perr : ACM_ERR_OTHER;
 	{
 		std::lock_guard<std::mutex> lock(g_ws_mutex);
-		if (cudaGetDevice(&dev) == cudaSuccess) {
-			Workspace &w = g_ws[dev & 15];
-			err = run_segments(plan, b, w, ev_in, ev_k);
-			if (w.s_in) {
-				cudaStreamSynchronize(w.s_in);
-				cudaStreamSynchronize(w.s_out);
-				for (unsigned k = 0; k < MAX_SEG; k++)
-					cudaStreamSynchronize(w.s_k[k]);
-			}
+		if (cudaGetDevice(&dev) != cudaSuccess) {
+			acm_set_error("cudaGetDevice failed");
+			return ACM_ERR_OTHER;
+		}
+		Workspace &w = g_ws[dev & 15];
+		plan = plan_create(b->streams, b->n, opts, nseg, &w.arena, &perr);
+		if (!plan)
+			return perr ? perr : ACM_ERR_OTHER;
+		err = run_segments(plan, b, w, ev_in, ev_k);
+		if (w.s_in) {
+			cudaStreamSynchronize(w.s_in);
+			cudaStreamSynchronize(w.s_out);
+			for (unsigned k = 0; k < MAX_SEG; k++)
+				cudaStreamSynchronize(w.s_k[k]);
 		}
 	}
 	for (cudaEvent_t e : ev_in)

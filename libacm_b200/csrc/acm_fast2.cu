@@ -1,30 +1,34 @@
 /*
  * acm_fast2.cu -- the throughput kernel for the common block shape: level 7 (128 columns),
- * 16 rows, 2048 words per block (the shape of BASELINE configs 1, 2, 4), second generation.
+ * 16 rows, 2048 words per block (the shape of BASELINE configs 1, 2, 4).
  *
  * What bounds this path: a stream's bitstream is serial -- where column
- * c+1 starts is only known once column c has been walked -- so the makespan of a
- * batch is at least (blocks of the longest stream) x (walk steps per block) x (latency of one
- * step).  Everything else is parallel and has to keep up with the walk.  Hence:
+ * c+1 starts is only known once column c has been walked -- so a batch cannot
+ * finish before (blocks of its longest stream) x (walk steps per block) x (latency of one
+ * step), and the walk's throughput is lanes / (steps x latency).  Everything else is parallel
+ * and has to keep up with the walk.  One persistent launch, two kinds of CTA:
  *
- *  - SCAN warps (the two highest warp ids of the CTA: the SM's warp arbiter prefers high warp
- *    ids, so the latency-critical walk issues first) walk column LENGTHS only, one stream per
- *    lane (64 stream slots per CTA).  A step is: fetch the 32 bits at bit position P from the
- *    lane's shared-memory ring (two conflict-free LDS + one funnel shift), one table lookup
- *    (sel13: selector + first prefix-code step, or the whole advance of a fixed-size column;
- *    kstep: one further prefix-code step with the row cap folded in), P += advance.  Every
- *    update is a select on the lane's state, so the 32 lanes run ONE instruction stream
- *    however their column types differ.  The ring (128 words per lane, word-interleaved across
- *    lanes) is filled with 4-byte cp.async copies issued for all lanes at the same time every
- *    SCAN_PERIOD steps and awaited one period later, so no step ever waits on global memory;
- *    the end-of-file rule (one zero byte, decode.c:57-61) is the zero-fill of cp.async's
- *    src-size operand.
- *  - The scan is DECOUPLED from the decode: every walked block becomes a 288-byte record (128
- *    column offsets + header facts) in a per-slot ring of RING_D records in global memory (L2
- *    resident), published through a shared-memory counter.  Scan lanes run up to RING_D blocks
- *    ahead of the decode, so neither side waits for the other at a per-round barrier: the
- *    kernel's time is max(longest walk, decode throughput), not their sum.
- *  - WORKER warps claim a slot that has records pending, and decode its blocks in order:
+ *  - SCAN CTAs (the first n_scan of the grid, one per SM, nothing else on that SM) walk column
+ *    LENGTHS only, one stream per lane (SW warps x 32 stream slots per CTA).  A step is: fetch
+ *    the 32 bits at bit position P from the lane's shared-memory ring (two conflict-free LDS +
+ *    one funnel shift), ONE table lookup (uni16: the whole walk as a state machine -- page 0 is
+ *    "at a column selector", indexed by selector + first payload byte; page (type, rows to come)
+ *    is "inside a prefix-coded column"; an entry is bits-to-advance | next page), P += advance.
+ *    No branches on the data: the 32 lanes run one instruction stream however their column
+ *    types differ, finished and idle lanes sit on a HALT page.  A warp issues in order and the
+ *    walk is one dependent chain, so a step costs ~4 cycles per instruction plus two shared-
+ *    memory latencies; sharing an SM with decode warps doubled that (measured), hence the
+ *    dedicated SMs.  The ring (64 words per lane, word-interleaved across lanes) is filled with
+ *    4-byte cp.async copies issued for all lanes together every SCAN_PERIOD steps and awaited
+ *    one period later; the end-of-file rule (one zero byte, decode.c:57-61) is the zero-fill
+ *    of cp.async's src-size operand.  End-of-file verdicts are not part of the walk: a block
+ *    whose walk ends inside the stream cannot have read past its end; the rare other block is
+ *    re-walked with the reference's verdicts (scan_block).
+ *  - Every walked block becomes a 288-byte RECORD (128 column offsets + header facts) in a
+ *    per-slot ring of RING_D records in global memory (L2 resident), announced through a
+ *    per-slot counter.  Scan lanes run up to RING_D blocks ahead of the decode.
+ *  - DECODE CTAs (the rest of the grid) own the slots round-robin.  A worker warp claims an
+ *    owned slot that has records pending and decodes its blocks in order:
  *      stage    the block's compressed bytes (<= 4.2 KB) into shared memory, coalesced;
  *      sort     the 128 columns by filler class (ballot + popc) into per-class work lists, so
  *               that every unpack pass runs one straight-line routine on 32 busy lanes;
@@ -32,16 +36,17 @@
  *               (up to 8 values + bit and row counts), 16 nibbles accumulated in two registers,
  *               no row cap (rows past the 16th shift out); radix-coded columns: all codes from
  *               one 64-bit window; linear columns: sliding window.  A column leaves as sixteen
- *               int16 indices in two 128-bit shared-memory stores (48-byte column pitch:
+ *               int16 indices in two 128-bit shared-memory stores (halves swizzled:
  *               conflict-free for the transform's 128-bit loads);
  *      juggle   dequantise (idx*val) on load; lifting stages 1-2 (C=64,32) in registers with
  *               lane j owning every word m = j mod 32; one transpose through shared memory;
- *               stages 3-7 (C=16..1) in registers over a recomputed 62-word halo;
- *      output   >>7, low 16 bits, byte order / sign bias folded into one PRMT (+LOP), eight
- *               128-bit streaming stores per lane: the block leaves as 4 KiB of PCM.
+ *               stages 3-7 (C=16..1) in registers over a recomputed halo, as a rolled loop
+ *               (the unrolled 40 KB version thrashed the instruction caches);
+ *      output   >>7, low 16 bits, byte order / sign bias folded into one PRMT (+LOP), 128-bit
+ *               streaming stores: the block leaves as 4 KiB of PCM.
  *    The reference's wrapbuf (decode.c:803, 2*cols-2 = 254 words) is 256 words of per-slot
  *    history (last 128 X0, 64 X1, 64 X2 words) in an L2-resident global array.
- *  - Streams are handed out by an atomic cursor in longest-first order.
+ *  - Streams are handed out to scan lanes by an atomic cursor in longest-first order.
  *
  * Bit-exactness: same arithmetic as the generic kernel (uint32 wrap-around, arithmetic shift,
  * truncation), same table-driven symbol decode, same status rules.
@@ -56,7 +61,6 @@ namespace fast2 {
 constexpr int LEVEL = 7;
 constexpr int COLS = 128;
 constexpr int BLEN = COLS * ROWS;        /* 2048 */
-constexpr int NSCAN = 2;                 /* scan warps (the highest warp ids) */
 #ifndef F2_W
 #define F2_W 16        /* worker warps of a decode CTA */
 #endif
@@ -119,9 +123,15 @@ struct SlotCtl {
 	uint32_t pad;
 };
 
+constexpr int OFFP = 2 * COLS + 8; /* bytes per lane of the column-offset staging (+8: bank spread, 8-byte rows) */
+
 struct SmemScan {
 	uint16_t uni16[ACM_UNI_PAGES * ACM_UNI_PSIZE];
 	uint32_t ring[SW][(RW + 1) * 32]; /* [word][lane] */
+	/* column offsets of the block a lane is walking, copied to the block's record with
+	 * coalesced stores at the end of the round (scattered 2-byte global stores from 32 lanes
+	 * are 32 partial-sector writes per instruction) */
+	unsigned char off[SW][32 * OFFP];
 };
 
 struct SmemWork {
@@ -287,13 +297,6 @@ struct ScanRing {
 	}
 };
 
-__device__ __forceinline__ void st_global_u16(uint32_t lo, uint32_t hi, uint32_t v)
-{
-	asm volatile("{\n\t.reg .b64 p;\n\tmov.b64 p, {%0, %1};\n\tst.global.u16 [p], %2;\n\t}" ::"r"(lo), "r"(hi),
-		     "h"((unsigned short)v)
-		     : "memory");
-}
-
 /*
  * One walk step for all lanes of a scan warp: fetch the 32 stream bits at P from the ring, note
  * the column offset if the lane is at a selector, one uni16 lookup, apply it.  After the 128th
@@ -305,17 +308,15 @@ __device__ __forceinline__ void st_global_u16(uint32_t lo, uint32_t hi, uint32_t
  * A single warp issues in order and the walk is one dependent chain, so the step costs about
  * four cycles per instruction plus the two shared-memory latencies: it is kept to the minimum.
  */
-__device__ __forceinline__ void fast_step(Walk &s, uint32_t &cp, uint32_t cph, uint32_t cpend, uint32_t pblock,
+__device__ __forceinline__ void fast_step(Walk &s, uint16_t *&cp, const uint16_t *cpend, uint32_t pblock,
 					  const uint32_t *ringw, uint32_t ready_p, const unsigned char *uni)
 {
 	const uint32_t *rp = ringw + ((s.P >> 5) & (RW - 1)) * 32u;
 	const uint32_t w = fsr(rp[0], rp[32], s.P);
 	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s, w));
 	const bool have = s.P < ready_p;
-	if (have && s.msk == MSK_SEL) {
-		st_global_u16(cp, cph, s.P - pblock);
-		cp += 2u;
-	}
+	if (have && s.msk == MSK_SEL)
+		*cp++ = (uint16_t)(s.P - pblock); /* shared memory: see SmemScan::off */
 	const uint32_t ee = have ? e : (s.s8 >> (UNI_PSHIFT - 8u)); /* not landed: advance 0, same page */
 	const bool at_sel = walk_next(s, ee);
 	const bool done = at_sel && cp == cpend;
@@ -790,9 +791,9 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 				mode = 1;
 			}
 		}
-		const unsigned long long rec64 = (unsigned long long)(uintptr_t)recbase;
-		uint32_t cp = (uint32_t)rec64;
-		const uint32_t cph = (uint32_t)(rec64 >> 32), cpend = cp + 2u * COLS;
+		uint16_t *const off0 = reinterpret_cast<uint16_t *>(&sm.off[warp][lane * OFFP]);
+		uint16_t *cp = off0;
+		const uint16_t *const cpend = off0 + COLS;
 		bool hdr_eof = false;
 		while (__any_sync(0xFFFFFFFFu, mode != 0)) {
 			PROF_MARK(4); /* 4: walk steps */
@@ -815,7 +816,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			PROF_MARK(5); /* 5: top-up + header */
 #pragma unroll 4
 			for (int k = 0; k < SCAN_PERIOD; k++)
-				fast_step(s, cp, cph, cpend, P, ring.rw, ring.ready_p,
+				fast_step(s, cp, cpend, P, ring.rw, ring.ready_p,
 					  reinterpret_cast<const unsigned char *>(sm.uni16));
 			if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
 				mode = 0;
@@ -835,9 +836,8 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 				const DevStream d = a.streams[cur];
 				BitReader br;
 				br.init(reinterpret_cast<const uint32_t *>(a.blob + d.base_off), d.file_end);
-				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS,
-								 reinterpret_cast<uint16_t *>(recbase), P, a.tables->kind,
-								 a.tables->k8);
+				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS, off0, P,
+								 a.tables->kind, a.tables->k8);
 				e.status = sc.status;
 				e.ncols = sc.ncols;
 				e.pend = sc.end;
@@ -848,6 +848,20 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			blk++;
 			if (e.status != SCAN_OK || blk >= n_attempt)
 				e.blk |= 0x80000000u;
+		}
+		/* ---- the walked blocks' column offsets leave as 256-byte rows: thread t copies columns
+		 * 4t..4t+3 of lane i's block */
+		{
+			const unsigned wm = __ballot_sync(0xFFFFFFFFu, walk);
+			const unsigned long long rec64 = (unsigned long long)(uintptr_t)recbase;
+			__syncwarp();
+			for (unsigned mm = wm; mm; mm &= mm - 1u) {
+				const int i = __ffs((int)mm) - 1;
+				const unsigned long long r = __shfl_sync(0xFFFFFFFFu, rec64, i);
+				const uint2 v = *reinterpret_cast<const uint2 *>(&sm.off[warp][i * OFFP + 8 * lane]);
+				reinterpret_cast<uint2 *>((uintptr_t)r)[lane] = v;
+			}
+			__syncwarp();
 		}
 		if (can) {
 			uint4 *rp = reinterpret_cast<uint4 *>(recbase + 256);
@@ -1003,33 +1017,37 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 
 } // namespace fast2
 
+bool fast_shape(uint32_t level, uint32_t rows) { return level == fast2::LEVEL && rows == (uint32_t)fast2::ROWS; }
+
 size_t fast2_smem_bytes() { return fast2::SMEM_BYTES; }
 
 /*
- * Grid geometry for `count` streams on a device with `sms` SMs: n_scan scan CTAs (fast2::SLOTS
- * stream slots each) followed by n_work decode CTAs (one CTA per SM at most: all CTAs of a
- * launch must be resident together, decode CTAs wait for records).  n_slots = slots in use.
+ * Grid geometry for `count` streams on a device with `sms` SMs, using at most max_ctas of them:
+ * n_scan scan CTAs (fast2::SLOTS stream slots each) followed by n_work decode CTAs (one CTA per
+ * SM: all CTAs of a launch must be resident together, decode CTAs wait for records; the scan CTAs
+ * have the lowest block indices, so they are placed first).  n_slots = slots in use.
  */
-void fast2_geometry(uint64_t count, int sms, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots)
+void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots)
 {
 #ifndef F2_SCAN_PCT
-#define F2_SCAN_PCT 27
+#define F2_SCAN_PCT 22
 #endif
-	uint64_t want_scan = (count + fast2::SLOTS - 1) / fast2::SLOTS;
-	uint32_t cap_scan = (uint32_t)((sms * F2_SCAN_PCT + 50) / 100);
+	int total = max_ctas < sms ? max_ctas : sms;
+	if (total < 2)
+		total = 2;
+	const uint64_t want_scan = (count + fast2::SLOTS - 1) / fast2::SLOTS;
+	uint32_t cap_scan = (uint32_t)((total * F2_SCAN_PCT + 50) / 100);
 	if (cap_scan < 1)
 		cap_scan = 1;
-	if (cap_scan > (uint32_t)sms - 1)
-		cap_scan = sms > 1 ? (uint32_t)sms - 1 : 1;
 	uint32_t ns = want_scan < cap_scan ? (uint32_t)want_scan : cap_scan;
 	if (ns < 1)
 		ns = 1;
 	uint64_t slots = (uint64_t)ns * fast2::SLOTS;
 	if (slots > count)
 		slots = (count + 31) / 32 * 32; /* whole warps */
-	/* one decode CTA per ~16 slots, at least one, at most what is left of the device */
-	uint64_t want_work = (slots + 15) / 16;
-	uint32_t cap_work = sms > (int)ns ? (uint32_t)sms - ns : 1;
+	/* one decode CTA per ~16 slots, at least one, at most what is left of the budget */
+	const uint64_t want_work = (slots + 15) / 16;
+	const uint32_t cap_work = (uint32_t)total - ns;
 	uint32_t nw = want_work < cap_work ? (uint32_t)want_work : cap_work;
 	if (nw < 1)
 		nw = 1;

@@ -23,12 +23,12 @@ struct KernelArgs {
 	const acm_tables *tables; /* device copy */
 	uint32_t *counter;        /* work-queue cursor (zeroed before launch) */
 	uint32_t *errflag;        /* set non-zero on an internal failure (e.g. copy timeout) */
-	uint32_t *hist;           /* fast kernel: per-CTA, per-slot transform history (256 words each) */
-	uint8_t *ring;            /* fast kernel 2: per-slot ring of block records */
-	uint8_t *slotctl;         /* fast kernel 2: per-slot control words (zeroed before launch) */
-	uint32_t *scan_done;      /* fast kernel 2: scan warps that have finished (zeroed before launch) */
-	uint32_t n_scan;          /* fast kernel 2: scan CTAs (the first n_scan of the grid) */
-	uint32_t n_slots;         /* fast kernel 2: stream slots in use */
+	uint32_t *hist;           /* fast kernel: per-slot transform history (256 words each) */
+	uint8_t *ring;            /* fast kernel: per-slot ring of block records */
+	uint8_t *slotctl;         /* fast kernel: per-slot control words (zeroed before launch) */
+	uint32_t *scan_done;      /* fast kernel: scan warps that have finished (zeroed before launch) */
+	uint32_t n_scan;          /* fast kernel: scan CTAs (the first n_scan of the grid) */
+	uint32_t n_slots;         /* fast kernel: stream slots in use */
 	unsigned long long *prof; /* 64 counters, only written by -DF2_PROF tuning builds */
 	/* generic kernel, resumable decode (acm_stream.cu): when resume_hist != NULL stream i of the
 	 * slice starts from / leaves its per-stage history at resume_hist + i * resume_stride (2*cols
@@ -57,16 +57,10 @@ inline size_t generic_scratch_words(uint32_t max_blen, uint32_t max_cols)
 cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_ctas,
 			   cudaStream_t st);
 
-/* level-7 / 16-row kernel (acm_fast.cu); 16-bit output formats only */
+/* level-7 / 16-row kernel (acm_fast2.cu): scan CTAs + decode CTAs; 16-bit output formats only */
 bool fast_shape(uint32_t level, uint32_t rows);
-size_t fast_smem_bytes();
-int fast_slots_per_cta();
-size_t fast_hist_words_per_cta();
-cudaError_t launch_fast(const KernelArgs &a, int n_ctas, cudaStream_t st);
-
-/* second generation of the same (acm_fast2.cu): scan CTAs + decode CTAs */
 size_t fast2_smem_bytes();
-void fast2_geometry(uint64_t count, int sms, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots);
+void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots);
 size_t fast2_hist_words_per_slot();
 size_t fast2_ring_bytes_per_slot();
 size_t fast2_ctl_bytes_per_slot();

@@ -205,34 +205,4 @@ void acm_tables_build(acm_tables *t)
 					k = (uint8_t)(ACM_CLS_K | (kt << 3));
 		t->kind[sel] = k;
 	}
-	/* scan table for 16-row blocks: selector + first payload byte in one lookup */
-	for (b = 0; b < 8192; b++) {
-		unsigned ind = b & 31u, sym = (b >> 5) & 255u, k = t->kind[ind], cls = k & 7u, sub = k >> 3;
-		unsigned v;
-		if (cls == ACM_CLS_BAD) {
-			v = 5u | (7u << 13); /* rows-to-come 0 with table 7: no valid entry looks like this */
-		} else if (cls == ACM_CLS_K) {
-			unsigned e = (unsigned)t->k8[sub * 256 + sym], nv = e & 15u;
-			v = (5u + ((e >> (4 * nv)) & 15u)) | ((16u - nv) << 9) | (sub << 13); /* nv in 1..7 */
-		} else if (cls == ACM_CLS_LINEAR) {
-			v = 5u + 16u * ind;
-		} else if (cls == ACM_CLS_T) {
-			v = 5u + (sub == 0 ? 30u : (sub == 1 ? 42u : 56u)); /* 6x5, 6x7, 8x7 bits */
-		} else {
-			v = 5u;
-		}
-		t->sel13_r16[b] = (uint16_t)v;
-	}
-	/* one prefix-code step with the row cap folded in */
-	for (kt = 0; kt < 8; kt++) {
-		unsigned m;
-		for (m = 0; m < 8; m++) {
-			for (b = 0; b < 256; b++) {
-				unsigned e = (unsigned)t->k8[kt * 256 + b], nv = e & 15u;
-				unsigned kk = nv < m ? nv : m;
-				unsigned len = kk ? (e >> (4 * kk)) & 15u : 0u;
-				t->kstep[(kt * 8 + m) * 256 + b] = (uint8_t)(len | (kk << 4));
-			}
-		}
-	}
 }

@@ -18,18 +18,7 @@
  *   t[tt][b]    tt = 0,1,2 for selectors 19 (t15), 22 (t27), 29 (t37); b = the 5/7-bit
  *               code.  16-bit entry: three 4-bit two's complement digits, bit 15 set
  *               when the code is out of range (ACM_ERR_CORRUPT, decode.c:412/438/464).
- *   sel13_r16[w]  scan-only, for the 16-row block shape: w = the 13 stream bits at a column
- *               boundary (5-bit selector + first 8 payload bits).  16-bit entry:
- *                 bits 0..8    bits to advance: 5 + the whole payload of a fixed-size filler
- *                              (zero, linear, t15/t27/t37), or 5 + the first k8 step
- *                 bits 9..12   rows still to come after that first step; non-zero exactly for
- *                              the prefix-coded fillers (a step yields at most 7 of 16 rows)
- *                 bits 13..15  k8 table number of that filler; a bad selector (f_bad,
- *                              decode.c:190-194) is entry >> 9 == 0x70 (table 7, no rows)
- *   kstep[kt][m][b]  scan-only: one prefix-code step with m = min(rows remaining, 7) and b = the
- *               next 8 stream bits.  8-bit entry: bits 0..3 bits consumed, bits 4..6 values
- *               produced (k8's nv and cum with the row cap already applied).
- *   k8w[kt][b]  the unpack-side variant of k8 (fast kernel 2): every whole symbol that fits in
+ *   k8w[kt][b]  the unpack-side variant of k8 (acm_fast2.cu): every whole symbol that fits in
  *               the 8 bits b while at most 8 rows are produced.  64-bit entry:
  *                 bits  0..31  the (up to 8) values, 4-bit two's complement, value j in nibble j
  *                 bits 32..35  bits consumed (1..8)
@@ -71,12 +60,10 @@
 typedef struct acm_tables {
 	uint64_t k8[ACM_K8_SIZE];
 	uint16_t t[ACM_T_SIZE];
-	uint16_t sel13_r16[8192];
-	uint8_t kstep[8 * 8 * 256];
 	uint8_t kind[32];  /* per selector: class | (subtype << 3); see ACM_CLS_* */
 	uint8_t pad[32];
 	uint64_t k8w[ACM_K8_SIZE]; /* worker-side prefix-code step, see above */
-	uint16_t uni16[ACM_UNI_PAGES * ACM_UNI_PSIZE]; /* scan walk of fast kernel 2, see above */
+	uint16_t uni16[ACM_UNI_PAGES * ACM_UNI_PSIZE]; /* scan walk of the fast kernel, see above */
 	uint32_t nib2w[256];       /* two 4-bit two's complement values -> two int16 in one word */
 } acm_tables;
 

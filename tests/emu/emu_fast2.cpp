@@ -1,0 +1,109 @@
+/*
+ * tests/emu/emu_fast2.cpp -- CPU run of the lane-local code of the level-7 / 16-row kernel
+ * (TEST ONLY; never part of the product).
+ *
+ * libacm_b200/csrc/acm_fast2_core.cuh (the uni16 column walk and the three column unpackers)
+ * is __host__ __device__: here the very same functions walk and unpack every block of a stream
+ * and are compared, column by column, with the generic building blocks (scan_block /
+ * decode_column of acm_device.cuh), which tests/test_emu.py pins against the oracle.
+ */
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "acm_fast2_core.cuh"
+#include "acm_host.h"
+#include "libacm.h"
+
+using namespace acm;
+
+namespace {
+struct WordReader {
+	BitReader *br;
+	uint32_t word(uint32_t i) const { return br->word(i); }
+};
+} // namespace
+
+/* returns the number of blocks checked, or -(1000*block + code) at the first difference */
+extern "C" long emu_fast2_check(const uint8_t *img, uint32_t len)
+{
+	acm_header h;
+	static acm_tables tab;
+	static bool built = false;
+	if (!built) {
+		acm_tables_build(&tab);
+		built = true;
+	}
+	if (acm_parse_header(img, len, 0, &h) < 0 || h.level != 7 || h.rows != 16)
+		return -1;
+	std::vector<uint32_t> words((len + 64) / 4 + 4, 0xA5A5A5A5u); /* garbage after the image */
+	memcpy(words.data(), img, len);
+	BitReader br;
+	const uint32_t file_end = len * 8u, limit = file_end + 8u;
+	br.init(words.data(), file_end);
+	uint32_t P = h.header_len * 8u;
+	const uint32_t nblocks = (h.total_values + 2047u) / 2048u;
+	long checked = 0;
+	for (uint32_t b = 0; b < nblocks; b++, checked++) {
+		uint16_t off[128];
+		const ScanResult sc = scan_block(br, P, limit, 128u, 16u, off, P, tab.kind, tab.k8);
+		/* ---- the walk, exactly as fast_step drives it */
+		fast2::Walk s;
+		s.P = P + 20u;
+		s.s8 = 0u;
+		s.msk = fast2::MSK_SEL;
+		uint32_t col = 0, guard = 0;
+		uint16_t woff[129];
+		bool ok_walk = P + 20u <= limit;
+		while (ok_walk && s.s8 != fast2::UNI_HALT8 && s.s8 != fast2::UNI_BAD8 && guard++ < 100000u) {
+			const uint32_t w = br.peek(s.P);
+			if (s.msk == fast2::MSK_SEL)
+				woff[col++] = (uint16_t)(s.P - P);
+			const uint32_t e = *reinterpret_cast<const uint16_t *>(
+				reinterpret_cast<const unsigned char *>(tab.uni16) + fast2::walk_index(s, w));
+			const bool at_sel = fast2::walk_next(s, e);
+			if (at_sel && col == 128u) {
+				s.s8 = fast2::UNI_HALT8;
+				s.msk = fast2::MSK_K;
+			}
+		}
+		const bool fast_ok = ok_walk && s.s8 == fast2::UNI_HALT8 && s.P <= limit;
+		if (fast_ok != (sc.status == SCAN_OK))
+			return -(1000L * b + 1);
+		if (!fast_ok)
+			break; /* the kernel re-walks this block with scan_block itself */
+		if (s.P != sc.end)
+			return -(1000L * b + 2);
+		for (uint32_t c = 0; c < 128; c++)
+			if (woff[c] != off[c])
+				return -(1000L * b + 3);
+		/* ---- the unpackers */
+		WordReader sr{ &br };
+		for (uint32_t c = 0; c < 128; c++) {
+			const uint32_t Pc = P + off[c];
+			const uint32_t ind = br.peek(Pc) & 31u, kind = tab.kind[ind], cls = kind & 7u, sub = kind >> 3;
+			int ref[16];
+			int16_t got[16];
+			uint32_t half0[4] = { 0, 0, 0, 0 }, half1[4] = { 0, 0, 0, 0 };
+			fast2::ColOut o{ half0, half1 };
+			const int rc = decode_column(br, Pc + 5u, limit, ind, kind, 16u, 1, ref, 1u, tab.k8, tab.t);
+			int bad = 0;
+			if (cls == ACM_CLS_K)
+				fast2::unpack_k(sr, Pc + 5u, sub, o, tab.k8w, tab.nib2w);
+			else if (cls == ACM_CLS_T)
+				bad = fast2::unpack_t(sr, Pc + 5u, limit, sub, o, tab.t, tab.nib2w, true);
+			else if (cls == ACM_CLS_LINEAR)
+				fast2::unpack_linear(sr, Pc + 5u, ind, o);
+			if ((rc == -6) != (bad != 0))
+				return -(1000L * b + 4);
+			memcpy(got, half0, 16);
+			memcpy(got + 8, half1, 16);
+			if (!bad)
+				for (int r = 0; r < 16; r++)
+					if ((int)got[r] != ref[r])
+						return -(1000L * b + 5);
+		}
+		P = sc.end;
+	}
+	return checked;
+}

@@ -9,6 +9,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "tests", "_build", "libemu.so")
 SRCS = [os.path.join(ROOT, "tests", "emu", "emu_generic.cpp"),
+        os.path.join(ROOT, "tests", "emu", "emu_fast2.cpp"),
         os.path.join(ROOT, "libacm_b200", "csrc", "acm_hostlogic.cpp"),
         os.path.join(ROOT, "libacm_b200", "csrc", "acm_tables.c")]
 _lib = None
@@ -27,7 +28,17 @@ def lib():
         _lib.emu_decode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint32),
                                     C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        _lib.emu_fast2_check.argtypes = [C.c_void_p, C.c_uint32]
+        _lib.emu_fast2_check.restype = C.c_long
     return _lib
+
+
+def fast2_check(img):
+    """Runs the fast kernel's lane-local code (acm_fast2_core.cuh: uni16 walk, column unpackers)
+    over every block of a level-7 / 16-row image on the CPU and compares it with the generic
+    building blocks.  Returns the number of blocks checked (negative: first difference)."""
+    raw = np.frombuffer(bytes(img), np.uint8).copy()
+    return lib().emu_fast2_check(raw.ctypes.data, raw.size)
 
 
 def decode(img, be=0, sgned=1, wordlen=2, force_chans=0, lead=0, nthreads=64, trail_fill=0xFF):

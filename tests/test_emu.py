@@ -49,3 +49,27 @@ def test_emu_force_chans(checker):
                                           total_values=(rows << level) * 3 + 1, dist=gen.DIST_STRESS,
                                           seed=fc + 10 * wavc + 100 * ch + level)
                     _check(img, checker, force_chans=fc)
+
+
+def test_fast2_core_walk_and_unpack():
+    """The fast kernel's table walk (uni16) and column unpackers, run on the CPU, agree with the
+    generic scan / column decode on every column: Fallout mix, stress mix (all fillers, extreme
+    val), every single filler, a bad selector, a bad t-code and every truncation of a stream."""
+    blocks = 0
+    plist = corpus.fallout_params(6, seed=3, lo=20_000, hi=60_000)
+    plist += [gen.params(level=7, rows=16, channels=1 + (k & 1), total_values=2048 * 5 + 77 * k, wavc=k & 1,
+                         dist=gen.DIST_STRESS, seed=700 + k) for k in range(6)]
+    plist += [gen.params(level=7, rows=16, total_values=2048 * 2 + 5, dist=gen.DIST_SINGLE, single_ind=ind,
+                         seed=800 + ind) for ind in gen.VALID_INDS]
+    plist += [gen.params(level=7, rows=16, total_values=2048 * 3, dist=gen.DIST_STRESS, seed=900,
+                         inject=gen.INJECT_BAD_IND, inject_block=1, inject_col=77, inject_value=25),
+              gen.params(level=7, rows=16, total_values=2048 * 3, dist=gen.DIST_SINGLE, single_ind=22, seed=901,
+                         inject=gen.INJECT_BAD_TCODE, inject_block=1, inject_col=5)]
+    for img in corpus.images(plist):
+        n = emu.fast2_check(img)
+        assert n >= 0, n
+        blocks += n
+    img = corpus.images([gen.params(level=7, rows=16, total_values=2048 * 2, dist=gen.DIST_STRESS, seed=77)])[0]
+    for cut in range(14, len(img), 7):
+        assert emu.fast2_check(img[:cut]) >= 0, cut
+    assert blocks > 100

@@ -141,3 +141,40 @@ def test_host_path_segmented_pipeline_matches_resident(checker):
     # second call reuses the cached workspace
     s3, out3 = gu.decode_host(imgs[:200], want_checksums=1)
     assert np.array_equal(s3["checksum"], s1["checksum"][:200])
+
+
+def test_fast_shape_negatives_among_good_streams(checker):
+    """Level-7 / 16-row streams (the scan-CTA / decode-CTA kernel) with one defect each -- bad
+    selectors (the scan's table walk ends on its BAD page and the block is re-walked with the
+    reference's verdicts) and out-of-range t-codes (found by the decode side, which must stop the
+    slot's scan lane) -- in the middle of healthy streams sharing the same slots."""
+    plist = corpus.fallout_params(40, seed=31, hi=50_000)
+    for k, bad in enumerate(gen.BAD_INDS):
+        plist.insert(3 * k + 1, gen.params(level=7, rows=16, total_values=2048 * 6 + 11 * k, dist=gen.DIST_STRESS,
+                                           seed=5000 + k, inject=gen.INJECT_BAD_IND, inject_block=k % 5,
+                                           inject_col=(37 * k + 3) % 128, inject_value=bad))
+    for k, ind in enumerate((19, 22, 29, 19, 22, 29)):
+        plist.insert(5 * k + 2, gen.params(level=7, rows=16, total_values=2048 * 7, dist=gen.DIST_SINGLE,
+                                           single_ind=ind, seed=5100 + k, inject=gen.INJECT_BAD_TCODE,
+                                           inject_block=k, inject_col=(29 * k + 1) % 128))
+    imgs = corpus.images(plist)
+    for dec in (gu.decode_host, gu.decode_device):
+        s, out = dec(imgs, want_checksums=1)
+        assert gu.compare(imgs, s, out, checker, checksums=True) == []
+        assert set(s["status"].tolist()) == {0, -6}
+
+
+def test_more_streams_than_slots(checker):
+    """Thousands of one-to-three-block streams: every stream slot is reused many times, every decode
+    CTA owns many slots, records of consecutive streams share a slot's ring."""
+    rng = np.random.default_rng(11)
+    tv = rng.integers(1, 3 * 2048 + 1, size=3000)
+    plist = [gen.params(level=7, rows=16, channels=1 + (i & 1), total_values=int(t), wavc=(i >> 1) & 1,
+                        dist=gen.DIST_FALLOUT if i % 3 else gen.DIST_STRESS, seed=9000 + i)
+             for i, t in enumerate(tv)]
+    imgs = corpus.images(plist)
+    s, out = gu.decode_device(imgs, want_checksums=1)
+    assert np.all(s["status"] == 0)
+    assert gu.compare(imgs[::7], s[::7], out, checker, checksums=True) == []
+    want = s["total_values"] - s["total_values"] % s["channels"]
+    assert np.array_equal(s["words"], want)
