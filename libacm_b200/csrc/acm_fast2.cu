@@ -68,7 +68,7 @@ constexpr int BLEN = COLS * ROWS;        /* 2048 */
 #define F2_SW 8        /* scan warps of a scan CTA */
 #endif
 #ifndef F2_RING_D
-#define F2_RING_D 8
+#define F2_RING_D 16
 #endif
 #ifndef F2_RW
 #define F2_RW 64
@@ -301,12 +301,14 @@ struct ScanRing {
  * One walk step for all lanes of a scan warp: fetch the 32 stream bits at P from the ring, note
  * the column offset if the lane is at a selector, one uni16 lookup, apply it.  After the 128th
  * column the lane moves to the HALT page (entries advance 0 bits and stay), which is also where
- * finished and idle lanes sit: every lane runs the same instructions.  A lane whose bits have
- * not landed yet (P >= ready_p) does nothing this step.  No end-of-file checks here: bits past
- * the end read as zero, and a block whose walk ends at or before the stream's limit cannot
- * have read past it (the caller re-walks the rare other case with the reference's verdicts).
- * A single warp issues in order and the walk is one dependent chain, so the step costs about
- * four cycles per instruction plus the two shared-memory latencies: it is kept to the minimum.
+ * finished and idle lanes sit: every lane runs the same instructions, no branch (a branch here
+ * costs a convergence barrier per step).  A lane whose bits have not landed yet (P >= ready_p)
+ * does nothing this step.  No end-of-file checks here: bits past the end read as zero, and a
+ * block whose walk ends at or before the stream's limit cannot have read past it (the caller
+ * re-walks the rare other case with the reference's verdicts).
+ * A warp issues in order and the walk is one dependent chain through two shared-memory round
+ * trips; measured variants (a register window that keeps the ring fetch off the chain, per-period
+ * instead of per-step data checks with rollback) are in profiles/r01_ncu_fast2.md.
  */
 __device__ __forceinline__ void fast_step(Walk &s, uint16_t *&cp, const uint16_t *cpend, uint32_t pblock,
 					  const uint32_t *ringw, uint32_t ready_p, const unsigned char *uni)
@@ -315,8 +317,10 @@ __device__ __forceinline__ void fast_step(Walk &s, uint16_t *&cp, const uint16_t
 	const uint32_t w = fsr(rp[0], rp[32], s.P);
 	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s, w));
 	const bool have = s.P < ready_p;
-	if (have && s.msk == MSK_SEL)
-		*cp++ = (uint16_t)(s.P - pblock); /* shared memory: see SmemScan::off */
+	const bool note = have && s.msk == MSK_SEL;
+	/* the store always happens, one past the lane's 128 offsets when there is nothing to note */
+	*(note ? cp : const_cast<uint16_t *>(cpend)) = (uint16_t)(s.P - pblock); /* shared memory: SmemScan::off */
+	cp += note ? 1 : 0;
 	const uint32_t ee = have ? e : (s.s8 >> (UNI_PSHIFT - 8u)); /* not landed: advance 0, same page */
 	const bool at_sel = walk_next(s, ee);
 	const bool done = at_sel && cp == cpend;
@@ -727,6 +731,9 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 	bool active = false, exhausted = !enabled;
 	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
 	PROF_DECL;
+#if F2_PROF
+	uint32_t prof_rounds = 0, prof_periods = 0;
+#endif
 	for (;;) {
 		PROF_MARK(0); /* 0: round tail (publish) */
 		uint32_t cons = 0, dead = 0;
@@ -772,6 +779,9 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		}
 #endif
 		PROF_MARK(3); /* 3: round head (retire / acquire) */
+#if F2_PROF
+		prof_rounds++;
+#endif
 		/* ---- one record per lane that can produce */
 		uint8_t *const recbase = slot_ring + (size_t)(prodn % RING_D) * REC_BYTES;
 		Rec e;
@@ -797,6 +807,9 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		bool hdr_eof = false;
 		while (__any_sync(0xFFFFFFFFu, mode != 0)) {
 			PROF_MARK(4); /* 4: walk steps */
+#if F2_PROF
+			prof_periods++;
+#endif
 			ring.topup(s.P);
 			if (mode == 1) {
 				/* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
@@ -879,6 +892,15 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 	}
 	__threadfence();
 	PROF_FLUSH(0);
+#if F2_PROF
+	if (lane == 0) {
+		/* 16: busiest scan warp (cycles in steps + top-up), 17: its rounds, 18: all rounds, 19: all periods */
+		atomicMax(a.prof + 16, prof_acc[4] + prof_acc[5]);
+		atomicMax(a.prof + 17, (unsigned long long)prof_rounds);
+		atomicAdd(a.prof + 18, (unsigned long long)prof_rounds);
+		atomicAdd(a.prof + 19, (unsigned long long)prof_periods);
+	}
+#endif
 	if (lane == 0)
 		atomicAdd(a.scan_done, 1u);
 }

@@ -42,6 +42,8 @@ if os.environ.get("F2_PROF"):
     api.lib().acm_gpu_plan_debug_counters(plan._h, buf)
     v = [x / args.runs / 1e6 for x in buf]
     print("scan  Mcycles/run (all warps): publish %.1f flow %.1f hyst %.1f head %.1f steps %.1f topup %.1f" % tuple(v[0:6]))
+    print("scan  busiest warp %.2f Mcycles, max rounds/warp %.0f, rounds %.0f, periods %.0f (x runs)" %
+          (buf[16] / 1e6, buf[17], buf[18] / args.runs, buf[19] / args.runs))
     print("work  Mcycles/run (all warps): decode %.1f idle %.1f claim %.1f" % tuple(v[8:11]))
 plan.fetch(s, cs)
 assert np.all(s["status"] == 0)
