@@ -186,6 +186,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+/* shared-memory words handed from one worker warp to the next under the slot's busy lock, or
+ * polled by other warps: every access is an atomic, which is also what racecheck understands */
+__device__ __forceinline__ uint32_t at_ld(uint32_t *p) { return atomicAdd(p, 0u); }
+__device__ __forceinline__ void at_st(uint32_t *p, uint32_t v) { atomicExch(p, v); }
 __device__ __forceinline__ uint32_t vol_ld(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void vol_st(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
@@ -548,7 +552,7 @@ juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint
 template <bool CKS>
 __device__ __forceinline__ void decode_record(SmemWork &sm, const KernelArgs &a, uint32_t *wb, int slot, int lane,
 					      const uint8_t *recbase, uint32_t *gh, DevStream &d, uint32_t &d_id,
-					      SlotCtl *ctl)
+					      SlotCtl *ctl, uint32_t &pos, unsigned long long &cks, uint32_t &dead)
 {
 	Rec e;
 	{
@@ -565,13 +569,10 @@ __device__ __forceinline__ void decode_record(SmemWork &sm, const KernelArgs &a,
 	const uint32_t bno = e.blk & 0x7FFFFFFFu;
 	const bool last = (e.blk >> 31) != 0;
 	if (bno == 0) {
-		if (lane == 0) {
-			sm.pos[slot] = 0u;
-			sm.cks[slot] = 0ull;
-		}
-		__syncwarp();
+		pos = 0u;
+		cks = 0ull;
 	}
-	if (vol_ld(&sm.dead[slot]) == e.desc + 1u)
+	if (dead == e.desc + 1u)
 		return; /* stream already finalised by a corrupt code (descriptor ids are unique) */
 	const uint32_t limit_w = d.file_end + 8u;
 	const bool ok = e.status == SCAN_OK;
@@ -665,7 +666,6 @@ __device__ __forceinline__ void decode_record(SmemWork &sm, const KernelArgs &a,
 	}
 	bad = __any_sync(0xFFFFFFFFu, bad);
 	__syncwarp();
-	uint32_t pos = sm.pos[slot];
 	int st = 0;
 	if (bad)
 		st = -6;
@@ -681,11 +681,8 @@ __device__ __forceinline__ void decode_record(SmemWork &sm, const KernelArgs &a,
 		if (CKS) {
 			for (int o = 16; o; o >>= 1)
 				c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
-			if (lane == 0)
-				sm.cks[slot] += c2;
+			cks += c2;
 		}
-		if (lane == 0)
-			sm.pos[slot] = pos;
 	}
 	if (!ok || bad || last) {
 		/* finalise: results + zero padding of the undelivered tail */
@@ -702,10 +699,10 @@ __device__ __forceinline__ void decode_record(SmemWork &sm, const KernelArgs &a,
 		if (lane == 0) {
 			a.status[d.index] = st;
 			a.words[d.index] = pos;
-			a.cks[d.index] = a.fmt.checksums ? sm.cks[slot] : 0ull;
-			vol_st(&sm.dead[slot], e.desc + 1u);
+			a.cks[d.index] = a.fmt.checksums ? cks : 0ull;
 			vol_st(&ctl->dead, e.desc + 1u); /* the slot's scan lane stops walking this stream */
 		}
+		dead = e.desc + 1u;
 	}
 	__syncwarp();
 }
@@ -927,7 +924,7 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 #pragma unroll
 		for (int k = 0; k < MAXOWN / 32; k++) {
 			const uint32_t j = (uint32_t)lane + 32u * k;
-			if (j < J && !vol_ld(&sm.busy[j]) && vol_ld(&ctl[w + n_work * j].prod) != vol_ld(&sm.cons[j]))
+			if (j < J && !at_ld(&sm.busy[j]) && vol_ld(&ctl[w + n_work * j].prod) != at_ld(&sm.cons[j]))
 				rdy |= 1u << k;
 		}
 		uint32_t m[MAXOWN / 32];
@@ -977,7 +974,19 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		PROF_MARK(2); /* 8+2: claim */
 		__threadfence_block();
 		const uint32_t g = w + n_work * (uint32_t)slot;
-		uint32_t c = vol_ld(&sm.cons[slot]);
+		/* the slot's running state, handed over under the busy lock */
+		uint32_t c = 0, pos = 0, dead = 0;
+		unsigned long long cks = 0ull;
+		if (lane == 0) {
+			c = at_ld(&sm.cons[slot]);
+			pos = at_ld(&sm.pos[slot]);
+			dead = at_ld(&sm.dead[slot]);
+			cks = atomicAdd(&sm.cks[slot], 0ull);
+		}
+		c = __shfl_sync(0xFFFFFFFFu, c, 0);
+		pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+		dead = __shfl_sync(0xFFFFFFFFu, dead, 0);
+		cks = __shfl_sync(0xFFFFFFFFu, cks, 0);
 		const uint32_t p = vol_ld(&ctl[g].prod);
 		__threadfence(); /* acquire: the records behind prod */
 		uint32_t nrec = p - c;
@@ -988,10 +997,13 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		uint32_t d_id = 0xFFFFFFFFu;
 		for (uint32_t k = 0; k < nrec; k++, c++)
 			decode_record<CKS>(sm, a, wb, slot, lane, slot_ring + (size_t)(c % RING_D) * REC_BYTES,
-					   a.hist + (size_t)g * HIST_WORDS, d, d_id, ctl + g);
+					   a.hist + (size_t)g * HIST_WORDS, d, d_id, ctl + g, pos, cks, dead);
 		__threadfence(); /* the records have been read before the scan lane may overwrite them */
 		if (lane == 0) {
-			vol_st(&sm.cons[slot], c);
+			at_st(&sm.pos[slot], pos);
+			at_st(&sm.dead[slot], dead);
+			atomicExch(&sm.cks[slot], cks);
+			at_st(&sm.cons[slot], c);
 			vol_st(&ctl[g].cons, c);
 			__threadfence_block();
 			atomicExch(&sm.busy[slot], 0u);
