@@ -229,8 +229,13 @@ struct ScanRing {
 	uint32_t fe_byte;     /* bytes of the stream that exist (relative to base) */
 	uint32_t fill, fill_prev, ready_w, ready_p;
 
+	/* no stream: the lane's walk sits on the HALT page at P = 0 over two zero ring words, so that
+	 * all idle lanes of a warp look up the same table word (a broadcast, not a bank conflict) */
 	__device__ __forceinline__ void idle()
 	{
+		cp_async_wait_all();
+		const_cast<uint32_t *>(rw)[0] = 0u;
+		const_cast<uint32_t *>(rw)[32] = 0u;
 		base = nullptr;
 		room16 = 0;
 		full16 = 0;
@@ -742,6 +747,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		if (active && dead == cur + 1u) {
 			active = false; /* the decode side found a corrupt t-code: abandon the stream */
 			ring.idle();
+			P = 0;
 		}
 		if (!active && !exhausted) {
 			const uint32_t idx = atomicAdd(a.counter, 1u);
@@ -880,6 +886,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			if (e.blk >> 31) {
 				active = false;
 				ring.idle();
+				P = 0;
 			}
 		}
 		/* the records are in L2 before they are announced to the decode CTA (another SM) */
