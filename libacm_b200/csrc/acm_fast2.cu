@@ -922,11 +922,11 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl);
 	uint32_t *wb = sm.wb[warp];
 	uint32_t rot = (uint32_t)warp * 5u, nap = 64u;
+	bool confirmed = false;
 	PROF_DECL;
 	for (;;) {
 		PROF_MARK(0); /* 8+0: decode */
 		const bool done = *reinterpret_cast<volatile uint32_t *>(a.scan_done) == a.n_scan * (uint32_t)SW;
-		__threadfence();
 		uint32_t rdy = 0; /* bit k: owned slot lane + 32 k has records pending and is not claimed */
 #pragma unroll
 		for (int k = 0; k < MAXOWN / 32; k++) {
@@ -943,8 +943,15 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		}
 		if (!any) {
 			if (done) {
-				PROF_FLUSH(8);
-				break;
+				/* every scan warp has finished: look once more behind a fence (acquire: all
+				 * their announcements are visible), then leave */
+				if (confirmed) {
+					PROF_FLUSH(8);
+					break;
+				}
+				__threadfence();
+				confirmed = true;
+				continue;
 			}
 			__nanosleep(nap); /* idle: back off */
 			nap = nap < 2048u ? nap * 2u : nap;
@@ -952,6 +959,7 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 			continue;
 		}
 		nap = 64u;
+		confirmed = false;
 		/* round robin from a rotating start so that every slot gets its turn */
 		int slot = -1;
 		rot &= (uint32_t)(MAXOWN - 1);
