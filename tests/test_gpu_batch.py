@@ -178,3 +178,34 @@ def test_more_streams_than_slots(checker):
     assert gu.compare(imgs[::7], s[::7], out, checker, checksums=True) == []
     want = s["total_values"] - s["total_values"] % s["channels"]
     assert np.array_equal(s["words"], want)
+
+
+def test_config2_full_size(checker):
+    """BASELINE configs[1] at full size (the bench workload: 10 000 clips, 1.2 G samples): every
+    stream ends with status 0 and all its words, every 12th stream is compared byte for byte (and
+    by checksum) with the checker, and the checksum of checksums equals the value the bench's parity
+    gate has reported since the first generic-kernel run of this corpus."""
+    import torch
+    import bench
+    blob, offs, lens = bench.build_corpus(bench.N_STREAMS, 0)
+    opts = api.make_opts(want_checksums=1)
+    s = api.new_streams(offs, lens)
+    d_blob = torch.from_numpy(blob).cuda()
+    api.probe(blob, s, opts)
+    nbytes = api.layout(s, 2)
+    d_out = torch.full((nbytes + 16,), 0xAA, dtype=torch.uint8, device="cuda")
+    plan = api.Plan(s, opts)
+    cs = torch.cuda.current_stream().cuda_stream
+    plan.run(d_blob, d_out, cs)
+    plan.fetch(s, cs)
+    plan.close()
+    assert np.all(s["status"] == 0) and np.array_equal(s["words"], s["total_values"])
+    assert int(np.sum(s["checksum"].astype(np.uint64), dtype=np.uint64)) == 2964506047360995033
+    out = d_out.cpu().numpy()
+    for i in range(0, bench.N_STREAMS, 12):
+        o, l = int(offs[i]), int(lens[i])
+        a = checker.decode(blob[o:o + l])
+        p = int(s["out_off"][i])
+        assert (a.status, a.words) == (0, int(s["words"][i])), i
+        assert np.array_equal(out[p:p + a.pcm.size], a.pcm), i
+        assert int(s["checksum"][i]) == api.checksum_ref(a.pcm, a.words), i
