@@ -355,7 +355,7 @@ def main():
     ap.add_argument("--streams", type=int, default=N_STREAMS)
     ap.add_argument("--ref-streams", type=int, default=N_STREAMS,
                     help="streams of the workload the CPU legs decode per step")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
