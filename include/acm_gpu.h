@@ -120,6 +120,9 @@ void acm_gpu_plan_split(const acm_gpu_plan *plan, uint64_t *n_fast, uint64_t *n_
 /* average device time of the kernels of the last run on that plan, ms (CUDA events on cuda_stream) */
 float acm_gpu_plan_last_ms(acm_gpu_plan *plan);
 void acm_gpu_plan_destroy(acm_gpu_plan *plan);
+/* tuning builds (-DF2_PROF, tools/build_variants.py): copies the 64 in-kernel cycle counters the
+ * kernels accumulated over this plan's runs; all zero in a normal build */
+int acm_gpu_plan_debug_counters(acm_gpu_plan *plan, unsigned long long *out64);
 
 /* acm_gpu_decode_batch keeps its device staging buffers and streams between calls (host-buffer
  * path); this frees them */
