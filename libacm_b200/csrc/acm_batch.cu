@@ -190,7 +190,7 @@ struct acm_gpu_plan {
 	uint32_t *d_words;
 	unsigned long long *d_cks;
 	acm_tables *d_tables;
-	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue; [4*nseg] error flag */
+	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue, [4g+2] finished scan warps, [4g+3] heartbeat; [4*nseg] error flag */
 	GenericScratch scratch;
 	uint32_t *d_hist;    /* fast kernel history, 256 words per stream slot */
 	uint8_t *d_ring;     /* fast kernel block-record rings */

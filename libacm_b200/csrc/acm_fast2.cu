@@ -193,6 +193,23 @@ __device__ __forceinline__ void at_st(uint32_t *p, uint32_t v) { atomicExch(p, v
 __device__ __forceinline__ uint32_t vol_ld(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void vol_st(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
 
+/*
+ * Watchdog of the two waiting loops.  The scan CTAs and the decode CTAs of a launch wait for each
+ * other, so all of them have to be resident; plan_create sizes the grid for that (one CTA per SM,
+ * at most the SM count), but a GPU shared with another process could still hold some back.
+ * Every scan round and every slot claim bumps a heartbeat word (scan_done[1]); a side that has
+ * waited WATCHDOG_NS while the heartbeat stood still raises the error flag (reported by
+ * acm_gpu_plan_fetch as an internal failure) and leaves, instead of hanging the device.
+ */
+constexpr unsigned long long WATCHDOG_NS = 4000000000ull;
+
+__device__ __forceinline__ unsigned long long now_ns()
+{
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
+
 /* selector facts: bit 16 prefix-coded (k), bit 17 bad, bit 18 t, bit 19 linear, bits 20..23 sub-type */
 enum { INF_K = 1u << 16, INF_BAD = 1u << 17, INF_T = 1u << 18, INF_LIN = 1u << 19 };
 
@@ -732,6 +749,8 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 	ring.idle();
 	bool active = false, exhausted = !enabled;
 	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
+	unsigned long long waiting_since = 0ull;
+	uint32_t seen_hb = 0;
 	PROF_DECL;
 #if F2_PROF
 	uint32_t prof_rounds = 0, prof_periods = 0;
@@ -772,8 +791,20 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 				break; /* every lane is out of streams */
 			__nanosleep(500);
 			PROF_MARK(1); /* 1: blocked by flow control */
+			const uint32_t hb = *reinterpret_cast<volatile uint32_t *>(a.scan_done + 1);
+			if (waiting_since == 0ull || hb != seen_hb) {
+				waiting_since = now_ns();
+				seen_hb = hb;
+			} else if (now_ns() - waiting_since > WATCHDOG_NS) {
+				if (lane == 0)
+					atomicExch(a.errflag, 2u); /* the decode side does not consume anything */
+				break;
+			}
 			continue;
 		}
+		waiting_since = 0ull;
+		if (lane == 0)
+			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
 #if F2_HYST
 		if (!__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2))) {
 			__nanosleep(300); /* nobody is close to starving the decode: let lanes bunch up */
@@ -923,6 +954,8 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 	uint32_t *wb = sm.wb[warp];
 	uint32_t rot = (uint32_t)warp * 5u, nap = 64u;
 	bool confirmed = false;
+	unsigned long long waiting_since = 0ull;
+	uint32_t seen_hb = 0;
 	PROF_DECL;
 	for (;;) {
 		PROF_MARK(0); /* 8+0: decode */
@@ -956,10 +989,20 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 			__nanosleep(nap); /* idle: back off */
 			nap = nap < 2048u ? nap * 2u : nap;
 			PROF_MARK(1); /* 8+1: idle */
+			const uint32_t hb = *reinterpret_cast<volatile uint32_t *>(a.scan_done + 1);
+			if (waiting_since == 0ull || hb != seen_hb) {
+				waiting_since = now_ns();
+				seen_hb = hb;
+			} else if (now_ns() - waiting_since > WATCHDOG_NS) {
+				if (lane == 0)
+					atomicExch(a.errflag, 3u); /* no record, no end of scan, nobody moving */
+				break;
+			}
 			continue;
 		}
 		nap = 64u;
 		confirmed = false;
+		waiting_since = 0ull;
 		/* round robin from a rotating start so that every slot gets its turn */
 		int slot = -1;
 		rot &= (uint32_t)(MAXOWN - 1);
@@ -986,6 +1029,8 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		got = __shfl_sync(0xFFFFFFFFu, got, 0);
 		if (!got)
 			continue;
+		if (lane == 0)
+			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
 		PROF_MARK(2); /* 8+2: claim */
 		__threadfence_block();
 		const uint32_t g = w + n_work * (uint32_t)slot;

@@ -26,7 +26,7 @@ struct KernelArgs {
 	uint32_t *hist;           /* fast kernel: per-slot transform history (256 words each) */
 	uint8_t *ring;            /* fast kernel: per-slot ring of block records */
 	uint8_t *slotctl;         /* fast kernel: per-slot control words (zeroed before launch) */
-	uint32_t *scan_done;      /* fast kernel: scan warps that have finished (zeroed before launch) */
+	uint32_t *scan_done;      /* fast kernel: [0] scan warps that have finished, [1] heartbeat (zeroed before launch) */
 	uint32_t n_scan;          /* fast kernel: scan CTAs (the first n_scan of the grid) */
 	uint32_t n_slots;         /* fast kernel: stream slots in use */
 	unsigned long long *prof; /* 64 counters, only written by -DF2_PROF tuning builds */
