@@ -123,6 +123,9 @@ void acm_gpu_plan_destroy(acm_gpu_plan *plan);
 /* tuning builds (-DF2_PROF, tools/build_variants.py): copies the 64 in-kernel cycle counters the
  * kernels accumulated over this plan's runs; all zero in a normal build */
 int acm_gpu_plan_debug_counters(acm_gpu_plan *plan, unsigned long long *out64);
+/* grid geometry of the level-7 / 16-row kernel for n streams: out3 = { scan CTAs, decode CTAs, stream
+ * slots }; host logic only (tests) */
+void acm_gpu_debug_geometry(uint64_t n, int sms, int max_ctas, uint32_t *out3);
 
 /* acm_gpu_decode_batch keeps its device staging buffers and streams between calls (host-buffer
  * path); this frees them */

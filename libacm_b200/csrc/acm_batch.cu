@@ -618,6 +618,14 @@ extern "C" float acm_gpu_plan_last_ms(acm_gpu_plan *p)
 
 extern "C" void acm_gpu_plan_destroy(acm_gpu_plan *p) { plan_free(p); }
 
+/* the grid the level-7 / 16-row kernel would get for n streams on a device with `sms` SMs when it may
+ * use at most max_ctas of them: out3 = { scan CTAs, decode CTAs, stream slots }.  Pure host logic
+ * (no device needed): lets the CPU-only test tier check the co-residency rules. */
+extern "C" void acm_gpu_debug_geometry(uint64_t n, int sms, int max_ctas, uint32_t *out3)
+{
+	fast2_geometry(n, sms, max_ctas, &out3[0], &out3[1], &out3[2]);
+}
+
 /* tuning builds (-DF2_PROF): the 64 in-kernel cycle counters, accumulated over the plan's runs */
 extern "C" int acm_gpu_plan_debug_counters(acm_gpu_plan *p, unsigned long long *out64)
 {

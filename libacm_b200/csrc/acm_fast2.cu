@@ -786,32 +786,30 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		}
 		const uint32_t lead = prodn - cons;
 		const bool can = active && lead < (uint32_t)RING_D;
-		if (!__any_sync(0xFFFFFFFFu, can)) {
-			if (!__any_sync(0xFFFFFFFFu, active))
-				break; /* every lane is out of streams */
-			__nanosleep(500);
-			PROF_MARK(1); /* 1: blocked by flow control */
-			const uint32_t hb = *reinterpret_cast<volatile uint32_t *>(a.scan_done + 1);
-			if (waiting_since == 0ull || hb != seen_hb) {
-				waiting_since = now_ns();
-				seen_hb = hb;
-			} else if (now_ns() - waiting_since > WATCHDOG_NS) {
-				if (lane == 0)
-					atomicExch(a.errflag, 2u); /* the decode side does not consume anything */
+		{
+			/* nothing to walk: every lane is out of streams (done), or every lane with a stream is
+			 * RING_D records ahead; nobody close to starving the decode: let lanes bunch up */
+			const bool none = !__any_sync(0xFFFFFFFFu, can);
+			if (none && !__any_sync(0xFFFFFFFFu, active))
 				break;
+			if (none || (F2_HYST && !__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2)))) {
+				__nanosleep(none ? 500 : 300);
+				PROF_MARK(1); /* 1: waiting for the decode side */
+				const uint32_t hb = *reinterpret_cast<volatile uint32_t *>(a.scan_done + 1);
+				if (waiting_since == 0ull || hb != seen_hb) {
+					waiting_since = now_ns();
+					seen_hb = hb;
+				} else if (now_ns() - waiting_since > WATCHDOG_NS) {
+					if (lane == 0)
+						atomicExch(a.errflag, 2u); /* the decode side does not consume anything */
+					break;
+				}
+				continue;
 			}
-			continue;
 		}
 		waiting_since = 0ull;
 		if (lane == 0)
 			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
-#if F2_HYST
-		if (!__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2))) {
-			__nanosleep(300); /* nobody is close to starving the decode: let lanes bunch up */
-			PROF_MARK(2); /* 2: hysteresis sleep */
-			continue;
-		}
-#endif
 		PROF_MARK(3); /* 3: round head (retire / acquire) */
 #if F2_PROF
 		prof_rounds++;
@@ -1105,6 +1103,9 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 			sm.cks[i] = 0ull;
 		}
 		__syncthreads();
+#ifdef F2_TEST_NO_DECODE
+		return; /* watchdog test: the scan side must give up on its own */
+#endif
 		work_cta<CKS>(a, sm, warp, lane);
 	}
 }

@@ -37,3 +37,25 @@ def test_sm100a_cubin_present():
     out = subprocess.run(["cuobjdump", "-lelf", api.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "sm_90" not in out and "sm_80" not in out
+
+
+def test_fast_kernel_geometry_rules():
+    """Host logic of the scan-CTA / decode-CTA launch: all CTAs of a launch have to be resident
+    together (they wait for each other), so the grid never exceeds its SM budget, there is at least one
+    CTA of each kind, every slot has an owner with room for it, and small batches use small grids."""
+    lib = C.CDLL(api.LIB_PATH)
+    lib.acm_gpu_debug_geometry.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint32)]
+    lib.acm_gpu_debug_geometry.restype = None
+    out = (C.c_uint32 * 3)()
+    for sms in (2, 8, 37, 132, 148):
+        for budget in sorted({2, sms // 4 or 2, sms}):
+            for n in (1, 31, 32, 33, 255, 256, 257, 1250, 10_000, 125_000, 5_000_000):
+                lib.acm_gpu_debug_geometry(n, sms, budget, out)
+                n_scan, n_work, n_slots = out[0], out[1], out[2]
+                assert n_scan >= 1 and n_work >= 1
+                assert n_scan + n_work <= max(2, min(budget, sms))
+                assert 32 <= n_slots <= n_scan * 256 and n_slots % 32 == 0
+                assert n_slots <= n_work * 128            # MAXOWN slots per decode CTA
+                assert n_slots <= (n + 31) // 32 * 32      # never more slots than streams (whole warps)
+    lib.acm_gpu_debug_geometry(10_000, 148, 148, out)
+    assert tuple(out) == (33, 115, 8448)                  # the bench's full-batch launch
