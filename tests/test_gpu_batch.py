@@ -209,3 +209,33 @@ def test_config2_full_size(checker):
         assert (a.status, a.words) == (0, int(s["words"][i])), i
         assert np.array_equal(out[p:p + a.pcm.size], a.pcm), i
         assert int(s["checksum"][i]) == api.checksum_ref(a.pcm, a.words), i
+
+
+def test_replication_by_descriptor():
+    """BASELINE configs[3] mechanics at small scale (tools/scale_1m.py runs it with 1 000 000 streams):
+    several descriptors reference the same image and write their own output range; all replicas of an
+    image produce the same bytes and checksum."""
+    import torch
+    imgs = corpus.images(corpus.fallout_params(300, seed=41, lo=500, hi=30_000, channels=2))
+    blob, offs, lens = gu.pack(imgs)
+    reps = 6
+    opts = api.make_opts(want_checksums=1)
+    s = api.new_streams(np.tile(offs, reps), np.tile(lens, reps))
+    d_blob = torch.from_numpy(blob).cuda()
+    api.probe(blob, s, opts)
+    nbytes = api.layout(s, 2)
+    d_out = torch.full((nbytes + 16,), 0xAA, dtype=torch.uint8, device="cuda")
+    plan = api.Plan(s, opts)
+    plan.run(d_blob, d_out, torch.cuda.current_stream().cuda_stream)
+    plan.fetch(s, torch.cuda.current_stream().cuda_stream)
+    plan.close()
+    out = d_out.cpu().numpy()
+    assert np.all(s["status"] == 0)
+    ck = s["checksum"].reshape(reps, len(imgs))
+    assert np.all(ck == ck[0])
+    for i in range(0, len(imgs), 17):
+        nb = int(s["total_values"][i]) * 2
+        first = out[int(s["out_off"][i]):int(s["out_off"][i]) + nb]
+        for r in range(1, reps):
+            o = int(s["out_off"][r * len(imgs) + i])
+            assert np.array_equal(out[o:o + nb], first)
