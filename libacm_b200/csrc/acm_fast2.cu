@@ -97,7 +97,10 @@ constexpr int STAGE_W = 1088;            /* 4352 bytes: a whole block (<= 4179 B
 constexpr int LIST_W = 256;              /* listA (k from the front, t from the back), listB (linear) */
 constexpr int WB_WORDS = X0_W + STAGE_W + LIST_W;
 constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [128,192) X2 tail [192,256) */
-constexpr int KMAX = 4;                  /* blocks a worker decodes per slot claim */
+#ifndef F2_KMAX
+#define F2_KMAX 8
+#endif
+constexpr int KMAX = F2_KMAX;            /* blocks a worker decodes per slot claim */
 
 static_assert(WB_WORDS >= XWORDS, "transform layout must fit the worker buffer");
 static_assert(SW <= W, "scan CTAs are launched with the decode CTAs' thread count");
