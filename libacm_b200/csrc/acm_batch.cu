@@ -363,6 +363,25 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			return a.index < b.index;
 		};
 		std::sort(fast.begin(), fast.end(), by_len);
+		if (!fast.empty()) {
+			/* The streams that start together (one per stream slot) are dealt out to the scan
+			 * warps like cards: every warp -- 32 consecutive queue entries -- gets one of the very
+			 * longest streams, one of the next longest, and so on down.  A scan warp walks its 32
+			 * lanes in lockstep, a round lasts as long as its slowest lane; with the longest
+			 * streams spread out, the warps that finish last (the launch is latency-bound on them)
+			 * run their final rounds with one or two busy lanes instead of 32.  The rest of the
+			 * queue stays longest-first. */
+			uint32_t n_scan = 0, n_work = 0, n_slots = 0;
+			fast2_geometry(fast.size(), sm_count, max_ctas, &n_scan, &n_work, &n_slots);
+			const size_t head = std::min<size_t>(n_slots, fast.size()) / 32 * 32, warps = head / 32;
+			if (warps > 1) {
+				std::vector<DevStream> dealt(head);
+				for (size_t w = 0; w < warps; w++)
+					for (size_t l = 0; l < 32; l++)
+						dealt[w * 32 + l] = fast[l * warps + w];
+				std::copy(dealt.begin(), dealt.end(), fast.begin());
+			}
+		}
 		auto by_work = [](const DevStream &a, const DevStream &b) {
 			uint64_t wa = (uint64_t)a.n_attempt * (a.rows << a.level);
 			uint64_t wb = (uint64_t)b.n_attempt * (b.rows << b.level);
