@@ -376,9 +376,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			const size_t head = std::min<size_t>(n_slots, fast.size()) / 32 * 32, warps = head / 32;
 			if (warps > 1) {
 				std::vector<DevStream> dealt(head);
-				for (size_t w = 0; w < warps; w++)
-					for (size_t l = 0; l < 32; l++)
-						dealt[w * 32 + l] = fast[l * warps + w];
+				for (size_t r = 0; r < head; r++)
+					dealt[(r % warps) * 32 + r / warps] = fast[r];
 				std::copy(dealt.begin(), dealt.end(), fast.begin());
 			}
 		}
