@@ -754,6 +754,8 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
 	unsigned long long waiting_since = 0ull;
 	uint32_t seen_hb = 0;
+	uint4 c4n = make_uint4(0u, 0u, 0u, 0u);
+	bool fresh = false;
 	PROF_DECL;
 #if F2_PROF
 	uint32_t prof_rounds = 0, prof_periods = 0;
@@ -762,10 +764,12 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		PROF_MARK(0); /* 0: round tail (publish) */
 		uint32_t cons = 0, dead = 0;
 		if (enabled) {
-			const uint4 c4 = __ldcv(reinterpret_cast<const uint4 *>(ctl)); /* never a stale line */
+			/* never a stale line; after a walk, the copy fetched while walking */
+			const uint4 c4 = fresh ? c4n : __ldcv(reinterpret_cast<const uint4 *>(ctl));
 			cons = c4.y;
 			dead = c4.z;
 		}
+		fresh = false;
 		if (active && dead == cur + 1u) {
 			active = false; /* the decode side found a corrupt t-code: abandon the stream */
 			ring.idle();
@@ -813,6 +817,12 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		waiting_since = 0ull;
 		if (lane == 0)
 			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
+		if (enabled) {
+			/* the control words for the next round: an L2 round trip that the walk hides (what it
+			 * may miss is one more consumed record or a stop request: both wait a round) */
+			c4n = __ldcv(reinterpret_cast<const uint4 *>(ctl));
+			fresh = true;
+		}
 		PROF_MARK(3); /* 3: round head (retire / acquire) */
 #if F2_PROF
 		prof_rounds++;
