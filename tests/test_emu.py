@@ -73,3 +73,23 @@ def test_fast2_core_walk_and_unpack():
     for cut in range(14, len(img), 7):
         assert emu.fast2_check(img[:cut]) >= 0, cut
     assert blocks > 100
+
+
+def test_fast2_core_on_garbage_payloads():
+    """Arbitrary bytes behind a valid level-7 / 16-row header: the table walk must reach the same
+    verdict as the generic scan (a clean block, or "re-walk me": bad selector / ran past the end),
+    and where a block is clean, the same offsets and values.  Random data runs into bad selectors
+    (6 of 32 codes), 16-bit linear columns (the SKIP6 page) and the end of the stream all the time."""
+    rng = np.random.default_rng(2026)
+    hdr = bytes(corpus.images([gen.params(level=7, rows=16, total_values=2048 * 40, dist=gen.DIST_STRESS, seed=1)])[0][:14])
+    clean = 0
+    for k in range(400):
+        body = rng.integers(0, 256, size=int(rng.integers(60, 9000)), dtype=np.uint8)
+        if k % 3 == 0:
+            body[rng.random(body.size) < 0.985] = 0   # long runs of zero columns / zero symbols
+        if k % 3 == 1:
+            body &= 0x9C                              # selectors biased towards valid small codes
+        n = emu.fast2_check(hdr + body.tobytes())
+        assert n >= 0, (k, n)
+        clean += n
+    assert clean > 20

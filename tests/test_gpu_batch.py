@@ -239,3 +239,27 @@ def test_replication_by_descriptor():
         for r in range(1, reps):
             o = int(s["out_off"][r * len(imgs) + i])
             assert np.array_equal(out[o:o + nb], first)
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_garbage_payloads_status_and_words(checker, kernel):
+    """Arbitrary bytes behind a valid level-7 / 16-row header.  The PCM of such streams is not defined by
+    the reference (a dequantisation index outside the block's table reads stale memory), but
+    what its read loop returns -- status and words delivered -- is: both kernels must agree with it."""
+    rng = np.random.default_rng(77)
+    hdr = bytes(corpus.images([gen.params(level=7, rows=16, total_values=2048 * 6, dist=gen.DIST_STRESS, seed=1)])[0][:14])
+    imgs = []
+    for k in range(240):
+        body = rng.integers(0, 256, size=int(rng.integers(40, 7000)), dtype=np.uint8)
+        if k % 3 == 0:
+            body[rng.random(body.size) < 0.985] = 0
+        if k % 3 == 1:
+            body &= 0x9C
+        imgs.append(hdr + body.tobytes())
+    s, _ = gu.decode_host(imgs, align=1, kernel=kernel)
+    seen = set()
+    for i, img in enumerate(imgs):
+        a = checker.decode(img)
+        assert (int(s["status"][i]), int(s["words"][i])) == (a.status, a.words), (i, k)
+        seen.add(a.status)
+    assert {-6, -7} <= seen
