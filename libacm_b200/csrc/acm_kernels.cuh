@@ -51,7 +51,7 @@ struct GenericScratch {
 /* words of scratch one CTA of the generic kernel needs */
 inline size_t generic_scratch_words(uint32_t max_blen, uint32_t max_cols)
 {
-	return 2 * (size_t)max_blen + 3 * (size_t)max_cols + 64;
+	return 2 * (size_t)max_blen + 4 * (size_t)max_cols + 64; /* two block buffers, history, two offset buffers */
 }
 
 cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_ctas,
