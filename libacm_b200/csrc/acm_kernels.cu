@@ -50,11 +50,15 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 {
 	__shared__ TablesSmem tab;
 	__shared__ int s_si;
-	__shared__ ScanResult s_scan[2];
+	/* scan -> decode hand-over, all through shared-memory atomics (ordered by fences; racecheck
+	 * understands atomics and barriers, not flags): the scan thread publishes a block's verdict in
+	 * s_hand[b & 1] and bumps s_scanned; decode thread 0 copies it to s_scan for the other decode
+	 * threads (behind their barrier) and bumps s_consumed once the block's offsets are free */
+	__shared__ uint32_t s_hand[2][4];
+	__shared__ ScanResult s_scan;
 	__shared__ int s_bad;
 	__shared__ unsigned long long s_cks;
-	/* scan -> decode hand-over: blocks scanned / blocks whose offsets are no longer needed */
-	__shared__ volatile uint32_t s_scanned, s_consumed, s_stop;
+	__shared__ uint32_t s_scanned, s_consumed, s_stop;
 
 	const int tid = threadIdx.x;
 	const bool scanner = tid >= GEN_THREADS;
@@ -94,15 +98,18 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 			/* ---- 1. scan, one block ahead of the decode */
 			if (tid == GEN_THREADS) {
 				for (uint32_t b = 0; b < d.n_attempt; b++) {
-					while (b - s_consumed >= 2u && !s_stop)
+					while (b - atomicAdd(&s_consumed, 0u) >= 2u && !atomicAdd(&s_stop, 0u))
 						__nanosleep(40);
-					if (s_stop)
+					if (atomicAdd(&s_stop, 0u))
 						break;
 					const ScanResult sc = scan_block(br, P, limit, cols, rows, coloff0 + (b & 1u) * scr.max_cols,
 									 0u, tab.kind, tab.k8);
-					s_scan[b & 1u] = sc;
-					__threadfence_block();
-					s_scanned = b + 1u;
+					atomicExch(&s_hand[b & 1u][0], (uint32_t)sc.status);
+					atomicExch(&s_hand[b & 1u][1], (uint32_t)sc.val);
+					atomicExch(&s_hand[b & 1u][2], sc.ncols);
+					atomicExch(&s_hand[b & 1u][3], sc.end);
+					__threadfence_block(); /* the offsets (global scratch, same CTA) and the verdict, then the count */
+					atomicExch(&s_scanned, b + 1u);
 					if (sc.status != SCAN_OK)
 						break; /* the stream ends with this block */
 					P = sc.end;
@@ -115,13 +122,18 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 			decode_sync();
 
 			for (uint32_t b = 0; b < d.n_attempt; b++) {
-				while (s_scanned <= b)
-					__nanosleep(20);
-				__threadfence_block();
-				if (tid == 0)
+				if (tid == 0) {
+					while (atomicAdd(&s_scanned, 0u) <= b)
+						__nanosleep(20);
+					__threadfence_block();
+					s_scan.status = (int)atomicAdd(&s_hand[b & 1u][0], 0u);
+					s_scan.val = (int)atomicAdd(&s_hand[b & 1u][1], 0u);
+					s_scan.ncols = atomicAdd(&s_hand[b & 1u][2], 0u);
+					s_scan.end = atomicAdd(&s_hand[b & 1u][3], 0u);
 					s_bad = 0;
+				}
 				decode_sync();
-				const ScanResult sc = s_scan[b & 1u];
+				const ScanResult sc = s_scan;
 				const uint32_t *coloff = coloff0 + (b & 1u) * scr.max_cols;
 				/* ---- 2. unpack (column sc.ncols is included when its payload ran past
 				 * the limit: a t-code that still fits may be out of range first) */
@@ -136,7 +148,7 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 				}
 				decode_sync();
 				if (tid == 0)
-					s_consumed = b + 1u; /* this block's offsets may be overwritten */
+					atomicExch(&s_consumed, b + 1u); /* this block's offsets may be overwritten */
 				if (s_bad)
 					st = -6;
 				else if (sc.status != SCAN_OK)
@@ -179,7 +191,7 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 				decode_sync();
 			}
 			if (tid == 0)
-				s_stop = 1; /* the scan thread may be a block ahead of a stream that just ended */
+				atomicExch(&s_stop, 1u); /* the scan thread may be a block ahead of a stream that just ended */
 
 			/* zero padding of the undelivered tail (acmtool.c:293-310) */
 			{
