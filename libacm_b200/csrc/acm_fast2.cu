@@ -963,7 +963,7 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 	const uint32_t J = a.n_slots > w ? (a.n_slots - w + n_work - 1u) / n_work : 0u; /* owned slots */
 	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl);
 	uint32_t *wb = sm.wb[warp];
-	uint32_t rot = (uint32_t)warp * 5u, nap = 64u;
+	uint32_t nap = 64u;
 	bool confirmed = false;
 	unsigned long long waiting_since = 0ull;
 	uint32_t seen_hb = 0;
@@ -971,20 +971,27 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 	for (;;) {
 		PROF_MARK(0); /* 8+0: decode */
 		const bool done = *reinterpret_cast<volatile uint32_t *>(a.scan_done) == a.n_scan * (uint32_t)SW;
-		uint32_t rdy = 0; /* bit k: owned slot lane + 32 k has records pending and is not claimed */
+		/* the owned slot with the largest backlog of records that nobody holds: best = backlog << 8
+		 * | local slot index (0: nothing pending).  Largest first, not round robin: the slots of the
+		 * longest streams are the ones that fall behind while decoding is the bottleneck, and a
+		 * slot's records are decoded one after the other -- whatever backlog they still have when
+		 * the scan ends is the launch's tail */
+		uint32_t best = 0;
 #pragma unroll
 		for (int k = 0; k < MAXOWN / 32; k++) {
 			const uint32_t j = (uint32_t)lane + 32u * k;
-			if (j < J && !at_ld(&sm.busy[j]) && vol_ld(&ctl[w + n_work * j].prod) != at_ld(&sm.cons[j]))
-				rdy |= 1u << k;
+			if (j < J && !at_ld(&sm.busy[j])) {
+				const uint32_t backlog = vol_ld(&ctl[w + n_work * j].prod) - at_ld(&sm.cons[j]);
+				const uint32_t key = backlog ? (backlog << 8) | j : 0u;
+				best = key > best ? key : best;
+			}
 		}
-		uint32_t m[MAXOWN / 32];
-		uint32_t any = 0;
 #pragma unroll
-		for (int k = 0; k < MAXOWN / 32; k++) {
-			m[k] = __ballot_sync(0xFFFFFFFFu, (rdy >> k) & 1u);
-			any |= m[k];
+		for (int o = 16; o; o >>= 1) {
+			const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+			best = other > best ? other : best;
 		}
+		const uint32_t any = best;
 		if (!any) {
 			if (done) {
 				/* every scan warp has finished: look once more behind a fence (acquire: all
@@ -1014,26 +1021,7 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		nap = 64u;
 		confirmed = false;
 		waiting_since = 0ull;
-		/* round robin from a rotating start so that every slot gets its turn */
-		int slot = -1;
-		rot &= (uint32_t)(MAXOWN - 1);
-#pragma unroll
-		for (int t = 0; t <= MAXOWN / 32; t++) {
-			const uint32_t k = ((rot >> 5) + (uint32_t)t) & (MAXOWN / 32 - 1);
-			uint32_t mk = m[0];
-#pragma unroll
-			for (int q = 1; q < MAXOWN / 32; q++)
-				mk = k == (uint32_t)q ? m[q] : mk;
-			if (t == 0)
-				mk &= ~0u << (rot & 31u); /* first group: only at or after the start position */
-			if (slot < 0 && mk)
-				slot = (int)(32u * k) + __ffs((int)mk) - 1;
-		}
-		if (slot < 0) { /* only bits before the start position in its group: wrap around */
-			rot = 0;
-			continue;
-		}
-		rot = (uint32_t)slot + 1u;
+		const int slot = (int)(best & 255u);
 		uint32_t got = 0;
 		if (lane == 0)
 			got = atomicCAS(&sm.busy[slot], 0u, 1u) == 0u;
