@@ -87,6 +87,11 @@ constexpr int MAXOWN = 128;              /* slots a decode CTA can own */
 constexpr int RING_D = F2_RING_D;              /* block records a scan lane may be ahead of the decode */
 constexpr int REC_BYTES = 288;           /* 128 x u16 column offsets + 32-byte Rec */
 constexpr int RW = F2_RW;               /* ring words per scan lane (+1 duplicate of word 0) */
+constexpr int RROW = 32 * SW;            /* words per ring row: one word of every scan lane of the CTA */
+#ifndef F2_NHOLD
+#define F2_NHOLD 2
+#endif
+constexpr int NHOLD = F2_NHOLD;          /* 16-byte chunks per lane and period that travel through registers */
 constexpr int LEAD = RW / 4 - 2;               /* 16-byte chunks requested ahead of the read position */
 constexpr int SCAN_PERIOD = F2_PERIOD;         /* walk steps between two top-ups */
 constexpr int XPRE = 68;                 /* chunk -1: the previous block's last 64 X2 words (+4 pad) */
@@ -130,7 +135,7 @@ constexpr int OFFP = 2 * COLS + 8; /* bytes per lane of the column-offset stagin
 
 struct SmemScan {
 	uint16_t uni16[ACM_UNI_PAGES * ACM_UNI_PSIZE];
-	uint32_t ring[SW][(RW + 1) * 32]; /* [word][lane] */
+	uint32_t ring[RW + 1][SW * 32];   /* [word][scan warp][lane] */
 	/* column offsets of the block a lane is walking, copied to the block's record with
 	 * coalesced stores at the end of the round (scattered 2-byte global stores from 32 lanes
 	 * are 32 partial-sector writes per instruction) */
@@ -235,11 +240,27 @@ __device__ __forceinline__ uint32_t make_info(uint32_t kind)
 
 /*
  * A scan lane's view of its stream: RW ring words in shared memory, word i of the stream
- * (32-bit words from the 16-byte aligned stream base) at ring[(i % RW) * 32 + lane], plus a
- * copy of ring word 0 at index RW so that the pair (i, i+1) is always (slot, slot + 32).
+ * (32-bit words from the 16-byte aligned stream base) at ring[i % RW][32 * warp + lane], plus a
+ * copy of ring word 0 in row RW so that the pair (i, i+1) is always (row, row + 1).  With a
+ * power-of-two row size the address of the lane's word is (P << 5 & mask) | lane bits: two
+ * instructions on the walk's dependent chain.
  * Chunks (16 bytes) [.., fill) have been requested; words [.., ready_w) have landed, and
  * a 32-bit fetch at P is safe while P < ready_p.
  */
+/* the lane's ring word that holds bit P.  ring0 = row 0 of the CTA's ring, lane4 = byte offset
+ * of the lane within a row; row offset and lane offset share no bits when a row is a power of
+ * two bytes, so the sum is one LOP3 (and | or) and the array base folds into the LDS. */
+__device__ __forceinline__ const uint32_t *ring_word(const uint32_t *ring0, uint32_t lane4, uint32_t P32)
+{
+	constexpr uint32_t ROWB = 4u * RROW;
+	uint32_t off;
+	if (ROWB == 1024u)
+		off = (P32 & ((RW - 1u) * ROWB)) | lane4; /* P32 = 32 * position: (P >> 5) * 1024 without the low bits */
+	else
+		off = ((P32 >> 10) & (RW - 1u)) * ROWB + lane4;
+	return reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(ring0) + off);
+}
+
 struct ScanRing {
 	uint32_t saddr;       /* shared-space address of this lane's ring word 0 */
 	const uint32_t *rw;   /* the same, generic */
@@ -248,6 +269,12 @@ struct ScanRing {
 	uint32_t full16;      /* chunks [0, full16) lie entirely inside the file and the blob */
 	uint32_t fe_byte;     /* bytes of the stream that exist (relative to base) */
 	uint32_t fill, fill_prev, ready_w, ready_p;
+	/* the first NHOLD chunks a lane asks for in a period travel as one 16-byte load into
+	 * registers and are written to the ring at the next top-up: a quarter of the load/store
+	 * pipe's work of four 4-byte async copies (the scan SM's pipe is its busiest unit);
+	 * whatever a lane wants beyond that (bursts of wide columns) goes by cp.async */
+	uint4 hold[NHOLD];
+	uint32_t hold_c0, hold_n;
 
 	/* no stream: the lane's walk sits on the HALT page at P = 0 over two zero ring words, so that
 	 * all idle lanes of a warp look up the same table word (a broadcast, not a bank conflict) */
@@ -255,8 +282,9 @@ struct ScanRing {
 	{
 		cp_async_wait_all();
 		const_cast<uint32_t *>(rw)[0] = 0u;
-		const_cast<uint32_t *>(rw)[32] = 0u;
+		const_cast<uint32_t *>(rw)[RROW] = 0u;
 		base = nullptr;
+		hold_n = 0;
 		room16 = 0;
 		full16 = 0;
 		fe_byte = 0;
@@ -268,6 +296,7 @@ struct ScanRing {
 	{
 		cp_async_wait_all(); /* copies of the slot's previous stream must not land after this one's */
 		base = src;
+		hold_n = 0;
 		room16 = (uint32_t)(room >> 4);
 		fe_byte = file_end >> 3;
 		full16 = fe_byte >> 4 < room16 ? fe_byte >> 4 : room16;
@@ -284,15 +313,15 @@ struct ScanRing {
 	}
 	__device__ __forceinline__ void request(uint32_t c)
 	{
-		const uint32_t sa = saddr + ((c & (RW / 4 - 1)) << 9);
+		const uint32_t sa = saddr + (c & (RW / 4 - 1)) * (16u * RROW);
 		const uint8_t *g = base + (size_t)c * 16u;
 		if (c < full16) {
 			cp_async4(sa, g);
-			cp_async4(sa + 128, g + 4);
-			cp_async4(sa + 256, g + 8);
-			cp_async4(sa + 384, g + 12);
+			cp_async4(sa + 4 * RROW, g + 4);
+			cp_async4(sa + 8 * RROW, g + 8);
+			cp_async4(sa + 12 * RROW, g + 12);
 			if ((c & (RW / 4 - 1)) == 0)
-				cp_async4(saddr + RW * 128, g);
+				cp_async4(saddr + RW * 4 * RROW, g);
 		} else {
 			/* touches the end of the file (or of the blob): bytes at and past it read as zero,
 			 * which is the reference's "one zero byte, then nothing" (decode.c:57-61) */
@@ -303,19 +332,45 @@ struct ScanRing {
 				if (c < room16 && at < fe_byte)
 					n = fe_byte - at < 4u ? fe_byte - at : 4u;
 				const void *src = n ? (const void *)(g + 4 * k) : (const void *)base;
-				cp_async4z(sa + 128 * k, src, n);
+				cp_async4z(sa + 4 * RROW * k, src, n);
 				if (k == 0 && (c & (RW / 4 - 1)) == 0)
-					cp_async4z(saddr + RW * 128, src, n);
+					cp_async4z(saddr + RW * 4 * RROW, src, n);
 			}
 		}
 	}
 	/* all lanes together, every SCAN_PERIOD steps */
 	__device__ __forceinline__ void topup(uint32_t P)
 	{
-		const int want = (int)((P >> 7) + LEAD) - (int)fill;
-		const uint32_t f0 = fill;
+		/* last period's register chunks go into the ring (the lane's own column of it) */
+#pragma unroll
+		for (int k = 0; k < NHOLD; k++) {
+			if ((uint32_t)k < hold_n) {
+				const uint32_t c = hold_c0 + k;
+				uint32_t *row = const_cast<uint32_t *>(rw) + (c & (RW / 4 - 1)) * (4u * RROW);
+				row[0] = hold[k].x;
+				row[RROW] = hold[k].y;
+				row[2 * RROW] = hold[k].z;
+				row[3 * RROW] = hold[k].w;
+				if ((c & (RW / 4 - 1)) == 0)
+					const_cast<uint32_t *>(rw)[RW * RROW] = hold[k].x;
+			}
+		}
+		/* after the position has jumped (a block re-walked from global memory), the chunks
+		 * behind it are never read: asking for them would wrap the ring */
+		const uint32_t f0 = fill < (P >> 7) ? (P >> 7) : fill;
+		const int want = (int)((P >> 7) + LEAD) - (int)f0;
+		int nreg = want < NHOLD ? want : NHOLD;
+		const int inside = (int)full16 - (int)f0; /* chunks from f0 that lie entirely inside the stream */
+		nreg = nreg < inside ? nreg : inside;
+		nreg = nreg > 0 ? nreg : 0;
+#pragma unroll
+		for (int k = 0; k < NHOLD; k++)
+			if (k < nreg)
+				hold[k] = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(f0 + k) * 16u));
+		hold_c0 = f0;
+		hold_n = (uint32_t)nreg;
 #pragma unroll 1
-		for (int j = 0; j < want; j++)
+		for (int j = nreg; j < want; j++)
 			request(f0 + j);
 		fill = want > 0 ? f0 + want : f0;
 		cp_async_commit();
@@ -339,19 +394,19 @@ struct ScanRing {
  * trips; measured variants (a register window that keeps the ring fetch off the chain, per-period
  * instead of per-step data checks with rollback) are in profiles/r01_ncu_fast2.md.
  */
-__device__ __forceinline__ void fast_step(Walk &s, uint16_t *&cp, const uint16_t *cpend, uint32_t pblock,
-					  const uint32_t *ringw, uint32_t ready_p, const unsigned char *uni)
+__device__ __forceinline__ void fast_step(Walk &s, uint16_t *&cp, const uint16_t *cpend, uint32_t qblock,
+					  const uint32_t *ring0, uint32_t lane4, uint32_t ready_p,
+					  const unsigned char *uni)
 {
-	const uint32_t *rp = ringw + ((s.P >> 5) & (RW - 1)) * 32u;
-	const uint32_t w = fsr(rp[0], rp[32], s.P);
-	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s, w));
-	const bool have = s.P < ready_p;
+	const uint32_t *rp = ring_word(ring0, lane4, s.Q32);
+	const uint32_t w1 = fsr(rp[0], rp[RROW], s.Q);
+	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s, w1));
+	const bool have = s.Q + 1u <= ready_p;
 	const bool note = have && s.msk == MSK_SEL;
 	/* the store always happens, one past the lane's 128 offsets when there is nothing to note */
-	*(note ? cp : const_cast<uint16_t *>(cpend)) = (uint16_t)(s.P - pblock); /* shared memory: SmemScan::off */
+	*(note ? cp : const_cast<uint16_t *>(cpend)) = (uint16_t)(s.Q - qblock); /* shared memory: SmemScan::off */
 	cp += note ? 1 : 0;
-	const uint32_t ee = have ? e : (s.s8 >> (UNI_PSHIFT - 8u)); /* not landed: advance 0, same page */
-	const bool at_sel = walk_next(s, ee);
+	const bool at_sel = walk_next_if(s, e, have); /* not landed: advance 0, same page */
 	const bool done = at_sel && cp == cpend;
 	s.s8 = done ? UNI_HALT8 : s.s8;
 	s.msk = done ? MSK_K : s.msk;
@@ -747,7 +802,8 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl) + g;
 	uint8_t *const slot_ring = a.ring + (size_t)g * RING_D * REC_BYTES;
 	ScanRing ring;
-	ring.rw = &sm.ring[warp][lane];
+	const uint32_t lane4 = 4u * (uint32_t)(warp * 32 + lane);
+	ring.rw = &sm.ring[0][warp * 32 + lane];
 	ring.saddr = (uint32_t)__cvta_generic_to_shared(ring.rw);
 	ring.idle();
 	bool active = false, exhausted = !enabled;
@@ -832,7 +888,8 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		Rec e;
 		e.pblock = P; e.pend = P; e.desc = cur; e.blk = blk; e.status = SCAN_EOF; e.ncols = 0; e.val = 0; e.pad = 0;
 		Walk s;
-		s.P = P;
+		s.Q = active ? P - 1u : 0u; /* P = 0 is a position like any other (Q wraps); idle lanes: ring rows 0 and 1 (zeros) */
+		s.Q32 = s.Q << 5;
 		s.s8 = UNI_HALT8;
 		s.msk = MSK_K;
 		int mode = 0; /* 0 not walking (any more), 1 block header pending, 2 walking */
@@ -855,17 +912,18 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 #if F2_PROF
 			prof_periods++;
 #endif
-			ring.topup(s.P);
+			ring.topup(s.Q + 1u);
 			if (mode == 1) {
 				/* pwr(4) / val(16): GET_BITS_EXPECT_EOF decode.c:588-589 */
-				if (s.P + 20u > limit) {
+				if (s.Q + 21u > limit) {
 					hdr_eof = true;
 					mode = 0;
-				} else if (s.P < ring.ready_p) {
-					const uint32_t *rp = ring.rw + ((s.P >> 5) & (RW - 1)) * 32u;
-					const uint32_t w = fsr(rp[0], rp[32], s.P);
-					e.val = (int)((w >> 4) & 0xFFFFu);
-					s.P += 20u;
+				} else if (s.Q + 1u <= ring.ready_p) {
+					const uint32_t *rp = ring_word(&sm.ring[0][0], lane4, s.Q32);
+					const uint32_t w1 = fsr(rp[0], rp[RROW], s.Q);
+					e.val = (int)((w1 >> 5) & 0xFFFFu);
+					s.Q += 20u;
+					s.Q32 = s.Q << 5;
 					s.s8 = 0u;
 					s.msk = MSK_SEL;
 					mode = 2;
@@ -874,7 +932,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			PROF_MARK(5); /* 5: top-up + header */
 #pragma unroll 4
 			for (int k = 0; k < SCAN_PERIOD; k++)
-				fast_step(s, cp, cpend, P, ring.rw, ring.ready_p,
+				fast_step(s, cp, cpend, P - 1u, &sm.ring[0][0], lane4, ring.ready_p,
 					  reinterpret_cast<const unsigned char *>(sm.uni16));
 			if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
 				mode = 0;
@@ -883,11 +941,11 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		if (walk) {
 			if (hdr_eof) {
 				e.status = SCAN_EOF;
-			} else if (s.s8 == UNI_HALT8 && s.P <= limit) {
+			} else if (s.s8 == UNI_HALT8 && s.Q + 1u <= limit) {
 				/* 128 columns, every read inside the stream */
 				e.status = SCAN_OK;
 				e.ncols = COLS;
-				e.pend = s.P;
+				e.pend = s.Q + 1u;
 			} else {
 				/* bad selector, or the stream ended inside the block: walk it again with the
 				 * reference's verdicts (rare: at most once per stream) */
@@ -900,9 +958,10 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 				e.ncols = sc.ncols;
 				e.pend = sc.end;
 				e.val = sc.val;
-				s.P = sc.end;
+				s.Q = sc.end - 1u;
+				s.Q32 = s.Q << 5;
 			}
-			P = s.P;
+			P = s.Q + 1u;
 			blk++;
 			if (e.status != SCAN_OK || blk >= n_attempt)
 				e.blk |= 0x80000000u;

@@ -32,25 +32,49 @@ ACM_HD uint32_t fsr(uint32_t lo, uint32_t hi, uint32_t sh)
 constexpr uint32_t UNI_PSHIFT = ACM_UNI_KBITS + 1;
 constexpr uint32_t UNI_HALT8 = (uint32_t)ACM_UNI_HALT << UNI_PSHIFT;
 constexpr uint32_t UNI_BAD8 = (uint32_t)ACM_UNI_BAD << UNI_PSHIFT;
-constexpr uint32_t MSK_SEL = 0x1FFFu, MSK_K = (1u << ACM_UNI_KBITS) - 1u;
+/* index masks, doubled (a table entry is two bytes) */
+constexpr uint32_t MSK_SEL = 0x1FFFu << 1, MSK_K = ((1u << ACM_UNI_KBITS) - 1u) << 1;
 
 /*
- * State of one lane's column walk: P = bit position, s8 = byte offset of the current page in
- * uni16, msk = index mask of that page (13 bits at a selector, ACM_UNI_KBITS inside a
- * prefix-coded column).  One step: w = the 32 stream bits at P; e = uni16 entry at
- * walk_index(s, w); walk_next(s, e).
+ * State of one lane's column walk.  Q = bit position - 1, s8 = byte offset of the current page
+ * in uni16, msk = doubled index mask of that page (13 bits at a selector, ACM_UNI_KBITS inside a
+ * prefix-coded column).  One step: w1 = the 32 stream bits at Q, i.e. the bits at the position
+ * shifted up by one, which is the byte offset of the 16-bit entry once masked; pages are aligned
+ * to their size, so page offset and entry offset combine with an OR (one LOP3 with the mask);
+ * e = the uni16 entry at walk_index(s, w1); walk_next(s, e).
  */
 struct Walk {
-	uint32_t P, s8, msk;
+	uint32_t Q, s8, msk;
+	uint32_t Q32; /* Q << 5, kept alongside (the scan's ring address is a mask of it) */
 };
 
-ACM_HD uint32_t walk_index(const Walk &s, uint32_t w) { return s.s8 + ((w & s.msk) << 1); }
+ACM_HD uint32_t walk_index(const Walk &s, uint32_t w1) { return s.s8 | (w1 & s.msk); }
 
 /* apply entry e; returns true when the lane is at a column selector afterwards */
 ACM_HD bool walk_next(Walk &s, uint32_t e)
 {
-	s.P += e & 0xFFu;
+	s.Q += e & 0xFFu;
+	s.Q32 = s.Q << 5;
 	s.s8 = (e & 0xFF00u) << (UNI_PSHIFT - 8u);
+	const bool at_sel = s.s8 == 0u;
+	s.msk = at_sel ? MSK_SEL : MSK_K;
+	return at_sel;
+}
+
+/* the same for a lane that may have to sit this step out (its bits have not landed): with
+ * go == false nothing moves.  On the device the advance is one dot-product instruction,
+ * Q + byte0(e) * go, which keeps the chain from the table load to the next ring address short. */
+ACM_HD bool walk_next_if(Walk &s, uint32_t e, bool go)
+{
+#if defined(__CUDA_ARCH__)
+	s.Q = __dp4a(e, go ? 1u : 0u, s.Q);
+	s.Q32 = __dp4a(e, go ? 32u : 0u, s.Q32);
+#else
+	s.Q += go ? (e & 0xFFu) : 0u;
+	s.Q32 = s.Q << 5;
+#endif
+	const uint32_t nx = (e & 0xFF00u) << (UNI_PSHIFT - 8u);
+	s.s8 = go ? nx : s.s8;
 	const bool at_sel = s.s8 == 0u;
 	s.msk = at_sel ? MSK_SEL : MSK_K;
 	return at_sel;

@@ -49,16 +49,16 @@ extern "C" long emu_fast2_check(const uint8_t *img, uint32_t len)
 		const ScanResult sc = scan_block(br, P, limit, 128u, 16u, off, P, tab.kind, tab.k8);
 		/* ---- the walk, exactly as fast_step drives it */
 		fast2::Walk s;
-		s.P = P + 20u;
+		s.Q = P + 20u - 1u;
 		s.s8 = 0u;
 		s.msk = fast2::MSK_SEL;
 		uint32_t col = 0, guard = 0;
 		uint16_t woff[129];
 		bool ok_walk = P + 20u <= limit;
 		while (ok_walk && s.s8 != fast2::UNI_HALT8 && s.s8 != fast2::UNI_BAD8 && guard++ < 100000u) {
-			const uint32_t w = br.peek(s.P);
+			const uint32_t w = br.peek(s.Q);
 			if (s.msk == fast2::MSK_SEL)
-				woff[col++] = (uint16_t)(s.P - P);
+				woff[col++] = (uint16_t)(s.Q + 1u - P);
 			const uint32_t e = *reinterpret_cast<const uint16_t *>(
 				reinterpret_cast<const unsigned char *>(tab.uni16) + fast2::walk_index(s, w));
 			const bool at_sel = fast2::walk_next(s, e);
@@ -67,12 +67,12 @@ extern "C" long emu_fast2_check(const uint8_t *img, uint32_t len)
 				s.msk = fast2::MSK_K;
 			}
 		}
-		const bool fast_ok = ok_walk && s.s8 == fast2::UNI_HALT8 && s.P <= limit;
+		const bool fast_ok = ok_walk && s.s8 == fast2::UNI_HALT8 && s.Q + 1u <= limit;
 		if (fast_ok != (sc.status == SCAN_OK))
 			return -(1000L * b + 1);
 		if (!fast_ok)
 			break; /* the kernel re-walks this block with scan_block itself */
-		if (s.P != sc.end)
+		if (s.Q + 1u != sc.end)
 			return -(1000L * b + 2);
 		for (uint32_t c = 0; c < 128; c++)
 			if (woff[c] != off[c])
