@@ -68,7 +68,7 @@ constexpr int BLEN = COLS * ROWS;        /* 2048 */
 #define F2_SW 8        /* scan warps of a scan CTA */
 #endif
 #ifndef F2_RING_D
-#define F2_RING_D 24
+#define F2_RING_D 32
 #endif
 #ifndef F2_RW
 #define F2_RW 64

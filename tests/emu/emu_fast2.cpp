@@ -107,3 +107,64 @@ extern "C" long emu_fast2_check(const uint8_t *img, uint32_t len)
 	}
 	return checked;
 }
+
+/* walk statistics of a level-7 / 16-row image (tuning aid): out[0] blocks, [1] walk steps,
+ * [2] steps that advance more than 31 bits, [3] steps the walk would take if no step could
+ * advance more than 31 bits, [4] columns, [5] selector steps by class: zero, [6] linear, [7] k,
+ * [8] t, [9] total bits */
+extern "C" long emu_fast2_stats(const uint8_t *img, uint32_t len, uint64_t *out)
+{
+	acm_header h;
+	static acm_tables tab;
+	static bool built = false;
+	if (!built) {
+		acm_tables_build(&tab);
+		built = true;
+	}
+	if (acm_parse_header(img, len, 0, &h) < 0 || h.level != 7 || h.rows != 16)
+		return -1;
+	std::vector<uint32_t> words((len + 64) / 4 + 4, 0u);
+	memcpy(words.data(), img, len);
+	BitReader br;
+	const uint32_t file_end = len * 8u, limit = file_end + 8u;
+	br.init(words.data(), file_end);
+	uint32_t P = h.header_len * 8u;
+	const uint32_t nblocks = (h.total_values + 2047u) / 2048u;
+	for (uint32_t b = 0; b < nblocks; b++) {
+		if (P + 20u > limit)
+			break;
+		fast2::Walk s;
+		s.Q = P + 20u - 1u;
+		s.s8 = 0u;
+		s.msk = fast2::MSK_SEL;
+		uint32_t col = 0, guard = 0;
+		while (s.s8 != fast2::UNI_HALT8 && s.s8 != fast2::UNI_BAD8 && guard++ < 100000u) {
+			const uint32_t w = br.peek(s.Q);
+			const bool sel = s.msk == fast2::MSK_SEL;
+			if (sel) {
+				col++;
+				const uint32_t ind = (w >> 1) & 31u, cls = tab.kind[ind] & 7u;
+				out[4]++;
+				out[cls == ACM_CLS_LINEAR ? 6 : cls == ACM_CLS_K ? 7 : cls == ACM_CLS_T ? 8 : 5]++;
+			}
+			const uint32_t e = *reinterpret_cast<const uint16_t *>(
+				reinterpret_cast<const unsigned char *>(tab.uni16) + fast2::walk_index(s, w));
+			const uint32_t q0 = s.Q;
+			const bool at_sel = fast2::walk_next(s, e);
+			const uint32_t adv = s.Q - q0;
+			out[1]++;
+			out[2] += adv > 31u;
+			out[3] += adv > 31u ? (adv + 30u) / 31u : 1u;
+			if (at_sel && col == 128u) {
+				s.s8 = fast2::UNI_HALT8;
+				s.msk = fast2::MSK_K;
+			}
+		}
+		if (s.s8 != fast2::UNI_HALT8 || s.Q + 1u > limit)
+			break;
+		out[9] += s.Q + 1u - P;
+		P = s.Q + 1u;
+		out[0]++;
+	}
+	return 0;
+}
