@@ -44,7 +44,8 @@ def dist_env():
     return rank, world, local
 
 
-def build_corpus(n_streams, rank, threads=None, workload="config2"):
+def corpus_params(n_streams, rank, workload="config2"):
+    """Generator parameters of the synthetic workload (one record per stream)."""
     from libacm_b200 import gen
     rng = np.random.default_rng(1234 + rank)
     if workload == "config4":
@@ -58,7 +59,12 @@ def build_corpus(n_streams, rank, threads=None, workload="config2"):
     plist = [gen.params(level=7, rows=16, channels=ch, rate=22050, total_values=int(t),
                         dist=gen.DIST_FALLOUT, seed=(rank << 32) + 17 * i + 1)
              for i, t in enumerate(tv)]
-    blob, offs, lens = gen.make_batch(plist, threads=threads)
+    return plist
+
+
+def build_corpus(n_streams, rank, threads=None, workload="config2"):
+    from libacm_b200 import gen
+    blob, offs, lens = gen.make_batch(corpus_params(n_streams, rank, workload), threads=threads)
     return blob, offs, lens
 
 

@@ -127,6 +127,21 @@ int acm_gpu_plan_debug_counters(acm_gpu_plan *plan, unsigned long long *out64);
  * slots }; host logic only (tests) */
 void acm_gpu_debug_geometry(uint64_t n, int sms, int max_ctas, uint32_t *out3);
 
+/*
+ * On-GPU corpus generation (test / benchmark input side, not part
+ * of the reference's API).  The reference ships neither an encoder nor sample files; its test
+ * inputs are synthetic (libacm_b200/csrc/acmgen.c).  This runs the same generator one thread per
+ * stream on the device and writes the images into d_blob back-to-back on 16-byte boundaries --
+ * byte-identical to the host generator -- so that a million-stream corpus never crosses PCIe.
+ *   params: n `acmgen_params` (libacm_b200/csrc/acmgen.h) in host memory; level <= 10
+ *   d_blob/cap: device buffer; NULL = sizing call (offs, lens, *used are still filled in)
+ *   offs, lens: host arrays of n entries (placement of every image); *used = bytes of d_blob used
+ *   device: CUDA device ordinal, -1 = current
+ * Returns ACM_OK or ACM_ERR_OTHER (acm_gpu_last_error() has the text).
+ */
+int acm_gpu_generate(const void *params, uint64_t n, void *d_blob, uint64_t cap, uint64_t *offs,
+		     uint32_t *lens, uint64_t *used, int device);
+
 /* acm_gpu_decode_batch keeps its device staging buffers and streams between calls (host-buffer
  * path); this frees them */
 void acm_gpu_release_workspace(void);

@@ -76,6 +76,9 @@ def lib():
         L.acm_gpu_plan_last_ms.restype = C.c_float
         L.acm_gpu_plan_destroy.argtypes = [C.c_void_p]
         L.acm_gpu_plan_destroy.restype = None
+        L.acm_gpu_generate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                       C.POINTER(C.c_uint64), C.c_int]
+        L.acm_gpu_generate.restype = C.c_int
         L.acm_gpu_last_error.restype = C.c_char_p
         L.acm_gpu_abi_version.restype = C.c_int
         _lib = L
@@ -185,6 +188,23 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+def generate_on_device(plist, d_blob_ptr: int | None, cap: int = 0, device: int = -1):
+    """Synthetic corpus generated on the GPU (acm_gpu_generate): plist = libacm_b200.gen.params(...)
+    records.  With d_blob_ptr None the call only sizes the corpus.  Returns (offs uint64[n],
+    lens uint32[n], bytes used); the images are byte-identical to gen.make_batch's."""
+    from . import gen
+    n = len(plist)
+    arr = (gen.GenParams * n)(*plist)
+    offs = np.zeros(n, np.uint64)
+    lens = np.zeros(n, np.uint32)
+    used = C.c_uint64(0)
+    rc = lib().acm_gpu_generate(C.cast(arr, C.c_void_p), n, C.c_void_p(d_blob_ptr) if d_blob_ptr else None, cap,
+                                offs.ctypes.data, lens.ctypes.data, C.byref(used), device)
+    if rc != 0:
+        raise RuntimeError(f"acm_gpu_generate: {rc}: {last_error()}")
+    return offs, lens, int(used.value)
 
 
 def checksum_ref(pcm_bytes: np.ndarray, words: int, wordlen=2, be=0) -> int:

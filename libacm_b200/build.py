@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v",
 ]
-CUDA_SOURCES = ["acm_batch.cu", "acm_kernels.cu", "acm_fast2.cu", "acm_stream.cu"]
+CUDA_SOURCES = ["acm_batch.cu", "acm_kernels.cu", "acm_fast2.cu", "acm_stream.cu", "acm_gen.cu"]
 C_SOURCES = ["acm_tables.c", "acm_hostlogic.cpp"]
 
 
@@ -52,7 +52,7 @@ def _run(cmd, log=None):
 def build_generator(force=False):
     os.makedirs(LIBDIR, exist_ok=True)
     src = os.path.join(CSRC, "acmgen.c")
-    deps = [src, os.path.join(CSRC, "acmgen.h")]
+    deps = [src, os.path.join(CSRC, "acmgen.h"), os.path.join(CSRC, "acmgen_core.h")]
     so = os.path.join(LIBDIR, "libacmgen.so")
     exe = os.path.join(LIBDIR, "acmgen")
     if force or _newer(so, deps):
