@@ -88,6 +88,9 @@ constexpr int RING_D = F2_RING_D;              /* block records a scan lane may 
 constexpr int REC_BYTES = 288;           /* 128 x u16 column offsets + 32-byte Rec */
 constexpr int RW = F2_RW;               /* ring words per scan lane (+1 duplicate of word 0) */
 constexpr int RROW = 32 * SW;            /* words per ring row: one word of every scan lane of the CTA */
+#ifndef F2_PRED_NOTE
+#define F2_PRED_NOTE 1
+#endif
 #ifndef F2_NHOLD
 #define F2_NHOLD 2
 #endif
@@ -394,7 +397,7 @@ struct ScanRing {
  * trips; measured variants (a register window that keeps the ring fetch off the chain, per-period
  * instead of per-step data checks with rollback) are in profiles/r01_ncu_fast2.md.
  */
-__device__ __forceinline__ void fast_step(Walk &s, uint16_t *&cp, const uint16_t *cpend, uint32_t qblock,
+__device__ __forceinline__ void fast_step(Walk &s, uint32_t &cp, uint32_t cpend, uint32_t qblock,
 					  const uint32_t *ring0, uint32_t lane4, uint32_t ready_p,
 					  const unsigned char *uni)
 {
@@ -403,9 +406,15 @@ __device__ __forceinline__ void fast_step(Walk &s, uint16_t *&cp, const uint16_t
 	const uint32_t e = *reinterpret_cast<const uint16_t *>(uni + walk_index(s, w1));
 	const bool have = s.Q + 1u <= ready_p;
 	const bool note = have && s.msk == MSK_SEL;
-	/* the store always happens, one past the lane's 128 offsets when there is nothing to note */
-	*(note ? cp : const_cast<uint16_t *>(cpend)) = (uint16_t)(s.Q - qblock); /* shared memory: SmemScan::off */
-	cp += note ? 1 : 0;
+#if F2_PRED_NOTE
+	/* SmemScan::off (cp = shared-space address): a predicated store, not a branch; lanes that are
+	 * not at a selector (two steps in three) stay out of the load/store pipe */
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t}"
+		     :: "r"(cp), "h"((unsigned short)(s.Q - qblock)), "r"((uint32_t)note) : "memory");
+#else
+	asm volatile("st.shared.u16 [%0], %1;" :: "r"(note ? cp : cpend), "h"((unsigned short)(s.Q - qblock)) : "memory");
+#endif
+	cp += note ? 2u : 0u;
 	const bool at_sel = walk_next_if(s, e, have); /* not landed: advance 0, same page */
 	const bool done = at_sel && cp == cpend;
 	s.s8 = done ? UNI_HALT8 : s.s8;
@@ -904,8 +913,8 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			}
 		}
 		uint16_t *const off0 = reinterpret_cast<uint16_t *>(&sm.off[warp][lane * OFFP]);
-		uint16_t *cp = off0;
-		const uint16_t *const cpend = off0 + COLS;
+		uint32_t cp = (uint32_t)__cvta_generic_to_shared(off0); /* shared-space address of the next offset to note */
+		const uint32_t cpend = cp + 2u * COLS;
 		bool hdr_eof = false;
 		while (__any_sync(0xFFFFFFFFu, mode != 0)) {
 			PROF_MARK(4); /* 4: walk steps */
