@@ -10,20 +10,27 @@
  *
  *  - SCAN CTAs (the first n_scan of the grid, one per SM, nothing else on that SM) walk column
  *    LENGTHS only, one stream per lane (SW warps x 32 stream slots per CTA).  A step is: fetch
- *    the 32 bits at bit position P from the lane's shared-memory ring (two conflict-free LDS +
- *    one funnel shift), ONE table lookup (uni16: the whole walk as a state machine -- page 0 is
- *    "at a column selector", indexed by selector + first payload byte; page (type, rows to come)
- *    is "inside a prefix-coded column"; an entry is bits-to-advance | next page), P += advance.
- *    No branches on the data: the 32 lanes run one instruction stream however their column
- *    types differ, finished and idle lanes sit on a HALT page.  A warp issues in order and the
- *    walk is one dependent chain, so a step costs ~4 cycles per instruction plus two shared-
- *    memory latencies; sharing an SM with decode warps doubled that (measured), hence the
- *    dedicated SMs.  The ring (64 words per lane, word-interleaved across lanes) is filled with
- *    4-byte cp.async copies issued for all lanes together every SCAN_PERIOD steps and awaited
- *    one period later; the end-of-file rule (one zero byte, decode.c:57-61) is the zero-fill
- *    of cp.async's src-size operand.  End-of-file verdicts are not part of the walk: a block
- *    whose walk ends inside the stream cannot have read past its end; the rare other block is
- *    re-walked with the reference's verdicts (scan_block).
+ *    32 stream bits from the lane's shared-memory ring (two conflict-free LDS + one funnel
+ *    shift), ONE table lookup (uni16: the whole walk as a state machine -- page 0 is "at a column
+ *    selector", indexed by selector + first payload byte; page (type, rows to come) is "inside
+ *    a prefix-coded column"; an entry is bits-to-advance | next page), position += advance, and
+ *    at a selector a predicated 2-byte store of the column's offset.  No branches on the data:
+ *    the 32 lanes run one instruction stream however their column types differ, finished and
+ *    idle lanes sit on a HALT page.  A warp issues in order and the walk is one dependent
+ *    chain: table LDS -> dp4a (position += advance byte) -> LOP3 (ring address) -> ring LDS ->
+ *    funnel shift -> LOP3 (table address).  To get there the lane keeps Q = position - 1 (the
+ *    32 bits at Q, masked, are the index already doubled for 16-bit entries, and page | index
+ *    is the same LOP3), 32 * Q alongside it (the ring row is a mask of it), and the ring is laid
+ *    out [word][warp][lane] with power-of-two rows.  Beyond the chain the step time is queueing
+ *    in the SM's load/store pipe: sharing an SM with decode warps doubled it (measured), hence
+ *    the dedicated SMs, and anything that keeps lanes out of that pipe pays.  The ring (64
+ *    words per lane) is topped up for all lanes together every SCAN_PERIOD steps, LEAD chunks
+ *    of 16 bytes ahead of the position: two chunks per lane as 16-byte loads into registers
+ *    (stored to the ring at the next top-up), bursts beyond that as 4-byte cp.async copies whose
+ *    src-size zero-fill is the end-of-file rule (one zero byte, decode.c:57-61).  End-of-file
+ *    verdicts are not part of the walk: a block whose walk ends inside the stream cannot have
+ *    read past its end; the rare other block is re-walked with the reference's verdicts
+ *    (scan_block).
  *  - Every walked block becomes a 288-byte RECORD (128 column offsets + header facts) in a
  *    per-slot ring of RING_D records in global memory (L2 resident), announced through a
  *    per-slot counter.  Scan lanes run up to RING_D blocks ahead of the decode.
