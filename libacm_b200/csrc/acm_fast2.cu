@@ -1222,6 +1222,12 @@ void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uin
 	uint32_t nw = want_work < cap_work ? (uint32_t)want_work : cap_work;
 	if (nw < 1)
 		nw = 1;
+	/* decode CTA w owns the slots w, w + nw, w + 2 nw, ..., and the host deals the longest streams
+	 * of a batch to lane 0 of every scan warp (slots 0, 32, 64, ...): with an even nw those land on
+	 * nw / gcd(32, nw) decode CTAs only (measured: 112 decode CTAs, 7 of them busy to the end, +25 %).
+	 * An odd nw spreads them over all decode CTAs; the odd CTA out stays unused. */
+	if (nw > 1 && (nw & 1u) == 0u)
+		nw -= 1;
 	if (slots > (uint64_t)nw * fast2::MAXOWN)
 		slots = (uint64_t)nw * fast2::MAXOWN;
 	*n_scan = ns;

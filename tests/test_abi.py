@@ -57,5 +57,6 @@ def test_fast_kernel_geometry_rules():
                 assert 32 <= n_slots <= n_scan * 256 and n_slots % 32 == 0
                 assert n_slots <= n_work * 128            # MAXOWN slots per decode CTA
                 assert n_slots <= (n + 31) // 32 * 32      # never more slots than streams (whole warps)
+                assert n_work == 1 or n_work % 2 == 1      # slots 0, 32, 64, .. (the longest streams) spread over all owners
     lib.acm_gpu_debug_geometry(10_000, 148, 148, out)
     assert tuple(out) == (33, 115, 8448)                  # the bench's full-batch launch
