@@ -30,6 +30,8 @@ def lib():
                                     C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         _lib.emu_fast2_check.argtypes = [C.c_void_p, C.c_uint32]
         _lib.emu_fast2_check.restype = C.c_long
+        _lib.emu_fast2_stats.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        _lib.emu_fast2_stats.restype = C.c_long
     return _lib
 
 
@@ -39,6 +41,18 @@ def fast2_check(img):
     building blocks.  Returns the number of blocks checked (negative: first difference)."""
     raw = np.frombuffer(bytes(img), np.uint8).copy()
     return lib().emu_fast2_check(raw.ctypes.data, raw.size)
+
+
+def fast2_stats(images):
+    """Walk statistics of level-7 / 16-row images (tests/emu/emu_fast2.cpp::emu_fast2_stats): dict with
+    blocks, steps, big_steps (> 31 bits in one step), capped_steps (if no step could advance more than
+    31 bits), columns, zero / linear / k / t columns, bits."""
+    out = np.zeros(16, np.uint64)
+    for img in images:
+        raw = np.frombuffer(bytes(img), np.uint8).copy()
+        lib().emu_fast2_stats(raw.ctypes.data, raw.size, out.ctypes.data)
+    names = ("blocks", "steps", "big_steps", "capped_steps", "columns", "zero", "linear", "k", "t", "bits")
+    return {n: int(out[i]) for i, n in enumerate(names)}
 
 
 def decode(img, be=0, sgned=1, wordlen=2, force_chans=0, lead=0, nthreads=64, trail_fill=0xFF):

@@ -93,3 +93,18 @@ def test_fast2_core_on_garbage_payloads():
         assert n >= 0, (k, n)
         clean += n
     assert clean > 20
+
+
+def test_fast2_walk_statistics_of_the_bench_corpus():
+    """The numbers DESIGN.md / profiles quote for the walk on Fallout-style streams: about 397 table
+    steps and 7.1 kbit per block, 128 columns of which about 32 linear, 30 radix-coded, 60 prefix-coded;
+    one step in six advances more than 31 bits (whole linear / radix columns)."""
+    st = emu.fast2_stats(corpus.images(corpus.fallout_params(12, seed=3, lo=20_000, hi=120_000)))
+    b = st["blocks"]
+    assert b > 300 and st["columns"] == 128 * b
+    assert st["zero"] + st["linear"] + st["k"] + st["t"] == st["columns"]
+    assert 380 < st["steps"] / b < 415
+    assert 6800 < st["bits"] / b < 7500
+    assert st["linear"] == 32 * b and 25 < st["t"] / b < 35
+    assert st["big_steps"] == st["linear"] + st["t"]
+    assert st["capped_steps"] > 1.2 * st["steps"]
