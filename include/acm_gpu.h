@@ -120,8 +120,10 @@ void acm_gpu_plan_split(const acm_gpu_plan *plan, uint64_t *n_fast, uint64_t *n_
 /* average device time of the kernels of the last run on that plan, ms (CUDA events on cuda_stream) */
 float acm_gpu_plan_last_ms(acm_gpu_plan *plan);
 void acm_gpu_plan_destroy(acm_gpu_plan *plan);
-/* tuning builds (-DF2_PROF, tools/build_variants.py): copies the 64 in-kernel cycle counters the
- * kernels accumulated over this plan's runs; all zero in a normal build */
+/* copies the plan's 64 in-kernel counters, accumulated over its runs.  Always counted: [32] = blocks
+ * the level-7 / 16-row kernel had to re-walk with the generic block scan (bad selector, end of a
+ * truncated stream; never for a healthy stream).  The cycle counters [0..19] are those of tuning
+ * builds (-DF2_PROF, tools/build_variants.py) and stay zero in a normal build */
 int acm_gpu_plan_debug_counters(acm_gpu_plan *plan, unsigned long long *out64);
 /* grid geometry of the level-7 / 16-row kernel for n streams: out3 = { scan CTAs, decode CTAs, stream
  * slots }; host logic only (tests) */

@@ -178,6 +178,15 @@ class Plan:
     def last_ms(self) -> float:
         return lib().acm_gpu_plan_last_ms(self._h)
 
+    def counters(self) -> np.ndarray:
+        """The plan's 64 in-kernel counters (acm_gpu_plan_debug_counters)."""
+        buf = np.zeros(64, np.uint64)
+        lib().acm_gpu_plan_debug_counters.argtypes = [C.c_void_p, C.c_void_p]
+        lib().acm_gpu_plan_debug_counters.restype = C.c_int
+        if lib().acm_gpu_plan_debug_counters(self._h, buf.ctypes.data) < 0:
+            raise AcmGpuError(f"acm_gpu_plan_debug_counters: {last_error()}")
+        return buf
+
     def close(self):
         if self._h:
             lib().acm_gpu_plan_destroy(self._h)

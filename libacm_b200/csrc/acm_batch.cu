@@ -644,7 +644,8 @@ extern "C" void acm_gpu_debug_geometry(uint64_t n, int sms, int max_ctas, uint32
 	fast2_geometry(n, sms, max_ctas, &out3[0], &out3[1], &out3[2]);
 }
 
-/* tuning builds (-DF2_PROF): the 64 in-kernel cycle counters, accumulated over the plan's runs */
+/* the plan's 64 in-kernel counters, accumulated over its runs ([32]: blocks re-walked by the generic scan,
+ * always counted; the cycle counters of -DF2_PROF tuning builds are zero otherwise) */
 extern "C" int acm_gpu_plan_debug_counters(acm_gpu_plan *p, unsigned long long *out64)
 {
 	if (!p || !p->d_prof)

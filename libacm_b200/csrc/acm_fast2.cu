@@ -967,6 +967,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 				 * reference's verdicts (rare: at most once per stream) */
 				const DevStream d = a.streams[cur];
 				BitReader br;
+				atomicAdd(a.prof + 32, 1ull); /* always counted (tests: a healthy stream never gets here) */
 				br.init(reinterpret_cast<const uint32_t *>(a.blob + d.base_off), d.file_end);
 				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS, off0, P,
 								 a.tables->kind, a.tables->k8);

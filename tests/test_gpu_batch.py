@@ -263,3 +263,38 @@ def test_garbage_payloads_status_and_words(checker, kernel):
         assert (int(s["status"][i]), int(s["words"][i])) == (a.status, a.words), (i, k)
         seen.add(a.status)
     assert {-6, 0} <= seen
+
+
+def test_healthy_streams_never_take_the_re_walk_path(checker):
+    """Every byte alignment of the stream start (position 0 of a 16-byte chunk included): the table
+    walk alone must carry a healthy stream.  The re-walk by the generic block scan is for bad selectors
+    and truncated streams; a walk that silently leans on it is slow, not wrong, so parity cannot see it."""
+    import torch
+    imgs = corpus.images(corpus.fallout_params(48, seed=21, lo=8_000, hi=40_000))
+    for lead in range(16):
+        blob, offs, lens = gu.pack(imgs, 1, lead)
+        opts = api.make_opts(device=0, want_checksums=1)
+        d_blob = torch.from_numpy(blob).cuda()
+        s = api.new_streams(offs, lens)
+        api.probe(d_blob, s, opts)
+        d_out = torch.empty(api.layout(s, 2) + 16, dtype=torch.uint8, device="cuda")
+        plan = api.Plan(s, opts)
+        plan.run(d_blob, d_out, torch.cuda.current_stream().cuda_stream)
+        plan.fetch(s, torch.cuda.current_stream().cuda_stream)
+        rewalked = int(plan.counters()[32])
+        plan.close()
+        assert set(s["status"].tolist()) == {0}
+        assert rewalked == 0, (lead, rewalked)
+    assert gu.compare(imgs, s, d_out.cpu().numpy(), checker, checksums=True) == []
+    # and it does count: a truncated stream ends in a re-walk
+    cut = [bytes(imgs[0])[: len(imgs[0]) * 2 // 3]]
+    blob, offs, lens = gu.pack(cut, 16, 0)
+    d_blob = torch.from_numpy(blob).cuda()
+    s = api.new_streams(offs, lens)
+    api.probe(d_blob, s, opts)
+    d_out = torch.empty(api.layout(s, 2) + 16, dtype=torch.uint8, device="cuda")
+    plan = api.Plan(s, opts)
+    plan.run(d_blob, d_out, torch.cuda.current_stream().cuda_stream)
+    plan.fetch(s, torch.cuda.current_stream().cuda_stream)
+    assert int(plan.counters()[32]) == 1
+    plan.close()
