@@ -10,6 +10,10 @@
 
 #include "acm_device.cuh"
 
+#ifndef F2_NIB_ALU
+#define F2_NIB_ALU 1   /* nibbles -> int16 pairs by arithmetic (0: nib2w table in shared memory) */
+#endif
+
 namespace acm {
 namespace fast2 {
 
@@ -96,11 +100,26 @@ ACM_HD void store8(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 #endif
 }
 
+/* two 4-bit two's-complement values in a byte -> two int16 in a word, without a table: spread the
+ * nibbles to bits 0-3 and 16-19 (x 0x1001, mask), then fill bits 4-15 / 20-31 of each half from
+ * its sign bit (0x0008 x 0x1FFE = 0xFFF0; the two products cannot meet) */
+ACM_HD uint32_t nib2w_alu(uint32_t byte)
+{
+	const uint32_t x = (byte * 0x1001u) & 0x000F000Fu;
+	return (x & 0x00080008u) * 0x1FFEu + x;
+}
+
 /* 16 nibbles (a0: rows 0-7, a1: rows 8-15) -> sixteen int16 */
 ACM_HD void store_nibbles(uint32_t a0, uint32_t a1, const ColOut &o, const uint32_t *nib2w)
 {
+#if F2_NIB_ALU
+	(void)nib2w;
+	store8(o.h0, nib2w_alu(a0 & 255u), nib2w_alu((a0 >> 8) & 255u), nib2w_alu((a0 >> 16) & 255u), nib2w_alu(a0 >> 24));
+	store8(o.h1, nib2w_alu(a1 & 255u), nib2w_alu((a1 >> 8) & 255u), nib2w_alu((a1 >> 16) & 255u), nib2w_alu(a1 >> 24));
+#else
 	store8(o.h0, nib2w[a0 & 255u], nib2w[(a0 >> 8) & 255u], nib2w[(a0 >> 16) & 255u], nib2w[a0 >> 24]);
 	store8(o.h1, nib2w[a1 & 255u], nib2w[(a1 >> 8) & 255u], nib2w[(a1 >> 16) & 255u], nib2w[a1 >> 24]);
+#endif
 }
 
 /*
