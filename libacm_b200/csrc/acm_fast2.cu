@@ -98,6 +98,9 @@ constexpr int RROW = 32 * SW;            /* words per ring row: one word of ever
 #ifndef F2_PRED_NOTE
 #define F2_PRED_NOTE 1
 #endif
+#ifndef F2_CARRY
+#define F2_CARRY 1
+#endif
 #ifndef F2_NHOLD
 #define F2_NHOLD 2
 #endif
@@ -563,6 +566,22 @@ juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint
 		A4[j] = 0u;
 	A5[0] = A5[1] = A5[2] = A5[3] = 0u;
 	A6[0] = A6[1] = 0u;
+#if F2_CARRY >= 1
+	uint32_t P1[16]; /* the inputs of piece k - 1 */
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const uint4 v = reinterpret_cast<const uint4 *>(win + 16)[q];
+		P1[4 * q] = v.x; P1[4 * q + 1] = v.y; P1[4 * q + 2] = v.z; P1[4 * q + 3] = v.w;
+	}
+#endif
+#if F2_CARRY >= 2
+	uint32_t P2[16]; /* the inputs of piece k - 2 */
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const uint4 v = reinterpret_cast<const uint4 *>(win)[q];
+		P2[4 * q] = v.x; P2[4 * q + 1] = v.y; P2[4 * q + 2] = v.z; P2[4 * q + 3] = v.w;
+	}
+#endif
 #pragma unroll 1
 	for (int k = 2; k < 8; k++) {
 		/* word t of the window lives at t + (t >= 64 ? 4 : 0) */
@@ -573,7 +592,22 @@ juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint
 		uint32_t a3[16];
 #pragma unroll
 		for (int q = 0; q < 4; q++) {
+#if F2_CARRY >= 2
+			const uint4 c0 = p0[q];
+			const uint4 c1 = make_uint4(P1[4 * q], P1[4 * q + 1], P1[4 * q + 2], P1[4 * q + 3]);
+			const uint4 c2 = make_uint4(P2[4 * q], P2[4 * q + 1], P2[4 * q + 2], P2[4 * q + 3]);
+			P2[4 * q] = c1.x; P2[4 * q + 1] = c1.y; P2[4 * q + 2] = c1.z; P2[4 * q + 3] = c1.w;
+			P1[4 * q] = c0.x; P1[4 * q + 1] = c0.y; P1[4 * q + 2] = c0.z; P1[4 * q + 3] = c0.w;
+#elif F2_CARRY == 1
+			/* the piece before this one was this loop's c0 a turn ago: kept in registers, one
+			 * 128-bit shared-memory load less per four words (these loads are a fifth of the
+			 * kernel's shared-memory traffic) */
+			const uint4 c0 = p0[q], c2 = p2[q];
+			const uint4 c1 = make_uint4(P1[4 * q], P1[4 * q + 1], P1[4 * q + 2], P1[4 * q + 3]);
+			P1[4 * q] = c0.x; P1[4 * q + 1] = c0.y; P1[4 * q + 2] = c0.z; P1[4 * q + 3] = c0.w;
+#else
 			const uint4 c0 = p0[q], c1 = p1[q], c2 = p2[q];
+#endif
 			/* C = 16 (decode.c:518-519): 2*in[t-16] +- (in[t] + in[t-32]) */
 			a3[4 * q + 0] = 2u * c1.x + sgn * (c0.x + c2.x);
 			a3[4 * q + 1] = 2u * c1.y + sgn * (c0.y + c2.y);
