@@ -121,6 +121,8 @@ constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [1
 constexpr int KMAX = F2_KMAX;            /* blocks a worker decodes per slot claim */
 
 static_assert(WB_WORDS >= XWORDS, "transform layout must fit the worker buffer");
+static_assert((RW & (RW - 1)) == 0 && RW % 4 == 0, "the scan ring is a power of two of words, whole 16-byte chunks");
+static_assert(LEAD + 2 <= RW / 4, "the chunk being read and the one after it are never re-requested");
 static_assert(SW <= W, "scan CTAs are launched with the decode CTAs' thread count");
 
 
