@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define ACM_GPU_ABI_VERSION 1
+#define ACM_GPU_ABI_VERSION 2
 
 typedef struct acm_gpu_stream {
 	/* ---- caller fills */
@@ -63,7 +63,11 @@ typedef struct acm_gpu_opts {
 	int32_t want_checksums; /* compute acm_gpu_stream.checksum on the device */
 	int32_t pad_tail;       /* zero-fill words [words, total_values) of every stream */
 	int32_t kernel;         /* 0 auto; 1 force the generic kernel (testing) */
-	int32_t reserved[8];
+	uint32_t device_mask;   /* acm_gpu_decode_batch only: bit d = use CUDA device d.  More than one
+				   bit shards the batch by stream over those GPUs (contiguous ranges of the
+				   stream array with equal shares of the output, one host thread per GPU, no
+				   collective: the streams are independent); host buffers only.  0 = `device` */
+	int32_t reserved[7];
 } acm_gpu_opts;
 
 typedef struct acm_gpu_batch {
@@ -109,7 +113,9 @@ typedef struct acm_gpu_plan acm_gpu_plan;
 
 acm_gpu_plan *acm_gpu_plan_create(const acm_gpu_stream *streams, uint64_t n,
 				  const acm_gpu_opts *opts, int *err);
-/* asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream) */
+/* asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream).  d_out must hold the
+ * acm_gpu_layout() byte count: every stream's slot ends on a 16-byte boundary and is written
+ * (PCM, then zeros) up to there */
 int acm_gpu_plan_run(acm_gpu_plan *plan, const void *d_blob, void *d_out, void *cuda_stream);
 /* waits for cuda_stream and copies status / words / checksum into streams[] */
 int acm_gpu_plan_fetch(acm_gpu_plan *plan, acm_gpu_stream *streams, void *cuda_stream);

@@ -1,4 +1,28 @@
 /*
+ * libacm - Interplay ACM audio decoder.
+ *
+ * Copyright (c) 2004-2010, Marko Kreen
+ *
+ * Permission to use, copy, modify, and/or distribute this software for any
+ * purpose with or without fee is hereby granted, provided that the above
+ * copyright notice and this permission notice appear in all copies.
+ *
+ * THE SOFTWARE IS PROVIDED "AS IS" AND THE AUTHOR DISCLAIMS ALL WARRANTIES
+ * WITH REGARD TO THIS SOFTWARE INCLUDING ALL IMPLIED WARRANTIES OF
+ * MERCHANTABILITY AND FITNESS. IN NO EVENT SHALL THE AUTHOR BE LIABLE FOR
+ * ANY SPECIAL, DIRECT, INDIRECT, OR CONSEQUENTIAL DAMAGES OR ANY DAMAGES
+ * WHATSOEVER RESULTING FROM LOSS OF USE, DATA OR PROFITS, WHETHER IN AN
+ * ACTION OF CONTRACT, NEGLIGENCE OR OTHER TORTIOUS ACTION, ARISING OUT OF
+ * OR IN CONNECTION WITH THE USE OR PERFORMANCE OF THIS SOFTWARE.
+ */
+
+/*
+ * The declarations below reproduce the public interface of libacm 1.3
+ * (constants, ACMInfo, acm_io_callbacks, struct ACMStream and the prototypes of
+ * reference src/libacm.h:26-170), which is why the ISC notice above is kept.
+ */
+
+/*
  * libacm.h -- drop-in C surface of the B200 ACM decoder.
  *
  * Source- and ABI-compatible with markokr/libacm 1.3's public header

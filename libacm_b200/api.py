@@ -32,7 +32,8 @@ assert STREAM_DTYPE.itemsize == 72
 class Opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("bigendianp", C.c_int32), ("wordlen", C.c_int32),
                 ("sgned", C.c_int32), ("force_chans", C.c_int32), ("want_checksums", C.c_int32),
-                ("pad_tail", C.c_int32), ("kernel", C.c_int32), ("reserved", C.c_int32 * 8)]
+                ("pad_tail", C.c_int32), ("kernel", C.c_int32), ("device_mask", C.c_uint32),
+                ("reserved", C.c_int32 * 7)]
 
 
 class Batch(C.Structure):
@@ -94,11 +95,12 @@ class AcmGpuError(RuntimeError):
 
 
 def make_opts(device=-1, bigendianp=0, wordlen=2, sgned=1, force_chans=0, want_checksums=0,
-              pad_tail=1, kernel=0) -> Opts:
+              pad_tail=1, kernel=0, device_mask=0) -> Opts:
     o = Opts()
     lib().acm_gpu_opts_init(C.byref(o))
     o.device, o.bigendianp, o.wordlen, o.sgned = device, bigendianp, wordlen, sgned
     o.force_chans, o.want_checksums, o.pad_tail, o.kernel = force_chans, want_checksums, pad_tail, kernel
+    o.device_mask = device_mask
     return o
 
 

@@ -12,6 +12,8 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -174,6 +176,7 @@ struct Segment {
 	size_t ring_off;                  /* block-record rings of the fast kernel (offset in bytes) */
 	size_t ctl_off;                   /* slot control words (offset in bytes) */
 	uint32_t n_scan, n_slots;         /* fast kernel geometry: scan CTAs, slots in use */
+	bool sparse;                      /* the kernels do not write every byte of [out_lo, out_hi) */
 };
 
 struct acm_gpu_plan {
@@ -323,10 +326,12 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	}
 	for (Segment &sg : p->seg) {
 		std::vector<DevStream> fast, gen;
+		uint64_t slot_bytes = 0;
 		sg.blob_lo = sg.out_lo = ~(uint64_t)0;
+		sg.sparse = !opts->pad_tail;
 		for (uint64_t i = sg.s_first; i < sg.s_first + sg.s_count; i++) {
 			const acm_gpu_stream &g = s[i];
-			if (g.status == 0 && (g.out_off & 15u)) {
+			if (acm_stream_accepted(&g) && (g.out_off & 15u)) {
 				acm_set_error("stream %llu: out_off must be a multiple of 16", (unsigned long long)i);
 				goto fail;
 			}
@@ -334,6 +339,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			int hs = acm_make_devstream(&g, (uint32_t)i, opts->pad_tail, &d);
 			if (hs < 0) {
 				p->host_status[i] = hs;
+				if (g.total_values)
+					sg.sparse = true; /* a refused stream's slot stays unwritten */
 				continue;
 			}
 			uint32_t blen = g.rows << g.level;
@@ -344,6 +351,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			sg.blob_hi = std::max(sg.blob_hi, in_hi);
 			sg.out_lo = std::min(sg.out_lo, g.out_off);
 			sg.out_hi = std::max(sg.out_hi, o_hi);
+			slot_bytes += o_hi - g.out_off;
 			if (opts->kernel != 1 && fast_eligible(g, opts)) {
 				fast.push_back(d);
 			} else {
@@ -356,6 +364,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			sg.blob_lo = sg.blob_hi = 0;
 		if (sg.out_lo > sg.out_hi)
 			sg.out_lo = sg.out_hi = 0;
+		if (slot_bytes != sg.out_hi - sg.out_lo)
+			sg.sparse = true; /* gaps (or overlaps) in a caller-chosen layout */
 		/* longest first: the work queues hand out streams in this order (LPT) */
 		auto by_len = [](const DevStream &a, const DevStream &b) {
 			if (a.n_attempt != b.n_attempt)
@@ -487,6 +497,10 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		CU(cudaMemset(base + o_results, 0, (n + 1) * 16));
 		CU(cudaMemset(p->d_prof, 0, 64 * sizeof(unsigned long long)));
 		CU(cudaMemcpy(p->d_tables, host_tables(), sizeof(acm_tables), cudaMemcpyHostToDevice));
+		/* the kernels run on non-blocking streams (or the caller's), which do not wait for the
+		 * legacy default stream: the descriptor / table uploads and the memsets above must have
+		 * landed before this function returns (a pageable cudaMemcpy may return before its DMA) */
+		CU(cudaStreamSynchronize(cudaStreamLegacy));
 	}
 	if (err_out)
 		*err_out = ACM_OK;
@@ -669,8 +683,11 @@ struct Workspace {
 	cudaStream_t s_k[MAX_SEG] = {};
 	DevArena arena; /* the plans' descriptor tables, rings, history */
 };
-std::mutex g_ws_mutex;
-Workspace g_ws[16];
+/* one workspace and one lock per device: callers on different GPUs never wait for each other;
+ * two callers on the same GPU take turns (they would share its copy engines anyway) */
+constexpr int MAX_DEV = 64;
+std::mutex g_ws_mutex[MAX_DEV];
+Workspace g_ws[MAX_DEV];
 
 int ws_reserve(Workspace &w, size_t blob_bytes, size_t out_bytes)
 {
@@ -703,10 +720,10 @@ fail:
 
 extern "C" void acm_gpu_release_workspace(void)
 {
-	std::lock_guard<std::mutex> lock(g_ws_mutex);
 	int cur = 0;
 	cudaGetDevice(&cur);
-	for (int d = 0; d < 16; d++) {
+	for (int d = 0; d < MAX_DEV; d++) {
+		std::lock_guard<std::mutex> lock(g_ws_mutex[d]);
 		Workspace &w = g_ws[d];
 		if (!w.s_in && !w.d_blob && !w.d_out && !w.arena.base)
 			continue;
@@ -774,6 +791,11 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 		}
 		CUR(cudaEventRecord(ev_in[g], w.s_in));
 		CUR(cudaStreamWaitEvent(sk, ev_in[g], 0));
+		/* the PCM staging buffer is reused between calls: where the kernels will not write every
+		 * byte of the segment's range (streams refused on the host, no tail padding, gaps in a
+		 * caller-chosen layout) it is cleared first, so that no stale byte reaches the caller */
+		if (!b->out_on_device && sg.out_hi > sg.out_lo && sg.sparse)
+			CUR(cudaMemsetAsync(w.d_out + sg.out_lo, 0, sg.out_hi - sg.out_lo, sk));
 		if (plan_run_segment(plan, g, blob_dev, out_dev, sk) < 0)
 			return ACM_ERR_OTHER;
 		CUR(cudaEventRecord(ev_k[g], sk));
@@ -793,36 +815,28 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 	return ACM_OK;
 }
 
-extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *opts)
+static int decode_batch_one_device(const acm_gpu_batch *b, const acm_gpu_opts *opts)
 {
-	acm_gpu_opts defaults;
 	acm_gpu_plan *plan = nullptr;
 	std::vector<cudaEvent_t> ev_in, ev_k;
 	int err = ACM_ERR_OTHER, perr = 0, dev = 0;
 	bool need_probe = false, host_io, monotonic = true;
 	unsigned nseg = 1;
 
-	g_err[0] = 0;
-	if (!b || (!b->streams && b->n)) {
-		acm_set_error("acm_gpu_decode_batch: null batch");
-		return ACM_ERR_OTHER;
-	}
-	if (!opts) {
-		acm_gpu_opts_init(&defaults);
-		opts = &defaults;
-	}
 	if (use_device(opts) < 0)
 		return ACM_ERR_OTHER;
 	for (uint64_t i = 0; i < b->n; i++)
-		if (b->streams[i].rows == 0 && b->streams[i].status == 0)
-			need_probe = true;
+		if (b->streams[i].rows == 0 && b->streams[i].total_values == 0 && b->streams[i].status == 0)
+			need_probe = true; /* never probed (a rejected header keeps its ACM_ERR_NOT_ACM) */
 	if (need_probe &&
 	    acm_gpu_probe(b->blob, b->blob_len, b->blob_on_device, b->streams, b->n, opts) < 0)
 		return ACM_ERR_OTHER;
 	for (uint64_t i = 0; i < b->n; i++) {
 		const acm_gpu_stream &g = b->streams[i];
-		uint64_t need = g.out_off + (uint64_t)g.total_values * (uint64_t)opts->wordlen;
-		if (g.status == 0 && (need > b->out_len || g.in_off + g.in_len > b->blob_len)) {
+		/* a stream's slot ends at the next 16-byte boundary: the kernels zero-fill up to there, so
+		 * that is what `out` has to hold (acm_gpu_layout's figure) */
+		uint64_t need = g.out_off + (((uint64_t)g.total_values * (uint64_t)opts->wordlen + 15u) & ~(uint64_t)15u);
+		if (acm_stream_accepted(&g) && (need > b->out_len || g.in_off + g.in_len > b->blob_len)) {
 			acm_set_error("stream %llu does not fit its blob/out range", (unsigned long long)i);
 			return ACM_ERR_OTHER;
 		}
@@ -834,13 +848,13 @@ extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *
 	 * caller's order is also the byte order of blob and out (acm_gpu_layout's order) */
 	if (host_io && monotonic && b->out_len >= ((uint64_t)32 << 20) && b->n >= 64)
 		nseg = MAX_SEG;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEV) {
+		acm_set_error("cudaGetDevice failed (or device ordinal >= %d)", MAX_DEV);
+		return ACM_ERR_OTHER;
+	}
 	{
-		std::lock_guard<std::mutex> lock(g_ws_mutex);
-		if (cudaGetDevice(&dev) != cudaSuccess) {
-			acm_set_error("cudaGetDevice failed");
-			return ACM_ERR_OTHER;
-		}
-		Workspace &w = g_ws[dev & 15];
+		std::lock_guard<std::mutex> lock(g_ws_mutex[dev]);
+		Workspace &w = g_ws[dev];
 		plan = plan_create(b->streams, b->n, opts, nseg, &w.arena, &perr);
 		if (!plan)
 			return perr ? perr : ACM_ERR_OTHER;
@@ -860,4 +874,95 @@ extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *
 			cudaEventDestroy(e);
 	acm_gpu_plan_destroy(plan);
 	return err;
+}
+
+/*
+ * Streams are independent, so a batch shards over the GPUs of a box by
+ * stream, with no collective: opts->device_mask names the CUDA ordinals, the caller's stream
+ * array is cut into one contiguous range per device with (nearly) equal shares of the output
+ * words, and every range is decoded by its own host thread through the single-device path
+ * (own workspace, own lock, own CUDA streams).  Host buffers only: a device pointer belongs to
+ * one GPU.  The per-stream results land in the caller's array as usual.
+ */
+extern "C" int acm_gpu_decode_batch(const acm_gpu_batch *b, const acm_gpu_opts *opts)
+{
+	acm_gpu_opts defaults;
+	g_err[0] = 0;
+	if (!b || (!b->streams && b->n)) {
+		acm_set_error("acm_gpu_decode_batch: null batch");
+		return ACM_ERR_OTHER;
+	}
+	if (!opts) {
+		acm_gpu_opts_init(&defaults);
+		opts = &defaults;
+	}
+	std::vector<int> devs;
+	for (int d = 0; d < 32; d++)
+		if (opts->device_mask & (1u << d))
+			devs.push_back(d);
+	if (devs.size() <= 1) {
+		if (devs.size() == 1) {
+			acm_gpu_opts o = *opts;
+			o.device = devs[0];
+			o.device_mask = 0;
+			return decode_batch_one_device(b, &o);
+		}
+		return decode_batch_one_device(b, opts);
+	}
+	if (b->blob_on_device || b->out_on_device) {
+		acm_set_error("acm_gpu_decode_batch: device_mask with more than one GPU needs host buffers");
+		return ACM_ERR_OTHER;
+	}
+	int have = 0;
+	if (cudaGetDeviceCount(&have) != cudaSuccess || devs.back() >= have) {
+		acm_set_error("acm_gpu_decode_batch: device_mask names GPU %d, the box has %d", devs.back(), have);
+		return ACM_ERR_OTHER;
+	}
+	{
+		/* headers first (host work, once), so that the split can weigh the streams */
+		bool need_probe = false;
+		for (uint64_t i = 0; i < b->n; i++)
+			if (b->streams[i].rows == 0 && b->streams[i].total_values == 0 && b->streams[i].status == 0)
+				need_probe = true;
+		if (need_probe && acm_gpu_probe(b->blob, b->blob_len, 0, b->streams, b->n, opts) < 0)
+			return ACM_ERR_OTHER;
+	}
+	const size_t nd = devs.size();
+	std::vector<uint64_t> cut(nd + 1, 0);
+	{
+		uint64_t total = 0, acc = 0, i = 0;
+		for (uint64_t k = 0; k < b->n; k++)
+			total += b->streams[k].total_values;
+		for (size_t d = 0; d < nd; d++) {
+			const uint64_t target = total / nd * (d + 1);
+			while (i < b->n && (d + 1 == nd || acc < target))
+				acc += b->streams[i++].total_values;
+			cut[d + 1] = i;
+		}
+		cut[nd] = b->n;
+	}
+	std::vector<int> rc(nd, ACM_OK);
+	std::vector<std::string> msg(nd);
+	std::vector<std::thread> th;
+	for (size_t d = 0; d < nd; d++) {
+		th.emplace_back([&, d] {
+			acm_gpu_batch sb = *b;
+			acm_gpu_opts o = *opts;
+			o.device = devs[d];
+			o.device_mask = 0;
+			sb.streams = b->streams + cut[d];
+			sb.n = cut[d + 1] - cut[d];
+			if (sb.n)
+				rc[d] = decode_batch_one_device(&sb, &o);
+			msg[d] = g_err; /* the error text is per thread */
+		});
+	}
+	for (std::thread &t : th)
+		t.join();
+	for (size_t d = 0; d < nd; d++)
+		if (rc[d] != ACM_OK) {
+			acm_set_error("GPU %d: %s", devs[d], msg[d].c_str());
+			return rc[d];
+		}
+	return ACM_OK;
 }

@@ -109,18 +109,17 @@ constexpr int LEAD = RW / 4 - 2;               /* 16-byte chunks requested ahead
 constexpr int SCAN_PERIOD = F2_PERIOD;         /* walk steps between two top-ups */
 constexpr int XPRE = 68;                 /* chunk -1: the previous block's last 64 X2 words (+4 pad) */
 constexpr int XWORDS = XPRE + BLEN + 4 * 32; /* transpose layout: 4 pad words per 64 */
-constexpr int CPITCH = 8;                /* words per unpacked column (16 x int16), halves swizzled */
-constexpr int X0_W = COLS * CPITCH;      /* 1024 */
 constexpr int STAGE_W = 1088;            /* 4352 bytes: a whole block (<= 4179 B) + alignment + read-ahead */
-constexpr int LIST_W = 256;              /* listA (k from the front, t from the back), listB (linear) */
-constexpr int WB_WORDS = X0_W + STAGE_W + LIST_W;
+constexpr int WB_WORDS = XWORDS + STAGE_W; /* per worker warp: transpose buffer, then the staged block bytes */
 constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [128,192) X2 tail [192,256) */
 #ifndef F2_KMAX
 #define F2_KMAX 8
 #endif
-constexpr int KMAX = F2_KMAX;            /* blocks a worker decodes per slot claim */
+constexpr int KMAX = F2_KMAX;            /* blocks a worker decodes per visit of a slot */
+constexpr int OWN = MAXOWN / W;          /* slots a worker warp can own (lane k holds the state of the k-th) */
 
-static_assert(WB_WORDS >= XWORDS, "transform layout must fit the worker buffer");
+static_assert((XWORDS * 4) % 16 == 0 && (WB_WORDS * 4) % 16 == 0, "bulk copies need 16-byte aligned staging");
+static_assert(OWN <= 32 && MAXOWN % W == 0, "a worker warp keeps one slot per lane");
 static_assert((RW & (RW - 1)) == 0 && RW % 4 == 0, "the scan ring is a power of two of words, whole 16-byte chunks");
 static_assert(LEAD + 2 <= RW / 4, "the chunk being read and the one after it are never re-requested");
 static_assert(SW <= W, "scan CTAs are launched with the decode CTAs' thread count");
@@ -159,13 +158,8 @@ struct SmemScan {
 
 struct SmemWork {
 	uint64_t k8w[ACM_K8_SIZE];
-	uint32_t nib2w[256];
 	uint32_t wb[W][WB_WORDS];
-	unsigned long long cks[MAXOWN];
-	uint32_t cons[MAXOWN]; /* records consumed per owned slot */
-	uint32_t busy[MAXOWN]; /* slot claimed by a worker warp */
-	uint32_t pos[MAXOWN];  /* words delivered so far of the slot's current stream */
-	uint32_t dead[MAXOWN]; /* local copy of SlotCtl::dead */
+	unsigned long long mbar[W]; /* one transaction barrier per worker warp (bulk-copy staging) */
 	uint32_t info[32];
 	uint16_t t[ACM_T_SIZE];
 };
@@ -209,12 +203,36 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-/* shared-memory words handed from one worker warp to the next under the slot's busy lock, or
- * polled by other warps: every access is an atomic, which is also what racecheck understands */
-__device__ __forceinline__ uint32_t at_ld(uint32_t *p) { return atomicAdd(p, 0u); }
-__device__ __forceinline__ void at_st(uint32_t *p, uint32_t v) { atomicExch(p, v); }
 __device__ __forceinline__ uint32_t vol_ld(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 __device__ __forceinline__ void vol_st(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+/* transaction barrier + bulk copy (TMA): how a worker warp stages a block's bytes.  One lane arms
+ * the barrier with the byte count and issues the copy; the copy engine writes shared memory and
+ * completes the barrier's phase, every lane waits for that phase. */
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		     ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
+{
+	uint32_t done;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+			     "selp.u32 %0, 1, 0, p;\n\t}"
+			     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+	} while (!done);
+}
+/* generic-proxy accesses to shared memory are ordered before the copy engine's next write */
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 /*
  * Watchdog of the two waiting loops.  The scan CTAs and the decode CTAs of a launch wait for each
@@ -433,25 +451,6 @@ __device__ __forceinline__ void fast_step(Walk &s, uint32_t &cp, uint32_t cpend,
 	s.msk = done ? MSK_K : s.msk;
 }
 
-/* ------------------------------------------------------------------ unpack */
-
-struct Stage {
-	const uint32_t *st;
-	uint32_t w_lo;
-	__device__ __forceinline__ uint32_t word(uint32_t i) const { return st[i - w_lo]; }
-};
-
-/* where column c's two halves live: 8 words per column, the halves swapped for columns with
- * bit 2 set, so that the transform's 128-bit loads (lane = column mod 32) are conflict-free */
-__device__ __forceinline__ ColOut col_out(uint32_t *wb, uint32_t c)
-{
-	ColOut o;
-	const uint32_t swz = (c >> 2) & 1u;
-	o.h0 = wb + c * CPITCH + 4u * swz;
-	o.h1 = wb + c * CPITCH + 4u * (swz ^ 1u);
-	return o;
-}
-
 /* ------------------------------------------------------------------ transform + output */
 
 __device__ __forceinline__ uint32_t lift(uint32_t a, uint32_t p1, uint32_t p2, bool odd)
@@ -470,45 +469,41 @@ __device__ __forceinline__ uint32_t pack2(uint32_t a, uint32_t b, uint32_t sel, 
 }
 
 /*
- * Transform + output of one block by one warp.  wb[0 .. X0_W) holds the unpacked columns
- * (column c: sixteen int16 at words [8c, 8c+8), see col_out); val is the block's multiplier; gh is the
- * slot's history in global memory (first == true: all-zero history, decode.c:812).
- * n = words to emit (<= 2048).  Returns this lane's checksum contribution.
+ * Transform + output of one block by one warp.  x[i] = the dequantised word m = 32 i + lane of
+ * the block (row i / 4, column 32 (i % 4) + lane: the lane's own four columns, straight from
+ * the unpackers); xs = the warp's transpose buffer; h = the history of the slot's previous block
+ * (all zero for a stream's first block, decode.c:812), gh = where this block's goes.  n = words
+ * to emit (<= 2048).  Returns this lane's checksum contribution.
  */
-template <bool CKS>
-__device__ __forceinline__ unsigned long long
-juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint8_t *out, uint32_t pos0,
-		 uint32_t n, const Format fmt)
-{
-	uint32_t *xs = wb + XPRE;
-	uint32_t x[64];
-	unsigned long long cks = 0ull;
-
-	/* history of the previous block (L2 resident; .cg: never a stale L1 line) */
+struct Hist {
 	uint32_t hx[4], hy[2], hz[2];
+};
+
+/* history of the slot's previous block (L2 resident; .cg: never a stale L1 line); issued before
+ * the unpack, so that the transform does not wait for it */
+__device__ __forceinline__ void hist_load(Hist &h, const uint32_t *gh, bool first, int lane)
+{
 #pragma unroll
 	for (int k = 0; k < 4; k++)
-		hx[k] = first ? 0u : __ldcg(gh + 32 * k + lane);       /* X0[-128 + 32k + lane] */
-	hy[0] = first ? 0u : __ldcg(gh + 128 + lane);               /* X1[-64 + lane] */
-	hy[1] = first ? 0u : __ldcg(gh + 160 + lane);               /* X1[-32 + lane] */
-	hz[0] = first ? 0u : __ldcg(gh + 192 + lane);               /* X2[-64 + lane] */
-	hz[1] = first ? 0u : __ldcg(gh + 224 + lane);               /* X2[-32 + lane] */
+		h.hx[k] = first ? 0u : __ldcg(gh + 32 * k + lane);       /* X0[-128 + 32k + lane] */
+	h.hy[0] = first ? 0u : __ldcg(gh + 128 + lane);               /* X1[-64 + lane] */
+	h.hy[1] = first ? 0u : __ldcg(gh + 160 + lane);               /* X1[-32 + lane] */
+	h.hz[0] = first ? 0u : __ldcg(gh + 192 + lane);               /* X2[-64 + lane] */
+	h.hz[1] = first ? 0u : __ldcg(gh + 224 + lane);               /* X2[-32 + lane] */
+}
 
-	/* ---- dequantise (decode.c:174-177, :591-600) and stages 1, 2 in registers:
-	 * lane owns m = 32*i + lane = row i/4, column 32*(i%4) + lane */
-#pragma unroll
-	for (int p = 0; p < 4; p++) {
-		const uint32_t swz = ((uint32_t)lane >> 2) & 1u;
-		const uint32_t *c = wb + (32 * p + lane) * CPITCH;
-		const uint4 q0 = *reinterpret_cast<const uint4 *>(c + 4u * swz);
-		const uint4 q1 = *reinterpret_cast<const uint4 *>(c + 4u * (swz ^ 1u));
-		const uint32_t ww[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
-#pragma unroll
-		for (int j = 0; j < 8; j++) {
-			x[8 * j + p] = (uint32_t)((int)(short)(ww[j] & 0xFFFFu) * val);
-			x[8 * j + 4 + p] = (uint32_t)(((int)ww[j] >> 16) * val);
-		}
-	}
+template <bool CKS>
+__device__ __forceinline__ unsigned long long
+juggle_and_store(uint32_t (&x)[64], const Hist &h, uint32_t *xs0, uint32_t *gh, int lane, uint8_t *out,
+		 uint32_t pos0, uint32_t n, const Format fmt)
+{
+	uint32_t *xs = xs0 + XPRE;
+	unsigned long long cks = 0ull;
+	const uint32_t (&hx)[4] = h.hx;
+	const uint32_t (&hy)[2] = h.hy;
+	const uint32_t (&hz)[2] = h.hz;
+
+	/* ---- stages 1, 2 in registers: lane owns m = 32*i + lane */
 #pragma unroll
 	for (int k = 0; k < 4; k++)
 		__stcg(gh + 32 * k + lane, x[60 + k]);
@@ -525,7 +520,7 @@ juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint
 	}
 	__stcg(gh + 128 + lane, y[62]);
 	__stcg(gh + 160 + lane, y[63]);
-	__syncwarp(); /* every lane has read its columns: the buffer can be overwritten */
+	__syncwarp(); /* every lane has picked up its parked linear columns: the buffer can be overwritten */
 	/* chunk -1 = the previous block's last 64 X2 words */
 	xs[-XPRE + lane] = hz[0];
 	xs[-XPRE + 32 + lane] = hz[1];
@@ -681,162 +676,301 @@ juggle_and_store(uint32_t *wb, uint32_t *gh, bool first, int lane, int val, uint
 
 /* ------------------------------------------------------------------ worker: one block record */
 
-template <bool CKS>
-__device__ __forceinline__ void decode_record(SmemWork &sm, const KernelArgs &a, uint32_t *wb, int slot, int lane,
-					      const uint8_t *recbase, uint32_t *gh, DevStream &d, uint32_t &d_id,
-					      SlotCtl *ctl, uint32_t &pos, unsigned long long &cks, uint32_t &dead)
+/* the stream facts a worker needs, cached in the lane that holds the slot */
+struct Stage {
+	const uint32_t *st;
+	uint32_t w_lo;
+	__device__ __forceinline__ uint32_t word(uint32_t i) const { return st[i - w_lo]; }
+};
+
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 {
-	Rec e;
-	{
-		const uint4 r0 = __ldcg(reinterpret_cast<const uint4 *>(recbase + 256));
-		const uint4 r1 = __ldcg(reinterpret_cast<const uint4 *>(recbase + 272));
-		e.pblock = r0.x; e.pend = r0.y; e.desc = r0.z; e.blk = r0.w;
-		e.status = (int32_t)r1.x; e.ncols = r1.y; e.val = (int32_t)r1.z; e.pad = r1.w;
+	uint32_t v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release(uint32_t *p, uint32_t v)
+{
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ void rec_load(Rec &e, const uint8_t *recbase)
+{
+	const uint4 r0 = __ldcg(reinterpret_cast<const uint4 *>(recbase + 256));
+	const uint4 r1 = __ldcg(reinterpret_cast<const uint4 *>(recbase + 272));
+	e.pblock = r0.x; e.pend = r0.y; e.desc = r0.z; e.blk = r0.w;
+	e.status = (int32_t)r1.x; e.ncols = r1.y; e.val = (int32_t)r1.z; e.pad = r1.w;
+}
+
+/* 16-byte chunks [c_lo, c_hi) of the stream hold the block (and the unpackers' read-ahead) */
+__device__ __forceinline__ void stage_range(const Rec &e, uint32_t &c_lo, uint32_t &c_hi)
+{
+	c_lo = e.pblock >> 7;
+	c_hi = (e.pend + 160u + 127u) >> 7;
+	if (c_hi > c_lo + (uint32_t)(STAGE_W / 4))
+		c_hi = c_lo + (uint32_t)(STAGE_W / 4);
+}
+
+/* Issues the bulk copy of a block's bytes into the warp's staging area (which nobody reads any
+ * more: the caller has synchronised the warp).  Returns the bytes under way (0: nothing to wait
+ * for). */
+__device__ __forceinline__ uint32_t stage_issue(const KernelArgs &a, const DevStream &d, const Rec &e, uint32_t *stage,
+					       uint32_t mbar, int lane)
+{
+	uint32_t c_lo, c_hi;
+	stage_range(e, c_lo, c_hi);
+	const uint64_t room16 = (a.blob_room > d.base_off ? a.blob_room - d.base_off : 0) >> 4;
+	const uint32_t c_cp = (uint64_t)c_hi < room16 ? c_hi : (uint32_t)room16; /* chunks that exist in the blob */
+	const uint32_t nbytes = c_cp > c_lo ? (c_cp - c_lo) * 16u : 0u;
+	if (nbytes && lane == 0) {
+		fence_proxy_async();
+		mbar_expect_tx(mbar, nbytes);
+		bulk_g2s((uint32_t)__cvta_generic_to_shared(stage), a.blob + d.base_off + (size_t)c_lo * 16u, nbytes, mbar);
 	}
-	const uint2 offs = __ldcg(reinterpret_cast<const uint2 *>(recbase) + lane); /* columns 4*lane .. +3 */
-	if (e.desc != d_id) { /* consecutive records of a slot mostly belong to one stream */
-		d = a.streams[e.desc];
-		d_id = e.desc;
-	}
-	const uint32_t bno = e.blk & 0x7FFFFFFFu;
-	const bool last = (e.blk >> 31) != 0;
-	if (bno == 0) {
-		pos = 0u;
-		cks = 0ull;
-	}
-	if (dead == e.desc + 1u)
-		return; /* stream already finalised by a corrupt code (descriptor ids are unique) */
-	const uint32_t limit_w = d.file_end + 8u;
-	const bool ok = e.status == SCAN_OK;
-	const uint32_t ncheck = ok ? (uint32_t)COLS : e.ncols + (e.status == -7 ? 1u : 0u);
-	int bad = 0;
-	if (ncheck) {
-		uint32_t *stage = wb + X0_W;
-		uint32_t *listA = wb + X0_W + STAGE_W, *listB = listA + 128;
-		/* ---- stage the block's bytes: 16-byte chunks [c_lo, c_hi) of the stream, with the
-		 * EOF rule applied (bits at and past file_end read as zero) */
-		const uint32_t c_lo = e.pblock >> 7;
-		uint32_t c_hi = (e.pend + 160u + 127u) >> 7;
-		if (c_hi > c_lo + (uint32_t)(STAGE_W / 4))
-			c_hi = c_lo + (uint32_t)(STAGE_W / 4);
-		const uint8_t *src = a.blob + d.base_off;
-		const uint64_t room = a.blob_room > d.base_off ? a.blob_room - d.base_off : 0;
-		const uint32_t fe_word = d.file_end >> 5, fe_tail = d.file_end & 31u;
-		for (uint32_t c = c_lo + lane; c < c_hi; c += 32) {
-			uint4 v = make_uint4(0u, 0u, 0u, 0u);
-			if ((uint64_t)c * 16u + 16u <= room)
-				v = ldg_nc_v4(src + (size_t)c * 16u);
-			if (4u * c + 3u >= fe_word) {
-				uint32_t q[4] = { v.x, v.y, v.z, v.w };
+	return nbytes;
+}
+
+/*
+ * A visit: up to KMAX consecutive records (= blocks) of one slot, in order.
+ * Staging: a block's bytes arrive by ONE bulk copy (TMA) on the warp's transaction barrier; the
+ * copy for block i+1 is issued as soon as block i is unpacked, so it travels while block i is
+ * transformed.  The end-of-file rule (bits at and past file_end read as zero, decode.c:57-61) is
+ * applied afterwards to the rare block that reaches the end of its file.
+ * Unpack: lane j owns columns j, j+32, j+64, j+96 (pass p = 0..3), i.e. exactly the words
+ * m = j mod 32 that lifting stages 1-2 want in its registers: the values go from the code tables
+ * to the transform without touching shared memory (linear columns are parked in the lane's own
+ * words of the transpose buffer).
+ */
+template <bool CKS>
+__device__ __forceinline__ void decode_visit(SmemWork &sm, const KernelArgs &a, uint32_t *wb, uint32_t mbar,
+					     uint32_t &mphase, int lane, const uint8_t *slot_ring, uint32_t c0,
+					     uint32_t nrec, uint32_t *gh, SlotCtl *ctl, uint32_t &pos,
+					     unsigned long long &cks, uint32_t &dead)
+{
+	uint32_t *stage = wb + XWORDS;
+	DevStream d;
+	uint32_t d_id = 0xFFFFFFFFu;
+	uint32_t under_way = 0u;   /* bytes of a staging copy that has been issued and not waited for */
+	uint32_t staged_for = 0u;  /* ... and the record (index + 1) it belongs to */
+	PROF_DECL; /* 24: record + descriptor, 25: staging wait, 26: unpack, 27: next copy + dequantise, 28: transform, 29: rest */
+	for (uint32_t i = 0; i < nrec; i++) {
+		PROF_MARK(5);
+		const uint32_t c = c0 + i;
+		const uint8_t *recbase = slot_ring + (size_t)(c % RING_D) * REC_BYTES;
+		Rec e;
+		rec_load(e, recbase);
+		uint32_t offs[4]; /* selector positions of the lane's four columns, relative to the block */
 #pragma unroll
-				for (int j = 0; j < 4; j++) {
-					const uint32_t k = 4u * c + j;
-					if (k > fe_word || (k == fe_word && !fe_tail))
-						q[j] = 0u;
-					else if (k == fe_word)
-						q[j] &= (1u << fe_tail) - 1u;
-				}
-				v = make_uint4(q[0], q[1], q[2], q[3]);
-			}
-			reinterpret_cast<uint4 *>(stage)[c - c_lo] = v;
+		for (int p = 0; p < 4; p++)
+			offs[p] = __ldcg(reinterpret_cast<const uint16_t *>(recbase) + 32 * p + lane);
+		if (e.desc != d_id) { /* consecutive records of a slot mostly belong to one stream */
+			d = a.streams[e.desc];
+			d_id = e.desc;
 		}
-		__syncwarp();
-		Stage sr;
-		sr.st = stage;
-		sr.w_lo = c_lo * 4u;
-		/* ---- sort the columns by filler class */
-		uint32_t nk = 0, nt = 0, nl = 0;
-		const uint32_t lt = (1u << lane) - 1u;
+		const uint32_t bno = e.blk & 0x7FFFFFFFu;
+		const bool last = (e.blk >> 31) != 0;
+		if (bno == 0) {
+			pos = 0u;
+			cks = 0ull;
+		}
+		const bool skip = dead == e.desc + 1u; /* stream already finalised by a corrupt code (ids are unique) */
+		const uint32_t limit_w = d.file_end + 8u;
+		const bool ok = e.status == SCAN_OK;
+		const uint32_t ncheck = skip ? 0u : ok ? (uint32_t)COLS : e.ncols + (e.status == -7 ? 1u : 0u);
+		PROF_MARK(0);
+		/* ---- the block's bytes */
+		if (staged_for != c + 1u) {
+			if (under_way) { /* cannot happen (a copy is only issued for the next record); keep the phase right */
+				mbar_wait(mbar, mphase);
+				mphase ^= 1u;
+				under_way = 0u;
+			}
+			__syncwarp(); /* nobody still reads the previous block's bytes */
+			if (ncheck)
+				under_way = stage_issue(a, d, e, stage, mbar, lane);
+		}
+		if (under_way) {
+			mbar_wait(mbar, mphase);
+			mphase ^= 1u;
+			under_way = 0u;
+		}
+		staged_for = 0u;
+		if (skip) {
+			__syncwarp();
+			continue;
+		}
+		PROF_MARK(1);
+		int bad = 0;
+		uint32_t A0[4], A1[4];              /* per pass: the column's sixteen nibbles */
+		uint32_t linmask = 0u, linany = 0u; /* bit p: this lane's / some lane's column of pass p is linear */
+		Hist h;
+		hist_load(h, gh, bno == 0, lane);
+		/* the record after this one (it exists: nrec was counted behind an acquire): asked for now,
+		 * needed after the unpack */
+		const bool more = i + 1u < nrec && ok && !last;
+		Rec en;
+		if (more)
+			rec_load(en, slot_ring + (size_t)((c + 1u) % RING_D) * REC_BYTES);
+		if (ncheck) {
+			uint32_t c_lo, c_hi;
+			stage_range(e, c_lo, c_hi);
+			const uint32_t fe_word = d.file_end >> 5, fe_tail = d.file_end & 31u;
+			if (c_hi * 4u > fe_word) {
+				/* the staged range reaches the end of the file: zero what lies at and past it
+				 * (and the chunks past the end of the blob, which were not copied) */
+				const uint32_t k0 = fe_word > c_lo * 4u ? fe_word : c_lo * 4u;
+				for (uint32_t k = k0 + lane; k < c_hi * 4u; k += 32) {
+					uint32_t v = 0u;
+					if (k == fe_word && fe_tail)
+						v = stage[k - c_lo * 4u] & ((1u << fe_tail) - 1u);
+					stage[k - c_lo * 4u] = v;
+				}
+				__syncwarp();
+			}
+			Stage sr;
+			sr.st = stage;
+			sr.w_lo = c_lo * 4u;
+			/* ---- unpack: four passes of 32 columns.  Prefix- and radix-coded (and zero) columns
+			 * leave the pass as sixteen nibbles in two registers (A0 / A1 of that pass); the sixteen
+			 * words of a linear column are parked in the lane's own words of the transpose buffer
+			 * (word 32 i + lane, i = 4 r + p: conflict-free, nobody else touches them).  One copy of
+			 * the code: the loop is not unrolled. */
+#pragma unroll 1
+			for (int p = 0; p < 4; p++) {
+				const uint32_t col = 32u * (uint32_t)p + (uint32_t)lane;
+				const uint32_t off = p == 0 ? offs[0] : p == 1 ? offs[1] : p == 2 ? offs[2] : offs[3];
+				uint32_t inf = 0u, ind = 0u, lo = 0u, mid = 0u, hi = 0u;
+				const uint32_t P = e.pblock + off + 5u; /* payload */
+				if (col < ncheck) {
+					const uint32_t Pc = e.pblock + off, iw = Pc >> 5;
+					const uint32_t w0 = sr.word(iw), w1 = sr.word(iw + 1), w2 = sr.word(iw + 2),
+						       w3 = sr.word(iw + 3), w4 = sr.word(iw + 4);
+					ind = __funnelshift_r(w0, w1, Pc) & 31u;
+					inf = sm.info[ind];
+					const bool up = (Pc & 31u) + 5u >= 32u; /* the payload starts in the next word */
+					const uint32_t v0 = up ? w1 : w0, v1 = up ? w2 : w1, v2 = up ? w3 : w2, v3 = up ? w4 : w3;
+					lo = __funnelshift_r(v0, v1, P);
+					mid = __funnelshift_r(v1, v2, P);
+					hi = __funnelshift_r(v2, v3, P);
+				}
+				const bool isk = (inf & INF_K) != 0u, ist = (inf & INF_T) != 0u, isl = (inf & INF_LIN) != 0u;
+				uint32_t a0 = 0u, a1 = 0u; /* f_zero decode.c:181-188: all rows zero */
+				if (ok && __any_sync(0xFFFFFFFFu, isk)) {
+					if (isk)
+						unpack_k(lo, mid, hi, inf >> 20, sm.k8w, a0, a1);
+					__syncwarp();
+				}
+				if (__any_sync(0xFFFFFFFFu, ist)) {
+					if (ist)
+						bad |= unpack_t(lo, mid, P, limit_w, inf >> 20, sm.t, a0, a1);
+					__syncwarp();
+				}
+				const uint32_t ml = __ballot_sync(0xFFFFFFFFu, ok && isl);
+				if (ml) {
+					if (isl) {
+						uint32_t v[ROWS];
+						unpack_linear(sr, P, ind, e.val, v);
 #pragma unroll
-		for (int j = 0; j < 4; j++) {
-			const uint32_t c = 4u * lane + j;
-			const uint32_t off = (j & 1) ? ((j & 2) ? offs.y : offs.x) >> 16 : ((j & 2) ? offs.y : offs.x) & 0xFFFFu;
-			uint32_t inf = 0u, ent = 0u;
-			if (c < ncheck) {
-				const uint32_t Pc = e.pblock + off, i = Pc >> 5;
-				const uint32_t ind = __funnelshift_r(sr.word(i), sr.word(i + 1), Pc) & 31u;
-				inf = sm.info[ind];
-				ent = c | (((inf & INF_LIN) ? ind : (inf >> 20)) << 8) | (off << 16);
-				if (ok && !(inf & (INF_K | INF_T | INF_LIN))) {
-					/* f_zero decode.c:181-188 */
-					uint4 *z = reinterpret_cast<uint4 *>(wb + c * CPITCH);
-					z[0] = make_uint4(0u, 0u, 0u, 0u);
-					z[1] = make_uint4(0u, 0u, 0u, 0u);
+						for (int r = 0; r < ROWS; r++)
+							wb[32 * (4 * r + p) + lane] = v[r];
+					}
+					__syncwarp();
+					linmask |= (isl ? 1u : 0u) << p;
+					linany |= 1u << p;
+				}
+				if (p == 0) {
+					A0[0] = a0; A1[0] = a1;
+				} else if (p == 1) {
+					A0[1] = a0; A1[1] = a1;
+				} else if (p == 2) {
+					A0[2] = a0; A1[2] = a1;
+				} else {
+					A0[3] = a0; A1[3] = a1;
 				}
 			}
-			const uint32_t mk = __ballot_sync(0xFFFFFFFFu, (inf & INF_K) != 0u);
-			const uint32_t mt = __ballot_sync(0xFFFFFFFFu, (inf & INF_T) != 0u);
-			const uint32_t ml = __ballot_sync(0xFFFFFFFFu, (inf & INF_LIN) != 0u);
-			if (inf & INF_K)
-				listA[nk + __popc(mk & lt)] = ent;
-			if (inf & INF_T)
-				listA[127u - (nt + __popc(mt & lt))] = ent;
-			if (inf & INF_LIN)
-				listB[nl + __popc(ml & lt)] = ent;
-			nk += __popc(mk);
-			nt += __popc(mt);
-			nl += __popc(ml);
 		}
-		__syncwarp();
-		/* ---- unpack, one class at a time */
-		if (ok) {
-			for (uint32_t j = lane; j < nk; j += 32) {
-				const uint32_t ent = listA[j];
-				unpack_k(sr, e.pblock + (ent >> 16) + 5u, (ent >> 8) & 31u, col_out(wb, ent & 127u), sm.k8w,
-					 sm.nib2w);
-			}
-			for (uint32_t j = lane; j < nl; j += 32) {
-				const uint32_t ent = listB[j];
-				unpack_linear(sr, e.pblock + (ent >> 16) + 5u, (ent >> 8) & 31u, col_out(wb, ent & 127u));
+		bad = __any_sync(0xFFFFFFFFu, bad);
+		PROF_MARK(2);
+		/* ---- the next block's bytes travel while this one is transformed */
+		__syncwarp(); /* the staged bytes have been read */
+		if (more && !bad) {
+			if (en.desc == e.desc && en.status == SCAN_OK) {
+				under_way = stage_issue(a, d, en, stage, mbar, lane);
+				staged_for = c + 2u;
 			}
 		}
-		for (uint32_t j = lane; j < nt; j += 32) {
-			const uint32_t ent = listA[127u - j];
-			bad |= unpack_t(sr, e.pblock + (ent >> 16) + 5u, limit_w, (ent >> 8) & 31u, col_out(wb, ent & 127u),
-					sm.t, sm.nib2w, ok);
+		int st = 0;
+		if (bad)
+			st = -6;
+		else if (!ok)
+			st = e.status == SCAN_EOF ? 0 : e.status;
+		if (ok && !bad) {
+			uint32_t n = d.words_limit - pos;
+			if (n > (uint32_t)BLEN)
+				n = BLEN;
+			uint8_t *out = a.out + d.out_off;
+			/* dequantise (set_pos + midbuf, decode.c:174-177, :591-600): x[i] = word m = 32 i + lane */
+			uint32_t x[64];
+#pragma unroll
+			for (int p = 0; p < 4; p++) {
+#pragma unroll
+				for (int r = 0; r < ROWS; r++)
+					x[4 * r + p] = nib_val(r < 8 ? A0[p] : A1[p], r & 7, e.val);
+			}
+			if (linany) {
+				/* pick up the parked linear columns; real branches (a loop of one turn per pass with
+				 * a linear column): predicated, this would be 128 instructions for every block */
+#pragma unroll
+				for (int p = 0; p < 4; p++) {
+					const bool isl = (linmask >> p) & 1u;
+#pragma unroll 1
+					for (uint32_t t = (linany >> p) & 1u; t; t--) {
+#pragma unroll
+						for (int r = 0; r < ROWS; r++) {
+							const uint32_t lv = wb[32 * (4 * r + p) + lane];
+							x[4 * r + p] = isl ? lv : x[4 * r + p];
+						}
+					}
+				}
+			}
+			PROF_MARK(3);
+			unsigned long long c2 = juggle_and_store<CKS>(x, h, wb, gh, lane, out, pos, n, a.fmt);
+			PROF_MARK(4);
+			pos += n;
+			if (CKS) {
+				for (int o = 16; o; o >>= 1)
+					c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+				cks += c2;
+			}
 		}
-	}
-	bad = __any_sync(0xFFFFFFFFu, bad);
-	__syncwarp();
-	int st = 0;
-	if (bad)
-		st = -6;
-	else if (!ok)
-		st = e.status == SCAN_EOF ? 0 : e.status;
-	if (ok && !bad) {
-		uint32_t n = d.words_limit - pos;
-		if (n > (uint32_t)BLEN)
-			n = BLEN;
-		uint8_t *out = a.out + d.out_off;
-		unsigned long long c2 = juggle_and_store<CKS>(wb, gh, bno == 0, lane, e.val, out, pos, n, a.fmt);
-		pos += n;
-		if (CKS) {
-			for (int o = 16; o; o >>= 1)
-				c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
-			cks += c2;
+		if (!ok || bad || last) {
+			/* finalise: results + zero padding of the undelivered tail */
+			uint8_t *p0 = a.out + d.out_off + (size_t)pos * a.fmt.wordlen;
+			/* up to the 16-byte boundary that ends this stream's slot (out_off is 16-byte
+			 * aligned), so that alignment gaps never carry stale bytes */
+			size_t nb = d.pad_words >= pos && d.pad_words
+					    ? (((size_t)d.pad_words * a.fmt.wordlen + 15u) & ~(size_t)15u) -
+						      (size_t)pos * a.fmt.wordlen
+					    : 0;
+			for (size_t k = lane; k < nb; k += 32)
+				p0[k] = 0;
+			__syncwarp();
+			if (lane == 0) {
+				a.status[d.index] = st;
+				a.words[d.index] = pos;
+				a.cks[d.index] = a.fmt.checksums ? cks : 0ull;
+				vol_st(&ctl->dead, e.desc + 1u); /* the slot's scan lane stops walking this stream */
+			}
+			dead = e.desc + 1u;
 		}
-	}
-	if (!ok || bad || last) {
-		/* finalise: results + zero padding of the undelivered tail */
-		uint8_t *p0 = a.out + d.out_off + (size_t)pos * a.fmt.wordlen;
-		/* up to the 16-byte boundary that ends this stream's slot (out_off is 16-byte
-		 * aligned), so that alignment gaps never carry stale bytes */
-		size_t nb = d.pad_words >= pos && d.pad_words
-				    ? (((size_t)d.pad_words * a.fmt.wordlen + 15u) & ~(size_t)15u) -
-					      (size_t)pos * a.fmt.wordlen
-				    : 0;
-		for (size_t i = lane; i < nb; i += 32)
-			p0[i] = 0;
 		__syncwarp();
-		if (lane == 0) {
-			a.status[d.index] = st;
-			a.words[d.index] = pos;
-			a.cks[d.index] = a.fmt.checksums ? cks : 0ull;
-			vol_st(&ctl->dead, e.desc + 1u); /* the slot's scan lane stops walking this stream */
-		}
-		dead = e.desc + 1u;
 	}
-	__syncwarp();
+	if (under_way) { /* not reached: a copy is only issued when the visit goes on */
+		mbar_wait(mbar, mphase);
+		mphase ^= 1u;
+	}
+	PROF_MARK(5);
+	PROF_FLUSH(24);
 }
 
 /* ------------------------------------------------------------------ kernel */
@@ -1064,47 +1198,43 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 }
 
 /*
- * Decode CTA number w of n_work owns the slots g = w, w + n_work, w + 2 n_work, ... (local
- * index j).  Its worker warps claim an owned slot that has records pending and decode them in
- * order.
+ * Decode CTA number w of n_work owns the slots g = w, w + n_work, w + 2 n_work, ... (local index
+ * j), and within the CTA worker warp v owns the local indices j = v, v + W, ...: at most OWN slots,
+ * the state of the k-th one (records consumed, words delivered, checksum) lives in the registers
+ * of lane k.  Fixed ownership: no locks, no shared-memory hand-over, and polling for work is one
+ * load per lane.  A worker visits the owned slot with the largest backlog and decodes up to KMAX
+ * of its records in order.
  */
 template <bool CKS>
 __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int warp, int lane)
 {
 	const uint32_t w = (uint32_t)blockIdx.x - a.n_scan, n_work = (uint32_t)gridDim.x - a.n_scan;
-	const uint32_t J = a.n_slots > w ? (a.n_slots - w + n_work - 1u) / n_work : 0u; /* owned slots */
+	const uint32_t J = a.n_slots > w ? (a.n_slots - w + n_work - 1u) / n_work : 0u; /* the CTA's slots */
+	const uint32_t jmine = (uint32_t)warp + (uint32_t)W * (uint32_t)lane;
+	const bool own = lane < OWN && jmine < J;
+	const uint32_t g = own ? w + n_work * jmine : 0u;
 	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl);
 	uint32_t *wb = sm.wb[warp];
+	const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&sm.mbar[warp]);
+	uint32_t mphase = 0u;
+	/* lane k: the k-th owned slot */
+	uint32_t cons = 0u, pos = 0u, dead = 0u;
+	unsigned long long cks = 0ull;
 	uint32_t nap = 64u;
 	bool confirmed = false;
 	unsigned long long waiting_since = 0ull;
 	uint32_t seen_hb = 0;
 	PROF_DECL;
+	if (!__any_sync(0xFFFFFFFFu, own))
+		return;
 	for (;;) {
 		PROF_MARK(0); /* 8+0: decode */
 		const bool done = *reinterpret_cast<volatile uint32_t *>(a.scan_done) == a.n_scan * (uint32_t)SW;
-		/* the owned slot with the largest backlog of records that nobody holds: best = backlog << 8
-		 * | local slot index (0: nothing pending).  Largest first, not round robin: the slots of the
-		 * longest streams are the ones that fall behind while decoding is the bottleneck, and a
-		 * slot's records are decoded one after the other -- whatever backlog they still have when
-		 * the scan ends is the launch's tail */
-		uint32_t best = 0;
-#pragma unroll
-		for (int k = 0; k < MAXOWN / 32; k++) {
-			const uint32_t j = (uint32_t)lane + 32u * k;
-			if (j < J && !at_ld(&sm.busy[j])) {
-				const uint32_t backlog = vol_ld(&ctl[w + n_work * j].prod) - at_ld(&sm.cons[j]);
-				const uint32_t key = backlog ? (backlog << 8) | j : 0u;
-				best = key > best ? key : best;
-			}
-		}
-#pragma unroll
-		for (int o = 16; o; o >>= 1) {
-			const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
-			best = other > best ? other : best;
-		}
-		const uint32_t any = best;
-		if (!any) {
+		const uint32_t backlog = own ? vol_ld(&ctl[g].prod) - cons : 0u;
+		/* largest backlog first: the slots of the longest streams are the ones that fall behind
+		 * while decoding is the bottleneck, and a slot's records are decoded one after the other */
+		const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, backlog ? (backlog << 5) | (uint32_t)lane : 0u);
+		if (!best) {
 			if (done) {
 				/* every scan warp has finished: look once more behind a fence (acquire: all
 				 * their announcements are visible), then leave */
@@ -1117,7 +1247,7 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 				continue;
 			}
 			__nanosleep(nap); /* idle: back off */
-			nap = nap < 2048u ? nap * 2u : nap;
+			nap = nap < 1024u ? nap * 2u : nap;
 			PROF_MARK(1); /* 8+1: idle */
 			const uint32_t hb = *reinterpret_cast<volatile uint32_t *>(a.scan_done + 1);
 			if (waiting_since == 0ull || hb != seen_hb) {
@@ -1133,51 +1263,29 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		nap = 64u;
 		confirmed = false;
 		waiting_since = 0ull;
-		const int slot = (int)(best & 255u);
-		uint32_t got = 0;
-		if (lane == 0)
-			got = atomicCAS(&sm.busy[slot], 0u, 1u) == 0u;
-		got = __shfl_sync(0xFFFFFFFFu, got, 0);
-		if (!got)
-			continue;
-		if (lane == 0)
-			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
-		PROF_MARK(2); /* 8+2: claim */
-		__threadfence_block();
-		const uint32_t g = w + n_work * (uint32_t)slot;
-		/* the slot's running state, handed over under the busy lock */
-		uint32_t c = 0, pos = 0, dead = 0;
-		unsigned long long cks = 0ull;
-		if (lane == 0) {
-			c = at_ld(&sm.cons[slot]);
-			pos = at_ld(&sm.pos[slot]);
-			dead = at_ld(&sm.dead[slot]);
-			cks = atomicAdd(&sm.cks[slot], 0ull);
-		}
-		c = __shfl_sync(0xFFFFFFFFu, c, 0);
-		pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
-		dead = __shfl_sync(0xFFFFFFFFu, dead, 0);
-		cks = __shfl_sync(0xFFFFFFFFu, cks, 0);
-		const uint32_t p = vol_ld(&ctl[g].prod);
-		__threadfence(); /* acquire: the records behind prod */
-		uint32_t nrec = p - c;
+		const int k = (int)(best & 31u);
+		const uint32_t gk = __shfl_sync(0xFFFFFFFFu, g, k);
+		uint32_t c = __shfl_sync(0xFFFFFFFFu, cons, k);
+		uint32_t ps = __shfl_sync(0xFFFFFFFFu, pos, k);
+		uint32_t dd = __shfl_sync(0xFFFFFFFFu, dead, k);
+		unsigned long long ck = __shfl_sync(0xFFFFFFFFu, cks, k);
+		/* acquire: the records behind prod (the poll above was a plain load) */
+		uint32_t nrec = ld_acquire(&ctl[gk].prod) - c;
 		if (nrec > (uint32_t)KMAX)
 			nrec = KMAX;
-		const uint8_t *slot_ring = a.ring + (size_t)g * RING_D * REC_BYTES;
-		DevStream d;
-		uint32_t d_id = 0xFFFFFFFFu;
-		for (uint32_t k = 0; k < nrec; k++, c++)
-			decode_record<CKS>(sm, a, wb, slot, lane, slot_ring + (size_t)(c % RING_D) * REC_BYTES,
-					   a.hist + (size_t)g * HIST_WORDS, d, d_id, ctl + g, pos, cks, dead);
-		__threadfence(); /* the records have been read before the scan lane may overwrite them */
-		if (lane == 0) {
-			at_st(&sm.pos[slot], pos);
-			at_st(&sm.dead[slot], dead);
-			atomicExch(&sm.cks[slot], cks);
-			at_st(&sm.cons[slot], c);
-			vol_st(&ctl[g].cons, c);
-			__threadfence_block();
-			atomicExch(&sm.busy[slot], 0u);
+		if (lane == 0)
+			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
+		decode_visit<CKS>(sm, a, wb, mbar, mphase, lane, a.ring + (size_t)gk * RING_D * REC_BYTES, c, nrec,
+				  a.hist + (size_t)gk * HIST_WORDS, ctl + gk, ps, ck, dd);
+		c += nrec;
+		__syncwarp();
+		if (lane == k) {
+			cons = c;
+			pos = ps;
+			dead = dd;
+			cks = ck;
+			/* release: the records have been read before the scan lane may overwrite them */
+			st_release(&ctl[g].cons, c);
 		}
 		__syncwarp();
 	}
@@ -1204,17 +1312,11 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 			sm.k8w[i] = a.tables->k8w[i];
 		for (int i = tid; i < ACM_T_SIZE; i += THREADS)
 			sm.t[i] = a.tables->t[i];
-		for (int i = tid; i < 256; i += THREADS)
-			sm.nib2w[i] = a.tables->nib2w[i];
 		if (tid < 32)
 			sm.info[tid] = make_info(a.tables->kind[tid]);
-		for (int i = tid; i < MAXOWN; i += THREADS) {
-			sm.cons[i] = 0;
-			sm.busy[i] = 0;
-			sm.dead[i] = 0;
-			sm.pos[i] = 0;
-			sm.cks[i] = 0ull;
-		}
+		if (lane == 0)
+			mbar_init((uint32_t)__cvta_generic_to_shared(&sm.mbar[warp]), 1u);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		__syncthreads();
 #ifdef F2_TEST_NO_DECODE
 		return; /* watchdog test: the scan side must give up on its own */

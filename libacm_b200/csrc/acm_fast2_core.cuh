@@ -10,10 +10,6 @@
 
 #include "acm_device.cuh"
 
-#ifndef F2_NIB_ALU
-#define F2_NIB_ALU 1   /* nibbles -> int16 pairs by arithmetic (0: nib2w table in shared memory) */
-#endif
-
 namespace acm {
 namespace fast2 {
 
@@ -86,58 +82,31 @@ ACM_HD bool walk_next_if(Walk &s, uint32_t e, bool go)
 
 /* ------------------------------------------------------------------ unpack */
 
-/* sixteen int16 of a column in two 128-bit halves (rows 0-7, rows 8-15) */
-struct ColOut {
-	uint32_t *h0, *h1;
-};
+/*
+ * The three column unpackers.  A decode lane owns whole columns (column = lane mod 32, the
+ * layout lifting stages 1 and 2 run in), so a column's sixteen values never leave the lane's
+ * registers: prefix- and radix-coded columns end up as sixteen 4-bit two's complement
+ * values in two registers (a0: rows 0-7, a1: rows 8-15), linear columns as sixteen
+ * dequantised words.  `lo`, `mid`, `hi` = the 96 stream bits that start at the column's
+ * payload.
+ */
 
-ACM_HD void store8(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-#if defined(__CUDA_ARCH__)
-	*reinterpret_cast<uint4 *>(p) = make_uint4(a, b, c, d);
-#else
-	p[0] = a; p[1] = b; p[2] = c; p[3] = d;
-#endif
-}
-
-/* two 4-bit two's-complement values in a byte -> two int16 in a word, without a table: spread the
- * nibbles to bits 0-3 and 16-19 (x 0x1001, mask), then fill bits 4-15 / 20-31 of each half from
- * its sign bit (0x0008 x 0x1FFE = 0xFFF0; the two products cannot meet) */
-ACM_HD uint32_t nib2w_alu(uint32_t byte)
-{
-	const uint32_t x = (byte * 0x1001u) & 0x000F000Fu;
-	return (x & 0x00080008u) * 0x1FFEu + x;
-}
-
-/* 16 nibbles (a0: rows 0-7, a1: rows 8-15) -> sixteen int16 */
-ACM_HD void store_nibbles(uint32_t a0, uint32_t a1, const ColOut &o, const uint32_t *nib2w)
-{
-#if F2_NIB_ALU
-	(void)nib2w;
-	store8(o.h0, nib2w_alu(a0 & 255u), nib2w_alu((a0 >> 8) & 255u), nib2w_alu((a0 >> 16) & 255u), nib2w_alu(a0 >> 24));
-	store8(o.h1, nib2w_alu(a1 & 255u), nib2w_alu((a1 >> 8) & 255u), nib2w_alu((a1 >> 16) & 255u), nib2w_alu(a1 >> 24));
-#else
-	store8(o.h0, nib2w[a0 & 255u], nib2w[(a0 >> 8) & 255u], nib2w[(a0 >> 16) & 255u], nib2w[a0 >> 24]);
-	store8(o.h1, nib2w[a1 & 255u], nib2w[(a1 >> 8) & 255u], nib2w[(a1 >> 16) & 255u], nib2w[a1 >> 24]);
-#endif
-}
+/* sign-extend nibble j of x and dequantise (set_pos / midbuf, decode.c:174-177, :591-600) */
+ACM_HD uint32_t nib_val(uint32_t x, int j, int val) { return (uint32_t)(nib_s(x, j) * val); }
 
 /*
  * Prefix codes (decode.c:208-403).  One k8w entry per step: up to 8 values, the bits and the
  * rows they cover.  No row cap: the 16 rows are nibbles of a 64-bit accumulator and whatever is
  * decoded past the 16th row (the bits of the next column) shifts out; the reference's tail rule
  * (a "two zeros" symbol at the last row emits one, decode.c:216-218) is the same thing.
- * SR::word(i) = 32-bit word i of the stream; words up to (P >> 5) + 3 are read.
+ * A column is at most 80 bits, so the 96-bit window never runs dry.
  */
-template <typename SR>
-ACM_HD void unpack_k(const SR &sr, uint32_t P, uint32_t sub, const ColOut &o, const uint64_t *k8w,
-		     const uint32_t *nib2w)
+ACM_HD void unpack_k(uint32_t lo, uint32_t mid, uint32_t hi, uint32_t sub, const uint64_t *k8w, uint32_t &a0,
+		     uint32_t &a1)
 {
-	const uint32_t i = P >> 5, sh = P & 31u;
-	const uint32_t w0 = sr.word(i), w1 = sr.word(i + 1), w2 = sr.word(i + 2), w3 = sr.word(i + 3);
-	uint32_t lo = fsr(w0, w1, sh), mid = fsr(w1, w2, sh), hi = fsr(w2, w3, sh);
 	const uint64_t *tab = k8w + sub * 256u;
-	uint32_t a0 = 0u, a1 = 0u, r4 = 0u;
+	uint32_t r4 = 0u;
+	a0 = a1 = 0u;
 	do {
 		const uint64_t e = tab[lo & 255u];
 		const uint32_t ev = (uint32_t)e, em = (uint32_t)(e >> 32);
@@ -150,26 +119,24 @@ ACM_HD void unpack_k(const SR &sr, uint32_t P, uint32_t sub, const ColOut &o, co
 		a1 |= (uint32_t)(vv >> 32);
 		r4 += em >> 8;
 	} while (r4 < 64u);
-	store_nibbles(a0, a1, o, nib2w);
 }
 
-/* f_t15 / f_t27 / f_t37 (decode.c:405-476): all codes sit in one 64-bit window.  Returns
- * non-zero if a code that the reference gets to read is out of range (decode.c:412/:438/:464). */
-template <typename SR>
-ACM_HD int unpack_t(const SR &sr, uint32_t P, uint32_t limit, uint32_t sub, const ColOut &o, const uint16_t *tt,
-		    const uint32_t *nib2w, bool store)
+/* f_t15 / f_t27 / f_t37 (decode.c:405-476): all codes sit in the first 64 bits of the window.
+ * P = position of the payload, limit = first position that cannot be read.  Returns non-zero
+ * if a code that the reference gets to read is out of range (decode.c:412/:438/:464). */
+ACM_HD int unpack_t(uint32_t lo, uint32_t mid, uint32_t P, uint32_t limit, uint32_t sub, const uint16_t *tt,
+		    uint32_t &a0, uint32_t &a1)
 {
 	const uint32_t width = sub == 0 ? 5u : 7u, per = sub == 2 ? 2u : 3u;
 	const uint32_t ncodes = sub == 2 ? 8u : 6u, cmask = (1u << width) - 1u;
 	const uint32_t vmask = sub == 2 ? 0xFFu : 0xFFFu;
 	const uint16_t *tab = tt + sub * 128u;
-	const uint32_t i = P >> 5, sh = P & 31u;
-	const uint32_t w0 = sr.word(i), w1 = sr.word(i + 1), w2 = sr.word(i + 2);
-	const unsigned long long win = (unsigned long long)fsr(w0, w1, sh) | ((unsigned long long)fsr(w1, w2, sh) << 32);
+	const unsigned long long win = (unsigned long long)lo | ((unsigned long long)mid << 32);
 	/* codes the reference gets to read before the stream runs dry: all of them, except in the
 	 * last block of a truncated stream */
 	const uint32_t nread = P + ncodes * width <= limit ? ncodes : (limit > P ? (limit - P) / width : 0u);
-	uint32_t a0 = 0u, a1 = 0u, seen = 0u;
+	uint32_t seen = 0u;
+	a0 = a1 = 0u;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -182,32 +149,26 @@ ACM_HD int unpack_t(const SR &sr, uint32_t P, uint32_t limit, uint32_t sub, cons
 			a1 |= (uint32_t)(vv >> 32);
 		}
 	}
-	if (store)
-		store_nibbles(a0, a1, o, nib2w);
 	return (seen & 0x8000u) != 0u;
 }
 
 /* f_linear (decode.c:196-206): sliding 64-bit window; the word that the next refill will need
- * is fetched one refill ahead, so that no value waits on a load */
+ * is fetched one refill ahead, so that no value waits on a load.  SR::word(i) = 32-bit word i
+ * of the stream; v[r] = (code - 2^(ind-1)) * val. */
 template <typename SR>
-ACM_HD void unpack_linear(const SR &sr, uint32_t P, uint32_t ind, const ColOut &o)
+ACM_HD void unpack_linear(const SR &sr, uint32_t P, uint32_t ind, int val, uint32_t (&v)[ROWS])
 {
 	const uint32_t mask = (1u << ind) - 1u;
-	const int mid = 1 << (ind - 1);
+	const uint32_t bias = (uint32_t)(-(1 << (ind - 1)) * val);
 	const uint32_t i = P >> 5, sh = P & 31u;
 	unsigned long long win = (((unsigned long long)sr.word(i + 1) << 32) | sr.word(i)) >> sh;
 	uint32_t avail = 64u - sh, nx = i + 3;
 	uint32_t nextw = sr.word(i + 2);
-	uint32_t w[8];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
 	for (int r = 0; r < ROWS; r++) {
-		const uint32_t v = (uint32_t)((int)((uint32_t)win & mask) - mid);
-		if (r & 1)
-			w[r >> 1] |= v << 16;
-		else
-			w[r >> 1] = v & 0xFFFFu;
+		v[r] = ((uint32_t)win & mask) * (uint32_t)val + bias;
 		win >>= ind;
 		avail -= ind;
 		if (avail <= 32u) {
@@ -217,8 +178,6 @@ ACM_HD void unpack_linear(const SR &sr, uint32_t P, uint32_t ind, const ColOut &
 			nx++;
 		}
 	}
-	store8(o.h0, w[0], w[1], w[2], w[3]);
-	store8(o.h1, w[4], w[5], w[6], w[7]);
 }
 
 } // namespace fast2

@@ -20,6 +20,10 @@ void acm_set_error(const char *fmt, ...);
 
 #ifdef __cplusplus
 struct acm_gpu_stream;
+/* acm_gpu_stream::status is an OUTPUT of every decode (and of acm_gpu_probe); what tells a probed,
+ * accepted stream from a rejected or never-probed one is its header fields: acm_gpu_probe leaves
+ * total_values = 0 in a rejected stream, and rows = 0 only in one it has never seen */
+bool acm_stream_accepted(const acm_gpu_stream *g);
 namespace acm { struct DevStream; }
 int acm_make_devstream(const acm_gpu_stream *g, uint32_t index, int pad_tail, acm::DevStream *d);
 #endif

@@ -117,6 +117,8 @@ void acm_read_plan(uint32_t total, uint32_t blen, uint32_t channels, uint32_t *w
 }
 
 
+bool acm_stream_accepted(const acm_gpu_stream *g) { return g->total_values != 0 && g->rows != 0; }
+
 /*
  * Device descriptor of one probed stream.  Returns ACM_OK, or the status the stream
  * gets without reaching the device.
@@ -128,8 +130,10 @@ int acm_make_devstream(const acm_gpu_stream *g, uint32_t index, int pad_tail, ac
 	uint64_t data_len = g->in_len > hdr ? g->in_len - hdr : 0;
 	uint32_t blen = g->rows << g->level;
 
-	if (g->status < 0 || g->total_values == 0 || g->rows == 0)
-		return g->status < 0 ? g->status : ACM_ERR_NOT_ACM;
+	/* the verdict of an earlier DECODE (-6, -7) must not keep a stream from being decoded again:
+	 * status is an output */
+	if (!acm_stream_accepted(g))
+		return ACM_ERR_NOT_ACM;
 	if (g->level > 15 || g->rows > 4095)
 		return ACM_ERR_NOT_ACM; /* not representable in the 4+12-bit header field */
 	/* bit positions are 32-bit on the device: images of 512 MiB and more are refused */

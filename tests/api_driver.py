@@ -87,26 +87,32 @@ class Handle:
         self.err, self.closed_on_fail = err.value, closed.value
         self.s = self.L.ref_stream(self.h) if self.h else None
 
+    def _stream(self):
+        if not self.s:
+            raise RuntimeError(f"stream is not open (open returned {self.err})")
+        return self.s
+
     def read(self, n, be=0, wordlen=2, sgned=1, loop=False, null=False):
+        self._stream()
         out = np.zeros(max(n, 1), np.uint8)
         f = self.L.acm_read_loop if loop else self.L.acm_read
         r = f(self.s, None if null else out.ctypes.data, n, be, wordlen, sgned)
         return r, (bytes(out[:r]) if r > 0 and not null else b"")
 
     def seek(self, pcm):
-        return self.L.acm_seek_pcm(self.s, pcm)
+        return self.L.acm_seek_pcm(self._stream(), pcm)
 
     def seek_time(self, ms):
-        return self.L.acm_seek_time(self.s, ms)
+        return self.L.acm_seek_time(self._stream(), ms)
 
     def state(self):
-        s = self.s.contents
+        s = self._stream().contents
         return dict(stream_pos=s.stream_pos, block_pos=s.block_pos, block_len=s.block_len,
                     total_values=s.total_values, data_len=s.data_len, wrapbuf_len=s.wrapbuf_len,
                     info={n: getattr(s.info, n) for n, _ in ACMInfo._fields_})
 
     def getters(self):
-        L, s = self.L, self.s
+        L, s = self.L, self._stream()
         return dict(rate=L.acm_rate(s), channels=L.acm_channels(s), raw_total=L.acm_raw_total(s),
                     pcm_total=L.acm_pcm_total(s), pcm_tell=L.acm_pcm_tell(s), time_total=L.acm_time_total(s),
                     time_tell=L.acm_time_tell(s), bitrate=L.acm_bitrate(s), seekable=L.acm_seekable(s))

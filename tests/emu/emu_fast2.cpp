@@ -77,30 +77,32 @@ extern "C" long emu_fast2_check(const uint8_t *img, uint32_t len)
 		for (uint32_t c = 0; c < 128; c++)
 			if (woff[c] != off[c])
 				return -(1000L * b + 3);
-		/* ---- the unpackers */
+		/* ---- the unpackers, fed like the kernel feeds them: the 96 stream bits at the payload */
 		WordReader sr{ &br };
 		for (uint32_t c = 0; c < 128; c++) {
-			const uint32_t Pc = P + off[c];
+			const uint32_t Pc = P + off[c], Pp = Pc + 5u;
 			const uint32_t ind = br.peek(Pc) & 31u, kind = tab.kind[ind], cls = kind & 7u, sub = kind >> 3;
 			int ref[16];
-			int16_t got[16];
-			uint32_t half0[4] = { 0, 0, 0, 0 }, half1[4] = { 0, 0, 0, 0 };
-			fast2::ColOut o{ half0, half1 };
-			const int rc = decode_column(br, Pc + 5u, limit, ind, kind, 16u, 1, ref, 1u, tab.k8, tab.t);
+			uint32_t got[16];
+			const int val = 1 + (int)((b * 131u + c * 7u) % 65535u);
+			const int rc = decode_column(br, Pp, limit, ind, kind, 16u, val, ref, 1u, tab.k8, tab.t);
+			const uint32_t lo = br.peek(Pp), mid = br.peek(Pp + 32u), hi = br.peek(Pp + 64u);
+			uint32_t a0 = 0u, a1 = 0u;
 			int bad = 0;
 			if (cls == ACM_CLS_K)
-				fast2::unpack_k(sr, Pc + 5u, sub, o, tab.k8w, tab.nib2w);
+				fast2::unpack_k(lo, mid, hi, sub, tab.k8w, a0, a1);
 			else if (cls == ACM_CLS_T)
-				bad = fast2::unpack_t(sr, Pc + 5u, limit, sub, o, tab.t, tab.nib2w, true);
-			else if (cls == ACM_CLS_LINEAR)
-				fast2::unpack_linear(sr, Pc + 5u, ind, o);
+				bad = fast2::unpack_t(lo, mid, Pp, limit, sub, tab.t, a0, a1);
+			if (cls == ACM_CLS_LINEAR)
+				fast2::unpack_linear(sr, Pp, ind, val, got);
+			else
+				for (int r = 0; r < 16; r++)
+					got[r] = fast2::nib_val(r < 8 ? a0 : a1, r & 7, val);
 			if ((rc == -6) != (bad != 0))
 				return -(1000L * b + 4);
-			memcpy(got, half0, 16);
-			memcpy(got + 8, half1, 16);
 			if (!bad)
 				for (int r = 0; r < 16; r++)
-					if ((int)got[r] != ref[r])
+					if (got[r] != (uint32_t)ref[r])
 						return -(1000L * b + 5);
 		}
 		P = sc.end;

@@ -26,7 +26,7 @@ def test_exports_every_declared_symbol():
 
 
 def test_abi_version_and_struct_sizes():
-    assert api.lib().acm_gpu_abi_version() == 1
+    assert api.lib().acm_gpu_abi_version() == 2
     assert C.sizeof(api.Opts) == 64
     assert api.STREAM_DTYPE.itemsize == 72
 

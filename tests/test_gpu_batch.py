@@ -298,3 +298,50 @@ def test_healthy_streams_never_take_the_re_walk_path(checker):
     plan.fetch(s, torch.cuda.current_stream().cuda_stream)
     assert int(plan.counters()[32]) == 1
     plan.close()
+
+
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_decode_twice_same_stream_array(checker, kernel):
+    """acm_gpu_stream.status is an output: a stream array that has been through a decode -- with
+    streams that ended ACM_ERR_CORRUPT (-6), ACM_ERR_UNEXPECTED_EOF (-7) and a rejected header (-3)
+    -- decodes to the very same bytes, statuses and word counts when handed in again."""
+    good = corpus.images(corpus.fallout_params(6, seed=5, hi=30_000))
+    bad = corpus.images(corpus.negative_params())
+    # a cut that lands inside a filler payload ends ACM_ERR_UNEXPECTED_EOF (most cuts do; the
+    # reference decides which)
+    cut7 = next(bytes(good[0])[:n] for n in range(len(good[0]) * 3 // 5, len(good[0]))
+                if checker.decode(bytes(good[0])[:n]).status == -7)
+    cut = [cut7, bytes(good[1])[:9]]
+    imgs = good + bad + cut
+    blob, offs, lens = gu.pack(imgs)
+    opts = api.make_opts(want_checksums=1, kernel=kernel)
+    s = api.new_streams(offs, lens)
+    api.probe(blob, s, opts)
+    nbytes = api.layout(s, 2)
+    out1 = np.full(nbytes, 0xAA, np.uint8)
+    api.decode_batch(blob, s, out1, opts)
+    first = s.copy()
+    assert {0, -3, -6, -7} <= set(first["status"].tolist())
+    assert gu.compare(imgs, s, out1, checker, checksums=True) == []
+    out2 = np.full(nbytes, 0x55, np.uint8)
+    api.decode_batch(blob, s, out2, opts)             # same array, statuses now hold the first verdicts
+    for f in ("status", "words", "checksum"):
+        assert np.array_equal(s[f], first[f]), f
+    assert gu.compare(imgs, s, out2, checker, checksums=True) == []
+
+
+def test_out_buffer_of_exactly_the_layout_size():
+    """`out` has to hold acm_gpu_layout() bytes -- every slot ends on a 16-byte boundary that the
+    kernels zero-fill up to -- and a buffer one byte short of the last slot is refused, not overrun."""
+    imgs = corpus.images(corpus.fallout_params(5, seed=8, lo=3_001, hi=9_000))
+    blob, offs, lens = gu.pack(imgs)
+    opts = api.make_opts()
+    s = api.new_streams(offs, lens)
+    api.probe(blob, s, opts)
+    nbytes = api.layout(s, 2)
+    assert int(s["total_values"][-1]) * 2 % 16 != 0
+    guard = np.full(nbytes + 64, 0x77, np.uint8)
+    api.decode_batch(blob, s, guard[:nbytes], opts)
+    assert np.all(s["status"] == 0) and np.all(guard[nbytes:] == 0x77)
+    with pytest.raises(Exception):
+        api.decode_batch(blob, s, guard[:nbytes - 1], opts)

@@ -45,5 +45,6 @@ if os.environ.get("F2_PROF"):
     print("scan  busiest warp %.2f Mcycles, max rounds/warp %.0f, rounds %.0f, periods %.0f (x runs)" %
           (buf[16] / 1e6, buf[17], buf[18] / args.runs, buf[19] / args.runs))
     print("work  Mcycles/run (all warps): decode %.1f idle %.1f claim %.1f" % tuple(v[8:11]))
+    print("work  phases Mcycles/run: record %.1f stage-wait %.1f unpack %.1f copy+dequant %.1f transform %.1f rest %.1f" % tuple(v[24:30]))
 plan.fetch(s, cs)
 assert np.all(s["status"] == 0)
