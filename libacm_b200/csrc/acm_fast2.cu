@@ -101,6 +101,12 @@ constexpr int RROW = 32 * SW;            /* words per ring row: one word of ever
 #ifndef F2_CARRY
 #define F2_CARRY 1
 #endif
+#ifndef F2_UNPACK4
+#define F2_UNPACK4 0 /* 1: a lane walks its four columns together (four independent chains) */
+#endif
+#ifndef F2_S37_UNROLL
+#define F2_S37_UNROLL 1 /* lifting stages 3..7 in pairs of pieces (0: a loop of single pieces) */
+#endif
 #ifndef F2_NHOLD
 #define F2_NHOLD 2
 #endif
@@ -116,10 +122,9 @@ constexpr int HIST_WORDS = 256;          /* per slot: X0 tail [0,128) X1 tail [1
 #define F2_KMAX 8
 #endif
 constexpr int KMAX = F2_KMAX;            /* blocks a worker decodes per visit of a slot */
-constexpr int OWN = MAXOWN / W;          /* slots a worker warp can own (lane k holds the state of the k-th) */
 
 static_assert((XWORDS * 4) % 16 == 0 && (WB_WORDS * 4) % 16 == 0, "bulk copies need 16-byte aligned staging");
-static_assert(OWN <= 32 && MAXOWN % W == 0, "a worker warp keeps one slot per lane");
+static_assert(MAXOWN == 128, "the slot scan reads four groups of 32 lock bits");
 static_assert((RW & (RW - 1)) == 0 && RW % 4 == 0, "the scan ring is a power of two of words, whole 16-byte chunks");
 static_assert(LEAD + 2 <= RW / 4, "the chunk being read and the one after it are never re-requested");
 static_assert(SW <= W, "scan CTAs are launched with the decode CTAs' thread count");
@@ -140,9 +145,14 @@ struct Rec {
  * that owns the slot */
 struct SlotCtl {
 	uint32_t prod; /* records published (scan lane writes) */
-	uint32_t cons; /* records consumed (decode CTA writes) */
+	uint32_t rem;  /* blocks the stream being walked still has to go (scan lane writes, with prod) */
+	uint32_t cons; /* records consumed (decode warp writes) */
 	uint32_t dead; /* desc+1 of a stream the decode side finalised early */
+	/* second half: the decode side's running state of the slot, handed from one worker warp to the
+	 * next under the slot's lock (a bit of SmemWork::busy) */
+	uint32_t pos;  /* words delivered so far of the slot's current stream */
 	uint32_t pad;
+	unsigned long long cks;
 };
 
 constexpr int OFFP = 2 * COLS + 8; /* bytes per lane of the column-offset staging (+8: bank spread, 8-byte rows) */
@@ -160,6 +170,7 @@ struct SmemWork {
 	uint64_t k8w[ACM_K8_SIZE];
 	uint32_t wb[W][WB_WORDS];
 	unsigned long long mbar[W]; /* one transaction barrier per worker warp (bulk-copy staging) */
+	uint32_t busy[MAXOWN / 32]; /* bit j: local slot j is being decoded by some worker warp */
 	uint32_t info[32];
 	uint16_t t[ACM_T_SIZE];
 };
@@ -249,24 +260,6 @@ __device__ __forceinline__ unsigned long long now_ns()
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
 	return t;
-}
-
-/* selector facts: bit 16 prefix-coded (k), bit 17 bad, bit 18 t, bit 19 linear, bits 20..23 sub-type */
-enum { INF_K = 1u << 16, INF_BAD = 1u << 17, INF_T = 1u << 18, INF_LIN = 1u << 19 };
-
-__device__ __forceinline__ uint32_t make_info(uint32_t kind)
-{
-	const uint32_t cls = kind & 7u, sub = kind >> 3;
-	uint32_t v = sub << 20;
-	if (cls == ACM_CLS_LINEAR)
-		v |= INF_LIN;
-	else if (cls == ACM_CLS_T)
-		v |= INF_T;
-	else if (cls == ACM_CLS_K)
-		v |= INF_K;
-	else if (cls == ACM_CLS_BAD)
-		v |= INF_BAD;
-	return v;
 }
 
 /* ------------------------------------------------------------------ scan */
@@ -460,12 +453,113 @@ __device__ __forceinline__ uint32_t lift(uint32_t a, uint32_t p1, uint32_t p2, b
 	return odd ? 2u * p1 - s : 2u * p1 + s;
 }
 
-/* pack two results into one 32-bit word of 16-bit PCM: (v >> 7) low 16 bits each */
+/*
+ * Everything the transform touches is carried times 2^QS (QS = 16 - LEVEL): the dequantisation
+ * multiplies by val << QS, the stage-1 "+1" is 1 << QS.  The lifting is linear modulo 2^32
+ * (decode.c:512: unsigned arithmetic), so a result is the reference's times 2^QS modulo 2^32,
+ * and the 16 bits the output wants -- bits LEVEL..LEVEL+15 of the reference's word, decode.c:620 --
+ * are its top half: packing two results is ONE byte permute instead of two shifts and a permute.
+ */
+constexpr int QS = 16 - LEVEL;
+
+/* pack two results into one 32-bit word of 16-bit PCM: the top halves of a and b */
 __device__ __forceinline__ uint32_t pack2(uint32_t a, uint32_t b, uint32_t sel, uint32_t flip)
 {
-	uint32_t lo = (uint32_t)((int32_t)a >> LEVEL); /* bytes 0,1 wanted */
-	uint32_t hi = b << (16 - LEVEL);               /* bytes 2,3 wanted */
-	return __byte_perm(lo, hi, sel) ^ flip;
+	return __byte_perm(a, b, sel) ^ flip;
+}
+
+/*
+ * One 16-word piece (window words t = 16 K .. 16 K + 15) of lifting stages 3..7.  Stage 3 runs
+ * from K = 2, stages 4-6 (S46) from K = 3, stage 7 and the output (OUT) from K = 4; ODD = K & 1 is
+ * the row parity of stage 3.  P1 = the stage-3 inputs of piece K - 1, A3..A6 = what the later
+ * stages need of piece K - 1; all are replaced by this piece's.  The caller runs the pieces in
+ * pairs (even, odd): within a pair nothing is copied, the stage-3 sign is a constant, and only
+ * one set of carried values crosses the loop's back edge (a loop of single pieces copies 46
+ * registers per piece; six pieces in a row are 16 KB of code and fall out of the instruction
+ * cache: measured, profiles/r02_decode.md).
+ */
+template <int ODD, bool S46, bool OUT, bool CKS>
+__device__ __forceinline__ void s37_piece(const int K, const uint32_t *win, uint32_t (&P1)[16], uint32_t (&A3)[16],
+					  uint32_t (&A4)[8], uint32_t (&A5)[4], uint32_t (&A6)[2], uint4 *dst, bool full,
+					  uint32_t n, int lane, uint32_t pos0, uint32_t sel, uint32_t flip, uint32_t bias,
+					  unsigned long long &cks)
+{
+	/* word t of the window lives at t + (t >= 64 ? 4 : 0) */
+	const uint4 *p0 = reinterpret_cast<const uint4 *>(win + 16 * K + (K >= 4 ? 4 : 0));
+	const uint4 *p2 = reinterpret_cast<const uint4 *>(win + 16 * (K - 2) + (K >= 6 ? 4 : 0));
+	uint32_t a3[16], c0[16];
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const uint4 v0 = p0[q], v2 = p2[q];
+		c0[4 * q] = v0.x; c0[4 * q + 1] = v0.y; c0[4 * q + 2] = v0.z; c0[4 * q + 3] = v0.w;
+		/* C = 16 (decode.c:518-519): 2*in[t-16] +- (in[t] + in[t-32]); row parity = K & 1 */
+		a3[4 * q + 0] = lift(v0.x, P1[4 * q + 0], v2.x, ODD);
+		a3[4 * q + 1] = lift(v0.y, P1[4 * q + 1], v2.y, ODD);
+		a3[4 * q + 2] = lift(v0.z, P1[4 * q + 2], v2.z, ODD);
+		a3[4 * q + 3] = lift(v0.w, P1[4 * q + 3], v2.w, ODD);
+	}
+	if (S46) {
+		uint32_t a4[16], a5[16], a6[16];
+#pragma unroll
+		for (int j = 0; j < 16; j++) /* C = 8 */
+			a4[j] = lift(a3[j], j >= 8 ? a3[j - 8] : A3[j + 8], A3[j], (j >> 3) & 1);
+#pragma unroll
+		for (int j = 0; j < 16; j++) /* C = 4 */
+			a5[j] = lift(a4[j], j >= 4 ? a4[j - 4] : A4[j + 4], j >= 8 ? a4[j - 8] : A4[j], (j >> 2) & 1);
+#pragma unroll
+		for (int j = 0; j < 16; j++) /* C = 2 */
+			a6[j] = lift(a5[j], j >= 2 ? a5[j - 2] : A5[j + 2], j >= 4 ? a5[j - 4] : A5[j], (j >> 1) & 1);
+		if (OUT) {
+			uint32_t pk[8];
+#pragma unroll
+			for (int j = 0; j < 16; j += 2) { /* C = 1 */
+				const uint32_t v0 = lift(a6[j], j >= 1 ? a6[j - 1] : A6[1], j >= 2 ? a6[j - 2] : A6[0], 0);
+				const uint32_t v1 = lift(a6[j + 1], a6[j], j >= 1 ? a6[j - 1] : A6[1], 1);
+				pk[j >> 1] = pack2(v0, v1, sel, flip);
+				if (CKS) {
+					/* u_i as an unsigned 16-bit value, independent of byte order */
+					const uint32_t m = pos0 + 64u * lane + 16u * (uint32_t)(K - 4) + (uint32_t)j;
+					const uint32_t w0 = ((v0 >> 16) + bias) & 0xFFFFu;
+					const uint32_t w1 = ((v1 >> 16) + bias) & 0xFFFFu;
+					if (m - pos0 < n)
+						cks += (unsigned long long)(m + 1u) * (w0 + 1ull);
+					if (m + 1u - pos0 < n)
+						cks += (unsigned long long)(m + 2u) * (w1 + 1ull);
+				}
+			}
+			const int q = 2 * (K - 4);
+			if (full) {
+				/* streaming stores: PCM is written once and must not evict the L2-resident
+				 * history, records and compressed bytes */
+				__stcs(dst + q, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+				__stcs(dst + q + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+			} else {
+				/* last block of a stream: word-granular tail */
+				uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + q);
+#pragma unroll 1
+				for (int e = 0; e < 16; e++) {
+					const uint32_t m = 64u * lane + 8u * q + e;
+					const uint32_t w = e < 8 ? (e < 4 ? (e < 2 ? pk[0] : pk[1]) : (e < 6 ? pk[2] : pk[3]))
+								 : (e < 12 ? (e < 10 ? pk[4] : pk[5]) : (e < 14 ? pk[6] : pk[7]));
+					if (m < n)
+						d16[e] = (uint16_t)(w >> (16 * (e & 1)));
+				}
+			}
+		}
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+			A4[j] = a4[8 + j];
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+			A5[j] = a5[12 + j];
+		A6[0] = a6[14];
+		A6[1] = a6[15];
+	}
+#pragma unroll
+	for (int j = 0; j < 16; j++) {
+		A3[j] = a3[j];
+		P1[j] = c0[j];
+	}
 }
 
 /*
@@ -507,16 +601,17 @@ juggle_and_store(uint32_t (&x)[64], const Hist &h, uint32_t *xs0, uint32_t *gh, 
 #pragma unroll
 	for (int k = 0; k < 4; k++)
 		__stcg(gh + 32 * k + lane, x[60 + k]);
-	const uint32_t one0 = lane == 0 ? 1u : 0u; /* decode.c:561-564: +1 where m % 64 == 0 */
+	/* decode.c:561-564: +1 where m % 64 == 0, i.e. lane 0, even i; it rides in the lift's first add */
+	const uint32_t one0 = lane == 0 ? 1u << QS : 0u;
 	uint32_t y[64];
 #pragma unroll
 	for (int i = 0; i < 64; i++) {
 		/* C = 64: m-64 -> i-2, m-128 -> i-4; row parity = (m/64)&1 = (i>>1)&1 */
-		uint32_t p1 = i >= 2 ? x[i - 2] : hx[i + 2];
-		uint32_t p2 = i >= 4 ? x[i - 4] : hx[i];
-		y[i] = lift(x[i], p1, p2, (i >> 1) & 1);
-		if ((i & 1) == 0)
-			y[i] += one0;
+		const uint32_t p1 = i >= 2 ? x[i - 2] : hx[i + 2];
+		const uint32_t p2 = i >= 4 ? x[i - 4] : hx[i];
+		const bool odd = (i >> 1) & 1;
+		const uint32_t sum = (i & 1) ? x[i] + p2 : odd ? x[i] + p2 - one0 : x[i] + p2 + one0;
+		y[i] = odd ? 2u * p1 - sum : 2u * p1 + sum;
 	}
 	__stcg(gh + 128 + lane, y[62]);
 	__stcg(gh + 160 + lane, y[63]);
@@ -549,7 +644,7 @@ juggle_and_store(uint32_t (&x)[64], const Hist &h, uint32_t *xs0, uint32_t *gh, 
 	 * (A3: its 16 stage-3 outputs, A4: its last 8 stage-4 outputs, A5: 4, A6: 2).  A stage is
 	 * only run where its inputs are complete: stage 3 from t = 32, stages 4-6 from t = 48,
 	 * stage 7 (= the output) from t = 64. */
-	const uint32_t sel = fmt.be ? 0x6701u : 0x7610u;
+	const uint32_t sel = fmt.be ? 0x6723u : 0x7632u;
 	const uint32_t flip = fmt.bias ? (fmt.be ? 0x00800080u : 0x80008000u) : 0u;
 	const bool full = (uint32_t)(64 * lane + 64) <= n;
 	uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)pos0 + 64u * lane) * 2u);
@@ -563,6 +658,23 @@ juggle_and_store(uint32_t (&x)[64], const Hist &h, uint32_t *xs0, uint32_t *gh, 
 		A4[j] = 0u;
 	A5[0] = A5[1] = A5[2] = A5[3] = 0u;
 	A6[0] = A6[1] = 0u;
+#if F2_S37_UNROLL
+	{
+		uint32_t P1[16]; /* the inputs of piece k - 1 */
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const uint4 v = reinterpret_cast<const uint4 *>(win + 16)[q];
+			P1[4 * q] = v.x; P1[4 * q + 1] = v.y; P1[4 * q + 2] = v.z; P1[4 * q + 3] = v.w;
+		}
+		s37_piece<0, false, false, CKS>(2, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+		s37_piece<1, true, false, CKS>(3, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+#pragma unroll 1
+		for (int k = 4; k < 8; k += 2) {
+			s37_piece<0, true, true, CKS>(k, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+			s37_piece<1, true, true, CKS>(k + 1, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+		}
+	}
+#else
 #if F2_CARRY >= 1
 	uint32_t P1[16]; /* the inputs of piece k - 1 */
 #pragma unroll
@@ -632,8 +744,8 @@ juggle_and_store(uint32_t (&x)[64], const Hist &h, uint32_t *xs0, uint32_t *gh, 
 					if (CKS) {
 						/* u_i as an unsigned 16-bit value, independent of byte order */
 						const uint32_t m = pos0 + 64u * lane + 16u * (uint32_t)(k - 4) + (uint32_t)j;
-						const uint32_t w0 = (((uint32_t)((int32_t)v0 >> LEVEL)) + fmt.bias) & 0xFFFFu;
-						const uint32_t w1 = (((uint32_t)((int32_t)v1 >> LEVEL)) + fmt.bias) & 0xFFFFu;
+						const uint32_t w0 = ((v0 >> 16) + fmt.bias) & 0xFFFFu;
+						const uint32_t w1 = ((v1 >> 16) + fmt.bias) & 0xFFFFu;
 						if (m - pos0 < n)
 							cks += (unsigned long long)(m + 1u) * (w0 + 1ull);
 						if (m + 1u - pos0 < n)
@@ -670,6 +782,7 @@ juggle_and_store(uint32_t (&x)[64], const Hist &h, uint32_t *xs0, uint32_t *gh, 
 		for (int j = 0; j < 16; j++)
 			A3[j] = a3[j];
 	}
+#endif
 	__syncwarp(); /* all shared-memory reads of this block are done */
 	return cks;
 }
@@ -683,6 +796,16 @@ struct Stage {
 	__device__ __forceinline__ uint32_t word(uint32_t i) const { return st[i - w_lo]; }
 };
 
+__device__ __forceinline__ uint2 vol_ld2(const uint32_t *p)
+{
+	uint2 v;
+	asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void vol_st2(uint32_t *p, uint32_t x, uint32_t y)
+{
+	asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire(const uint32_t *p)
 {
 	uint32_t v;
@@ -830,46 +953,102 @@ __device__ __forceinline__ void decode_visit(SmemWork &sm, const KernelArgs &a, 
 			Stage sr;
 			sr.st = stage;
 			sr.w_lo = c_lo * 4u;
-			/* ---- unpack: four passes of 32 columns.  Prefix- and radix-coded (and zero) columns
-			 * leave the pass as sixteen nibbles in two registers (A0 / A1 of that pass); the sixteen
-			 * words of a linear column are parked in the lane's own words of the transpose buffer
-			 * (word 32 i + lane, i = 4 r + p: conflict-free, nobody else touches them).  One copy of
-			 * the code: the loop is not unrolled. */
+#if F2_UNPACK4
+			/* ---- unpack the lane's four columns (32 p + lane).  Prefix- and radix-coded (and zero)
+			 * columns become sixteen nibbles in two registers (A0[p] / A1[p]), all four columns
+			 * advancing together (independent chains); the sixteen words of a linear column are
+			 * parked in the lane's own words of the transpose buffer (word 32 i + lane, i = 4 r + p:
+			 * conflict-free, nobody else touches them). */
+			uint32_t lo[4], mid[4], hi[4], cls[4], sub[4], Pp[4], ind[4];
+#pragma unroll
+			for (int p = 0; p < 4; p++) {
+				const uint32_t col = 32u * (uint32_t)p + (uint32_t)lane;
+				const uint32_t Pc = e.pblock + offs[p], iw = Pc >> 5;
+				Pp[p] = Pc + 5u; /* payload */
+				cls[p] = ACM_CLS_ZERO;
+				sub[p] = 0u;
+				ind[p] = 0u;
+				lo[p] = mid[p] = hi[p] = 0u;
+				A0[p] = A1[p] = 0u; /* f_zero decode.c:181-188: all rows zero */
+				if (col < ncheck) {
+					const uint32_t w0 = sr.word(iw), w1 = sr.word(iw + 1), w2 = sr.word(iw + 2),
+						       w3 = sr.word(iw + 3), w4 = sr.word(iw + 4);
+					ind[p] = __funnelshift_r(w0, w1, Pc) & 31u;
+					const uint32_t kind = sm.info[ind[p]];
+					cls[p] = kind & 7u;
+					sub[p] = kind >> 3;
+					const bool up = (Pc & 31u) + 5u >= 32u; /* the payload starts in the next word */
+					const uint32_t v0 = up ? w1 : w0, v1 = up ? w2 : w1, v2 = up ? w3 : w2, v3 = up ? w4 : w3;
+					lo[p] = __funnelshift_r(v0, v1, Pp[p]);
+					mid[p] = __funnelshift_r(v1, v2, Pp[p]);
+					hi[p] = __funnelshift_r(v2, v3, Pp[p]);
+				}
+			}
+			bad |= unpack_t4(lo, mid, Pp, limit_w, cls, sub, sm.t, A0, A1);
+			if (ok) {
+				unpack_k4(lo, mid, hi, cls, sub, sm.k8w, A0, A1);
+#pragma unroll
+				for (int p = 0; p < 4; p++) {
+					const bool isl = cls[p] == ACM_CLS_LINEAR;
+#pragma unroll 1
+					for (uint32_t t = __any_sync(0xFFFFFFFFu, isl) ? 1u : 0u; t; t--) { /* a real branch */
+						if (isl) {
+							uint32_t v[ROWS];
+							unpack_linear(sr, Pp[p], ind[p], e.val << QS, v);
+#pragma unroll
+							for (int r = 0; r < ROWS; r++)
+								wb[32 * (4 * r + p) + lane] = v[r];
+						}
+						__syncwarp();
+						linmask |= (isl ? 1u : 0u) << p;
+						linany |= 1u << p;
+					}
+				}
+			}
+#else
+			/* ---- unpack: four passes of 32 columns (pass p: column 32 p + lane).  Prefix- and
+			 * radix-coded (and zero) columns leave the pass as sixteen nibbles in two registers
+			 * (A0[p] / A1[p]); the sixteen words of a linear column are parked in the lane's own
+			 * words of the transpose buffer (word 32 i + lane, i = 4 r + p: conflict-free, nobody
+			 * else touches them).  One copy of the code: the loop is not unrolled.  (Walking the
+			 * lane's four columns together, F2_UNPACK4, costs more instructions than it hides
+			 * latency: the decode SMs are bound by instruction issue, profiles/r02_decode.md.) */
 #pragma unroll 1
 			for (int p = 0; p < 4; p++) {
 				const uint32_t col = 32u * (uint32_t)p + (uint32_t)lane;
 				const uint32_t off = p == 0 ? offs[0] : p == 1 ? offs[1] : p == 2 ? offs[2] : offs[3];
-				uint32_t inf = 0u, ind = 0u, lo = 0u, mid = 0u, hi = 0u;
+				uint32_t cls = ACM_CLS_ZERO, sub = 0u, ind = 0u, lo = 0u, mid = 0u, hi = 0u;
 				const uint32_t P = e.pblock + off + 5u; /* payload */
 				if (col < ncheck) {
 					const uint32_t Pc = e.pblock + off, iw = Pc >> 5;
 					const uint32_t w0 = sr.word(iw), w1 = sr.word(iw + 1), w2 = sr.word(iw + 2),
 						       w3 = sr.word(iw + 3), w4 = sr.word(iw + 4);
 					ind = __funnelshift_r(w0, w1, Pc) & 31u;
-					inf = sm.info[ind];
+					const uint32_t kind = sm.info[ind];
+					cls = kind & 7u;
+					sub = kind >> 3;
 					const bool up = (Pc & 31u) + 5u >= 32u; /* the payload starts in the next word */
 					const uint32_t v0 = up ? w1 : w0, v1 = up ? w2 : w1, v2 = up ? w3 : w2, v3 = up ? w4 : w3;
 					lo = __funnelshift_r(v0, v1, P);
 					mid = __funnelshift_r(v1, v2, P);
 					hi = __funnelshift_r(v2, v3, P);
 				}
-				const bool isk = (inf & INF_K) != 0u, ist = (inf & INF_T) != 0u, isl = (inf & INF_LIN) != 0u;
+				const bool isk = cls == ACM_CLS_K, ist = cls == ACM_CLS_T, isl = cls == ACM_CLS_LINEAR;
 				uint32_t a0 = 0u, a1 = 0u; /* f_zero decode.c:181-188: all rows zero */
 				if (ok && __any_sync(0xFFFFFFFFu, isk)) {
 					if (isk)
-						unpack_k(lo, mid, hi, inf >> 20, sm.k8w, a0, a1);
+						unpack_k(lo, mid, hi, sub, sm.k8w, a0, a1);
 					__syncwarp();
 				}
 				if (__any_sync(0xFFFFFFFFu, ist)) {
 					if (ist)
-						bad |= unpack_t(lo, mid, P, limit_w, inf >> 20, sm.t, a0, a1);
+						bad |= unpack_t(lo, mid, P, limit_w, sub, sm.t, a0, a1);
 					__syncwarp();
 				}
-				const uint32_t ml = __ballot_sync(0xFFFFFFFFu, ok && isl);
-				if (ml) {
+				if (ok && __any_sync(0xFFFFFFFFu, isl)) {
 					if (isl) {
 						uint32_t v[ROWS];
-						unpack_linear(sr, P, ind, e.val, v);
+						unpack_linear(sr, P, ind, e.val << QS, v);
 #pragma unroll
 						for (int r = 0; r < ROWS; r++)
 							wb[32 * (4 * r + p) + lane] = v[r];
@@ -888,6 +1067,7 @@ __device__ __forceinline__ void decode_visit(SmemWork &sm, const KernelArgs &a, 
 					A0[3] = a0; A1[3] = a1;
 				}
 			}
+#endif
 		}
 		bad = __any_sync(0xFFFFFFFFu, bad);
 		PROF_MARK(2);
@@ -909,13 +1089,13 @@ __device__ __forceinline__ void decode_visit(SmemWork &sm, const KernelArgs &a, 
 			if (n > (uint32_t)BLEN)
 				n = BLEN;
 			uint8_t *out = a.out + d.out_off;
-			/* dequantise (set_pos + midbuf, decode.c:174-177, :591-600): x[i] = word m = 32 i + lane */
+			/* dequantise (set_pos + midbuf, decode.c:174-177, :591-600), times 2^QS: x[i] = word m = 32 i + lane */
 			uint32_t x[64];
 #pragma unroll
 			for (int p = 0; p < 4; p++) {
 #pragma unroll
 				for (int r = 0; r < ROWS; r++)
-					x[4 * r + p] = nib_val(r < 8 ? A0[p] : A1[p], r & 7, e.val);
+					x[4 * r + p] = nib_val(r < 8 ? A0[p] : A1[p], r & 7, e.val << QS);
 			}
 			if (linany) {
 				/* pick up the parked linear columns; real branches (a loop of one turn per pass with
@@ -1008,8 +1188,8 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		if (enabled) {
 			/* never a stale line; after a walk, the copy fetched while walking */
 			const uint4 c4 = fresh ? c4n : __ldcv(reinterpret_cast<const uint4 *>(ctl));
-			cons = c4.y;
-			dead = c4.z;
+			cons = c4.z;
+			dead = c4.w;
 		}
 		fresh = false;
 		if (active && dead == cur + 1u) {
@@ -1179,8 +1359,13 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 		}
 		/* the records are in L2 before they are announced to the decode CTA (another SM) */
 		__threadfence();
-		if (can)
-			vol_st(&ctl->prod, ++prodn);
+		if (can) {
+			/* one 8-byte store: the count, and how far the stream still has to go -- the decode
+			 * warp serves the slot with the longest way to go first, so that the batch's longest
+			 * streams (its critical path) never wait for ring space */
+			const uint32_t rem = active ? n_attempt - blk : 0u;
+			vol_st2(&ctl->prod, ++prodn, rem);
+		}
 	}
 	__threadfence();
 	PROF_FLUSH(0);
@@ -1199,41 +1384,50 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 
 /*
  * Decode CTA number w of n_work owns the slots g = w, w + n_work, w + 2 n_work, ... (local index
- * j), and within the CTA worker warp v owns the local indices j = v, v + W, ...: at most OWN slots,
- * the state of the k-th one (records consumed, words delivered, checksum) lives in the registers
- * of lane k.  Fixed ownership: no locks, no shared-memory hand-over, and polling for work is one
- * load per lane.  A worker visits the owned slot with the largest backlog and decodes up to KMAX
- * of its records in order.
+ * j < MAXOWN); any of its worker warps may decode any of them, one warp per slot at a time (a
+ * slot's blocks depend on each other through the transform history).  Looking for work is one
+ * 16-byte load per lane and owned slot group (prod and cons sit side by side in SlotCtl) and one
+ * shared-memory atomic for the 128 lock bits; the slot's running state (words delivered,
+ * checksum) lives in the second half of its SlotCtl in global memory.  A worker takes the free
+ * slot with the largest backlog and decodes up to KMAX of its records in order.
  */
 template <bool CKS>
 __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int warp, int lane)
 {
 	const uint32_t w = (uint32_t)blockIdx.x - a.n_scan, n_work = (uint32_t)gridDim.x - a.n_scan;
 	const uint32_t J = a.n_slots > w ? (a.n_slots - w + n_work - 1u) / n_work : 0u; /* the CTA's slots */
-	const uint32_t jmine = (uint32_t)warp + (uint32_t)W * (uint32_t)lane;
-	const bool own = lane < OWN && jmine < J;
-	const uint32_t g = own ? w + n_work * jmine : 0u;
 	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl);
 	uint32_t *wb = sm.wb[warp];
 	const uint32_t mbar = (uint32_t)__cvta_generic_to_shared(&sm.mbar[warp]);
 	uint32_t mphase = 0u;
-	/* lane k: the k-th owned slot */
-	uint32_t cons = 0u, pos = 0u, dead = 0u;
-	unsigned long long cks = 0ull;
 	uint32_t nap = 64u;
 	bool confirmed = false;
 	unsigned long long waiting_since = 0ull;
 	uint32_t seen_hb = 0;
 	PROF_DECL;
-	if (!__any_sync(0xFFFFFFFFu, own))
+	if (J == 0u)
 		return;
 	for (;;) {
 		PROF_MARK(0); /* 8+0: decode */
 		const bool done = *reinterpret_cast<volatile uint32_t *>(a.scan_done) == a.n_scan * (uint32_t)SW;
-		const uint32_t backlog = own ? vol_ld(&ctl[g].prod) - cons : 0u;
-		/* largest backlog first: the slots of the longest streams are the ones that fall behind
-		 * while decoding is the bottleneck, and a slot's records are decoded one after the other */
-		const uint32_t best = __reduce_max_sync(0xFFFFFFFFu, backlog ? (backlog << 5) | (uint32_t)lane : 0u);
+		/* the free owned slot with the largest backlog: best = backlog << 8 | local index (0: none).
+		 * Largest first: the slots of the longest streams are the ones that fall behind while
+		 * decoding is the bottleneck, and whatever backlog they have when the scan ends is the
+		 * launch's tail. */
+		const uint32_t bw = atomicOr(&sm.busy[lane & (MAXOWN / 32 - 1)], 0u);
+		uint32_t best = 0u;
+#pragma unroll
+		for (int k = 0; k < MAXOWN / 32; k++) {
+			const uint32_t j = (uint32_t)lane + 32u * k;
+			const uint32_t busyk = __shfl_sync(0xFFFFFFFFu, bw, k);
+			if (j < J && !((busyk >> lane) & 1u)) {
+				const uint4 c4 = __ldcv(reinterpret_cast<const uint4 *>(&ctl[w + n_work * j]));
+				const uint32_t backlog = c4.x - c4.z;
+				const uint32_t key = backlog ? ((backlog < 0xFFFFu ? backlog : 0xFFFFu) << 8) | j : 0u;
+				best = key > best ? key : best;
+			}
+		}
+		best = __reduce_max_sync(0xFFFFFFFFu, best);
 		if (!best) {
 			if (done) {
 				/* every scan warp has finished: look once more behind a fence (acquire: all
@@ -1263,29 +1457,37 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		nap = 64u;
 		confirmed = false;
 		waiting_since = 0ull;
-		const int k = (int)(best & 31u);
-		const uint32_t gk = __shfl_sync(0xFFFFFFFFu, g, k);
-		uint32_t c = __shfl_sync(0xFFFFFFFFu, cons, k);
-		uint32_t ps = __shfl_sync(0xFFFFFFFFu, pos, k);
-		uint32_t dd = __shfl_sync(0xFFFFFFFFu, dead, k);
-		unsigned long long ck = __shfl_sync(0xFFFFFFFFu, cks, k);
-		/* acquire: the records behind prod (the poll above was a plain load) */
-		uint32_t nrec = ld_acquire(&ctl[gk].prod) - c;
+		const uint32_t j = best & 255u, bit = 1u << (j & 31u);
+		uint32_t got = 0;
+		if (lane == 0)
+			got = (atomicOr(&sm.busy[j >> 5], bit) & bit) == 0u;
+		got = __shfl_sync(0xFFFFFFFFu, got, 0);
+		if (!got)
+			continue; /* another warp was quicker */
+		PROF_MARK(2); /* 8+2: claim */
+		const uint32_t g = w + n_work * j;
+		/* acquire: the slot's state as the previous holder left it, and the records behind prod */
+		uint32_t c = ld_acquire(&ctl[g].cons);
+		uint32_t nrec = ld_acquire(&ctl[g].prod) - c;
+		uint32_t ps = __ldcv(&ctl[g].pos);
+		uint32_t dd = __ldcv(&ctl[g].dead);
+		unsigned long long ck = __ldcv(&ctl[g].cks);
 		if (nrec > (uint32_t)KMAX)
 			nrec = KMAX;
 		if (lane == 0)
 			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
-		decode_visit<CKS>(sm, a, wb, mbar, mphase, lane, a.ring + (size_t)gk * RING_D * REC_BYTES, c, nrec,
-				  a.hist + (size_t)gk * HIST_WORDS, ctl + gk, ps, ck, dd);
+		decode_visit<CKS>(sm, a, wb, mbar, mphase, lane, a.ring + (size_t)g * RING_D * REC_BYTES, c, nrec,
+				  a.hist + (size_t)g * HIST_WORDS, ctl + g, ps, ck, dd);
 		c += nrec;
 		__syncwarp();
-		if (lane == k) {
-			cons = c;
-			pos = ps;
-			dead = dd;
-			cks = ck;
-			/* release: the records have been read before the scan lane may overwrite them */
+		if (lane == 0) {
+			ctl[g].pos = ps;
+			ctl[g].cks = ck;
+			/* release: the state above, and the records have been read before the scan lane may
+			 * overwrite them */
 			st_release(&ctl[g].cons, c);
+			__threadfence_block();
+			atomicAnd(&sm.busy[j >> 5], ~bit);
 		}
 		__syncwarp();
 	}
@@ -1313,9 +1515,11 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 		for (int i = tid; i < ACM_T_SIZE; i += THREADS)
 			sm.t[i] = a.tables->t[i];
 		if (tid < 32)
-			sm.info[tid] = make_info(a.tables->kind[tid]);
+			sm.info[tid] = a.tables->kind[tid];
 		if (lane == 0)
 			mbar_init((uint32_t)__cvta_generic_to_shared(&sm.mbar[warp]), 1u);
+		if (tid < MAXOWN / 32)
+			sm.busy[tid] = 0u;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		__syncthreads();
 #ifdef F2_TEST_NO_DECODE

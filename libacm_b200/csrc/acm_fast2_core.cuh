@@ -82,6 +82,14 @@ ACM_HD bool walk_next_if(Walk &s, uint32_t e, bool go)
 
 /* ------------------------------------------------------------------ unpack */
 
+/* "does any lane of the warp ...": lets a warp skip work none of its lanes has (on the host, where
+ * the test tier runs one lane at a time, the lane's own answer) */
+#if defined(__CUDA_ARCH__)
+#define ACM_WARP_ANY(x) (__any_sync(0xFFFFFFFFu, (x)) != 0)
+#else
+#define ACM_WARP_ANY(x) (x)
+#endif
+
 /*
  * The three column unpackers.  A decode lane owns whole columns (column = lane mod 32, the
  * layout lifting stages 1 and 2 run in), so a column's sixteen values never leave the lane's
@@ -110,14 +118,19 @@ ACM_HD void unpack_k(uint32_t lo, uint32_t mid, uint32_t hi, uint32_t sub, const
 	do {
 		const uint64_t e = tab[lo & 255u];
 		const uint32_t ev = (uint32_t)e, em = (uint32_t)(e >> 32);
-		const uint32_t bits = em & 15u;
-		lo = fsr(lo, mid, bits);
-		mid = fsr(mid, hi, bits);
-		hi >>= bits;
+		/* em = bits consumed (1..8, bits 4-7 clear) | 4 * rows << 8: a funnel shift takes its
+		 * count from the low five bits, so em itself is the shift operand */
+		lo = fsr(lo, mid, em);
+		mid = fsr(mid, hi, em);
+		hi = fsr(hi, 0u, em);
 		const unsigned long long vv = (unsigned long long)ev << r4;
 		a0 |= (uint32_t)vv;
 		a1 |= (uint32_t)(vv >> 32);
-		r4 += em >> 8;
+#if defined(__CUDA_ARCH__)
+		r4 = __dp4a(em, 0x00000100u, r4); /* += byte 1 of em: one instruction, on the other pipe */
+#else
+		r4 += (em >> 8) & 0xFFu;
+#endif
 	} while (r4 < 64u);
 }
 
@@ -147,6 +160,88 @@ ACM_HD int unpack_t(uint32_t lo, uint32_t mid, uint32_t P, uint32_t limit, uint3
 			const unsigned long long vv = (unsigned long long)(e & vmask) << (4u * q * per);
 			a0 |= (uint32_t)vv;
 			a1 |= (uint32_t)(vv >> 32);
+		}
+	}
+	return (seen & 0x8000u) != 0u;
+}
+
+/*
+ * The same two unpackers for FOUR columns at once (a decode lane's columns 32 p + lane, p = 0..3).
+ * One column is one chain of dependent operations -- table lookup, shift, next lookup -- and a
+ * warp that has a single chain in flight issues an instruction every ten cycles or so; four
+ * independent chains per lane fill those gaps.  cls[p] = ACM_CLS_* of column p (anything but
+ * ACM_CLS_K / ACM_CLS_T: the column is left alone), sub[p] its sub-type.
+ */
+ACM_HD void unpack_k4(uint32_t (&lo)[4], uint32_t (&mid)[4], uint32_t (&hi)[4], const uint32_t (&cls)[4],
+		      const uint32_t (&sub)[4], const uint64_t *k8w, uint32_t (&a0)[4], uint32_t (&a1)[4])
+{
+	uint32_t r4[4];
+	const uint64_t *tab[4];
+	uint32_t busy = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int p = 0; p < 4; p++) {
+		const bool isk = cls[p] == ACM_CLS_K;
+		r4[p] = isk ? 0u : 64u;
+		tab[p] = k8w + (isk ? sub[p] : 0u) * 256u;
+		busy |= isk ? 1u : 0u;
+	}
+	while (busy) {
+		busy = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int p = 0; p < 4; p++) {
+			/* a finished (or other) column looks up nothing: entry 0 = no bits, no rows, no values */
+			const uint64_t e = r4[p] < 64u ? tab[p][lo[p] & 255u] : 0ull;
+			const uint32_t ev = (uint32_t)e, em = (uint32_t)(e >> 32);
+			const uint32_t bits = em & 15u;
+			lo[p] = fsr(lo[p], mid[p], bits);
+			mid[p] = fsr(mid[p], hi[p], bits);
+			hi[p] >>= bits;
+			const unsigned long long vv = (unsigned long long)ev << (r4[p] & 63u);
+			a0[p] |= (uint32_t)vv;
+			a1[p] |= (uint32_t)(vv >> 32);
+			r4[p] += em >> 8;
+			busy |= r4[p] < 64u ? 1u : 0u;
+		}
+	}
+}
+
+/* P[p] = position of column p's payload; returns non-zero if a radix code that the reference gets
+ * to read is out of range */
+ACM_HD int unpack_t4(const uint32_t (&lo)[4], const uint32_t (&mid)[4], const uint32_t (&P)[4], uint32_t limit,
+		     const uint32_t (&cls)[4], const uint32_t (&sub)[4], const uint16_t *tt, uint32_t (&a0)[4],
+		     uint32_t (&a1)[4])
+{
+	uint32_t seen = 0u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+	for (int p = 0; p < 4; p++) {
+		const bool ist = cls[p] == ACM_CLS_T;
+		if (!ACM_WARP_ANY(ist))
+			continue;
+		const uint32_t sb = ist ? sub[p] : 0u;
+		const uint32_t width = sb == 0 ? 5u : 7u, per = sb == 2 ? 2u : 3u;
+		const uint32_t ncodes = !ist ? 0u : sb == 2 ? 8u : 6u, cmask = (1u << width) - 1u;
+		const uint32_t vmask = sb == 2 ? 0xFFu : 0xFFFu;
+		const uint16_t *tab = tt + sb * 128u;
+		const unsigned long long win = (unsigned long long)lo[p] | ((unsigned long long)mid[p] << 32);
+		const uint32_t nread =
+			P[p] + ncodes * width <= limit ? ncodes : (limit > P[p] ? (limit - P[p]) / width : 0u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+		for (int q = 0; q < 8; q++) {
+			if ((uint32_t)q < ncodes) {
+				const uint32_t e = tab[(uint32_t)(win >> (q * width)) & cmask];
+				seen |= (uint32_t)q < nread ? e : 0u;
+				const unsigned long long vv = (unsigned long long)(e & vmask) << (4u * q * per);
+				a0[p] |= (uint32_t)vv;
+				a1[p] |= (uint32_t)(vv >> 32);
+			}
 		}
 	}
 	return (seen & 0x8000u) != 0u;

@@ -105,6 +105,37 @@ extern "C" long emu_fast2_check(const uint8_t *img, uint32_t len)
 					if (got[r] != (uint32_t)ref[r])
 						return -(1000L * b + 5);
 		}
+		/* ---- and four columns at once, as a decode lane holds them (columns j, j+32, j+64, j+96) */
+		for (uint32_t j = 0; j < 32; j++) {
+			uint32_t lo[4], mid[4], hi[4], cls[4], sub[4], Pp[4], a0[4] = { 0, 0, 0, 0 }, a1[4] = { 0, 0, 0, 0 };
+			int bad_ref = 0;
+			for (int p = 0; p < 4; p++) {
+				const uint32_t Pc = P + off[j + 32 * p];
+				const uint32_t ind = br.peek(Pc) & 31u, kind = tab.kind[ind];
+				Pp[p] = Pc + 5u;
+				cls[p] = kind & 7u;
+				sub[p] = kind >> 3;
+				lo[p] = br.peek(Pp[p]);
+				mid[p] = br.peek(Pp[p] + 32u);
+				hi[p] = br.peek(Pp[p] + 64u);
+			}
+			const int bad4 = fast2::unpack_t4(lo, mid, Pp, limit, cls, sub, tab.t, a0, a1);
+			fast2::unpack_k4(lo, mid, hi, cls, sub, tab.k8w, a0, a1);
+			for (int p = 0; p < 4; p++) {
+				if (cls[p] == ACM_CLS_LINEAR)
+					continue;
+				int ref[16];
+				const uint32_t Pc = P + off[j + 32 * p], ind = br.peek(Pc) & 31u;
+				const int rc = decode_column(br, Pc + 5u, limit, ind, tab.kind[ind], 16u, 3, ref, 1u, tab.k8, tab.t);
+				bad_ref |= rc == -6;
+				if (rc != -6)
+					for (int r = 0; r < 16; r++)
+						if (fast2::nib_val(r < 8 ? a0[p] : a1[p], r & 7, 3) != (uint32_t)ref[r])
+							return -(1000L * b + 6);
+			}
+			if ((bad_ref != 0) != (bad4 != 0))
+				return -(1000L * b + 7);
+		}
 		P = sc.end;
 	}
 	return checked;

@@ -1,0 +1,6 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_batch.py tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -4
+timeout 300 python tools/profile_run.py --streams 10000 --runs 4 2>&1 | tail -3
+timeout 600 python tools/profile_run.py --streams 125000 --runs 3 --workload config4 2>&1 | tail -2
+F2_PROF=1 ACM_B200_LIB=libacm_b200/_lib/var/prof/libacm_b200.so timeout 600 python tools/profile_run.py --streams 10000 --runs 3 2>&1 | grep -E "^ms|busiest|work " | tail -5
+timeout 600 compute-sanitizer --tool racecheck python tools/sanitize_run.py 2>&1 | tail -5
