@@ -435,7 +435,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			hist_words += (size_t)sg.n_slots * fast2_hist_words_per_slot();
 			ring_bytes += (size_t)sg.n_slots * fast2_ring_bytes_per_slot();
 			ctl_bytes += ((size_t)sg.n_slots * fast2_ctl_bytes_per_slot() + 255u) & ~(size_t)255u;
-			int ctas = p->sm_count * 4;
+			int ctas = p->sm_count * generic_ctas_per_sm();
 			if ((uint64_t)ctas > sg.n_gen)
 				ctas = (int)sg.n_gen;
 			while (ctas > 1 && (size_t)ctas * stride * 4 > budget)

@@ -1590,6 +1590,7 @@ cudaError_t launch_fast2(const KernelArgs &a, int n_ctas, cudaStream_t st)
 		return cudaSuccess;
 	/* the opt-in shared-memory size is a per-device function attribute */
 	static bool configured[2][64] = {};
+	static int resident[2][64] = {};
 	const size_t smem = fast2::SMEM_BYTES;
 	const int v = a.fmt.checksums ? 1 : 0;
 	int dev = 0;
@@ -1603,8 +1604,24 @@ cudaError_t launch_fast2(const KernelArgs &a, int n_ctas, cudaStream_t st)
 					     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess)
 			return e;
+		/* the scan CTAs and the decode CTAs of a launch wait for each other: the whole grid has to
+		 * be resident at once.  Ask the runtime instead of assuming (one CTA of this size per SM);
+		 * the in-kernel watchdog stays as the guard against a GPU shared with other work. */
+		int per_sm = 0, sms = 0;
+		e = v ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast2::acm_decode_fast2_kernel<true>,
+								    fast2::THREADS, smem)
+		      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fast2::acm_decode_fast2_kernel<false>,
+								    fast2::THREADS, smem);
+		if (e != cudaSuccess)
+			return e;
+		e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (e != cudaSuccess)
+			return e;
+		resident[v][dev & 63] = per_sm * sms;
 		configured[v][dev & 63] = true;
 	}
+	if (n_ctas > resident[v][dev & 63])
+		return cudaErrorCooperativeLaunchTooLarge; /* would deadlock: not all CTAs can be resident */
 	if (v)
 		fast2::acm_decode_fast2_kernel<true><<<n_ctas, fast2::THREADS, smem, st>>>(a);
 	else

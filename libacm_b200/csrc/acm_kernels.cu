@@ -23,7 +23,12 @@
 
 namespace acm {
 
-#define GEN_THREADS 256             /* decode threads (warps 0..7) */
+/* A block costs max(scan, decode), and the scan -- ONE thread, ~400 dependent table steps per
+ * 2048-word block -- is by far the longer of the two: what this kernel needs is many scan threads
+ * in flight, i.e. many small CTAs per SM, not many decode threads per CTA. */
+#ifndef GEN_THREADS
+#define GEN_THREADS 128             /* decode threads (warps 0..3) */
+#endif
 #define GEN_BLOCK (GEN_THREADS + 32) /* + the scan warp (only its first lane works) */
 
 struct TablesSmem {
@@ -226,6 +231,19 @@ acm_decode_generic_kernel(KernelArgs a, GenericScratch scr)
 		}
 		__syncthreads(); /* both sides are done with this stream */
 	}
+}
+
+/* CTAs of the generic kernel that fit one SM (threads, registers, the 17 KB of code tables) */
+int generic_ctas_per_sm()
+{
+	static int cached = 0;
+	if (!cached) {
+		int nb = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, acm_decode_generic_kernel, GEN_BLOCK, 0) != cudaSuccess || nb < 1)
+			nb = 4;
+		cached = nb > 8 ? 8 : nb; /* beyond 8 the tables leave no L1 for the scan threads' loads */
+	}
+	return cached;
 }
 
 cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_ctas, cudaStream_t st)

@@ -56,6 +56,7 @@ inline size_t generic_scratch_words(uint32_t max_blen, uint32_t max_cols)
 
 cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_ctas,
 			   cudaStream_t st);
+int generic_ctas_per_sm();
 
 /* level-7 / 16-row kernel (acm_fast2.cu): scan CTAs + decode CTAs; 16-bit output formats only */
 bool fast_shape(uint32_t level, uint32_t rows);

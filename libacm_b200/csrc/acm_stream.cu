@@ -9,9 +9,12 @@
  * GPU in look-ahead chunks (resumable generic kernel: bit position + per-stage history
  * carried from chunk to chunk) into a host-side PCM cache that acm_read serves from.
  *
- *  - acm_open_decoder pulls the whole image through read_func (the reference pulls
- *    64 KiB at a time, decode.c:41-67; short reads are fine), parses the header on the
- *    host and uploads the image once.
+ *  - the image is pulled through read_func as the reference pulls it: (1, 65536) requests
+ *    (decode.c:41-67; short reads are fine), one window at open for the header, and then
+ *    ahead of every chunk as many windows as that chunk can consume at most (a block is at
+ *    most 20 + cols * (5 + 16 * rows) bits).  What has been pulled stays cached on the host
+ *    and on the device; after a backward seek -- one seek_func call to the start of the data,
+ *    as util.c:223-228 -- the source is read again from there and the cached prefix skipped.
  *  - acm_read keeps the reference's contract to the letter: never crosses a block
  *    boundary, clips to total_values, rounds down to whole frames, dst == NULL decodes
  *    and discards (decode.c:826-876).  The PCM format is a per-call argument, so the
@@ -57,7 +60,13 @@ struct SavedState {
 
 struct GpuState {
 	int device = 0;
-	std::vector<uint8_t> file;
+	std::vector<uint8_t> file;   /* the image from byte 0, as far as it has been pulled */
+	uint64_t src_pos = 0;        /* file offset the data source stands at */
+	bool src_eof = false;        /* read_func has returned 0 */
+	bool complete = false;       /* ... at the end of the cache: the whole image is here */
+	size_t uploaded = 0;         /* bytes of `file` that are in d_blob */
+	size_t blob_cap = 0;         /* bytes d_blob can hold */
+	size_t len_hint = 0;         /* get_length_func's answer (0: unknown) */
 	acm_header hdr{};
 	DevStream base{};            /* descriptor of the whole stream (block 0 start) */
 	uint32_t n_attempt_total = 0, words_limit = 0, chunk_blocks = 1, cols = 1;
@@ -138,10 +147,7 @@ int gpu_setup(GpuState *g)
 	}
 	CUS(cudaGetDevice(&g->device));
 	CUS(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-	g->blob_room = (g->file.size() + 15u) & ~(uint64_t)15u;
-	CUS(cudaMalloc(&g->d_blob, g->blob_room + 64));
-	CUS(cudaMemsetAsync(g->d_blob, 0, g->blob_room + 64, g->stream));
-	CUS(cudaMemcpyAsync(g->d_blob, g->file.data(), g->file.size(), cudaMemcpyHostToDevice, g->stream));
+	g->blob_room = 0;
 	CUS(cudaMalloc(&g->d_desc, sizeof(DevStream)));
 	CUS(cudaMalloc(&g->d_status, 16));
 	CUS(cudaMalloc(&g->d_words, 16));
@@ -163,6 +169,69 @@ int gpu_setup(GpuState *g)
 }
 
 /*
+ * Pull the image through read_func until `want` bytes of it are cached (or the source ends), the
+ * way the reference's load_buf asks: (ptr, 1, 65536) (decode.c:50-52).  After a backward seek the
+ * source stands before the end of the cache: what comes again is skipped.
+ */
+int pull(ACMStream *acm, GpuState *g, size_t want)
+{
+	std::vector<uint8_t> chunk;
+	while (g->file.size() < want && !g->complete && !g->src_eof && !g->read_error) {
+		if (chunk.empty())
+			chunk.resize(65536);
+		const int got = acm->io.read_func ? acm->io.read_func(chunk.data(), 1, (int)chunk.size(), acm->io_arg) : 0;
+		if (got < 0) {
+			g->read_error = true;
+			break;
+		}
+		if (got == 0) {
+			g->src_eof = true;
+			if (g->src_pos >= g->file.size())
+				g->complete = true;
+			break;
+		}
+		const uint64_t end = g->src_pos + (uint64_t)got;
+		if (end > g->file.size()) {
+			const size_t skip = g->src_pos < g->file.size() ? (size_t)(g->file.size() - g->src_pos) : 0;
+			g->file.insert(g->file.end(), chunk.begin() + (long)skip, chunk.begin() + got);
+		}
+		g->src_pos = end;
+	}
+	return ACM_OK;
+}
+
+/* bring the device copy of the image up to date (grown geometrically, or sized from
+ * get_length_func's answer when there is one) */
+int upload(GpuState *g)
+{
+	const size_t have = g->file.size();
+	if (have + 64 > g->blob_cap) {
+		size_t cap = g->blob_cap ? g->blob_cap * 2 : ((size_t)1 << 20);
+		if (cap < have + 64)
+			cap = have + 64;
+		if (g->len_hint + 64 > cap && g->len_hint >= have)
+			cap = g->len_hint + 64;
+		cap = (cap + 255u) & ~(size_t)255u;
+		uint8_t *nb = nullptr;
+		CUS(cudaMalloc(&nb, cap));
+		CUS(cudaMemsetAsync(nb, 0, cap, g->stream));
+		if (g->uploaded)
+			CUS(cudaMemcpyAsync(nb, g->d_blob, g->uploaded, cudaMemcpyDeviceToDevice, g->stream));
+		CUS(cudaStreamSynchronize(g->stream));
+		cudaFree(g->d_blob);
+		g->d_blob = nb;
+		g->blob_cap = cap;
+	}
+	if (have > g->uploaded) {
+		CUS(cudaMemcpyAsync(g->d_blob + g->uploaded, g->file.data() + g->uploaded, have - g->uploaded,
+				    cudaMemcpyHostToDevice, g->stream));
+		g->uploaded = have;
+	}
+	g->blob_room = (have + 15u) & ~(uint64_t)15u;
+	return ACM_OK;
+}
+
+/*
  * Decode the chunk that starts at index entry `si` (blocks [b0, b0 + nb)) in format key
  * `fmt` into the host cache.  On full success the end state becomes a new index entry.
  */
@@ -179,6 +248,32 @@ int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, in
 	int32_t status = 0;
 
 	CUS(cudaSetDevice(g->device));
+	{
+		/* everything this chunk can consume at most, or the end of the source */
+		const unsigned long long colbits = 5ull + 16ull * g->hdr.rows;
+		const unsigned long long blkbytes = (20ull + (unsigned long long)g->cols * colbits + 7ull) / 8ull;
+		const unsigned long long at = g->base.base_off + (s0.P >> 3);
+		unsigned long long want = at + (unsigned long long)nb * blkbytes + 64ull;
+		if (want > ((unsigned long long)1 << 40))
+			want = (unsigned long long)1 << 40;
+		int perr = pull(acm, g, (size_t)want);
+		if (perr < 0)
+			return perr;
+		perr = upload(g);
+		if (perr < 0)
+			return perr;
+		const uint32_t hdr = g->hdr.header_len;
+		const unsigned long long data_len = g->file.size() > hdr ? g->file.size() - hdr : 0;
+		if (data_len * 8ull + 256ull + (1ull << 20) >= 0xFFFFFFFFull) {
+			acm_set_error("stream image of 512 MiB or more: not supported by the device decoder");
+			return ACM_ERR_OTHER;
+		}
+		/* file_end: the real end once the source has run dry (the reference's one zero byte follows
+		 * it, decode.c:57-61); until then the end of what has been pulled, which no block of this
+		 * chunk can reach */
+		d.file_end = g->base.bit0 + (uint32_t)data_len * 8u;
+		g->base.file_end = d.file_end;
+	}
 	d.bit0 = s0.P;
 	d.out_off = 0;
 	d.index = 0;
@@ -301,20 +396,10 @@ extern "C" int acm_open_decoder(ACMStream **res, void *io_arg, acm_io_callbacks 
 	g = new (std::nothrow) GpuState();
 	if (!g)
 		goto fail;
-	/* pull the whole image; the reference asks for (1, 65536) items (decode.c:50-52) */
-	{
-		std::vector<uint8_t> chunk(65536);
-		for (;;) {
-			int got = io.read_func ? io.read_func(chunk.data(), 1, (int)chunk.size(), io_arg) : 0;
-			if (got < 0) {
-				g->read_error = true;
-				break;
-			}
-			if (got == 0)
-				break;
-			g->file.insert(g->file.end(), chunk.begin(), chunk.begin() + got);
-		}
-	}
+	/* the first window: the header lies in it (the reference's first load_buf, decode.c:41-67;
+	 * a source that hands out a few bytes per call is asked until 42 bytes or its end are there) */
+	g->len_hint = acm->data_len;
+	pull(acm, g, 64);
 	err = ACM_ERR_NOT_ACM; /* decode.c:783-785: every header problem */
 	if (acm_parse_header(g->file.data(), g->file.size(), force_chans, &g->hdr) < 0)
 		goto fail;
@@ -336,7 +421,7 @@ extern "C" int acm_open_decoder(ACMStream **res, void *io_arg, acm_io_callbacks 
 		acm_gpu_stream s;
 		memset(&s, 0, sizeof(s));
 		s.in_off = 0;
-		s.in_len = (uint32_t)g->file.size();
+		s.in_len = (uint32_t)(g->len_hint > g->file.size() ? g->len_hint : g->file.size());
 		s.total_values = g->hdr.total_values;
 		s.channels = g->hdr.channels;
 		s.level = g->hdr.level;
@@ -476,6 +561,8 @@ extern "C" int acm_seek_pcm(ACMStream *acm, unsigned pcm_pos)
 			return ACM_ERR_NOT_SEEKABLE;
 		if (acm->io.seek_func(acm->io_arg, (int)g->hdr.header_len, SEEK_SET) < 0)
 			return ACM_ERR_NOT_SEEKABLE;
+		g->src_pos = g->hdr.header_len; /* where the source stands now; the cache keeps what it has */
+		g->src_eof = false;
 		acm->stream_pos = 0;
 		acm->block_pos = 0;
 		acm->block_ready = 0;
