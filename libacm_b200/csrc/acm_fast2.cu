@@ -101,6 +101,9 @@ constexpr int RROW = 32 * SW;            /* words per ring row: one word of ever
 #ifndef F2_CARRY
 #define F2_CARRY 1
 #endif
+#ifndef F2_KEEP_L2
+#define F2_KEEP_L2 1 /* L2 eviction hints on the two reads of the compressed bytes */
+#endif
 #ifndef F2_UNPACK4
 #define F2_UNPACK4 0 /* 1: a lane walks its four columns together (four independent chains) */
 #endif
@@ -202,13 +205,45 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void *p)
 		     : "l"(p));
 	return r;
 }
-__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g)
+/*
+ * The compressed bytes are read twice: by the scan lane that walks them, and a few blocks later by
+ * the decode warp that stages them.  In between, the batch's PCM (4.5 x as many bytes) streams
+ * through the L2; the scan's loads therefore ask the L2 to keep their lines (evict_last), so that
+ * the second read is a hit and not a second trip to HBM.
+ */
+__device__ __forceinline__ uint64_t l2_keep_policy()
 {
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
 }
-__device__ __forceinline__ void cp_async4z(uint32_t saddr, const void *g, uint32_t n)
+__device__ __forceinline__ void cp_async4(uint32_t saddr, const void *g, uint64_t pol)
 {
+#if F2_KEEP_L2
+	asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "l"(pol) : "memory");
+#else
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(g) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async4z(uint32_t saddr, const void *g, uint32_t n, uint64_t pol)
+{
+#if F2_KEEP_L2
+	asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 4, %2, %3;" ::"r"(saddr), "l"(g), "r"(n), "l"(pol) : "memory");
+#else
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(saddr), "l"(g), "r"(n) : "memory");
+#endif
+}
+__device__ __forceinline__ uint4 ldg_keep_v4(const void *p, uint64_t pol)
+{
+	uint4 r;
+#if F2_KEEP_L2
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol));
+#else
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+#endif
+	return r;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -230,8 +265,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes)
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t mbar)
 {
+#if F2_KEEP_L2
+	/* the second and last read of these bytes (the scan lane kept them in the L2): let them go */
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+		     ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar), "l"(pol) : "memory");
+#else
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 		     ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity)
 {
@@ -301,6 +344,7 @@ struct ScanRing {
 	 * whatever a lane wants beyond that (bursts of wide columns) goes by cp.async */
 	uint4 hold[NHOLD];
 	uint32_t hold_c0, hold_n;
+	uint64_t pol; /* L2 eviction policy of this lane's loads */
 
 	/* no stream: the lane's walk sits on the HALT page at P = 0 over two zero ring words, so that
 	 * all idle lanes of a warp look up the same table word (a broadcast, not a bank conflict) */
@@ -342,12 +386,12 @@ struct ScanRing {
 		const uint32_t sa = saddr + (c & (RW / 4 - 1)) * (16u * RROW);
 		const uint8_t *g = base + (size_t)c * 16u;
 		if (c < full16) {
-			cp_async4(sa, g);
-			cp_async4(sa + 4 * RROW, g + 4);
-			cp_async4(sa + 8 * RROW, g + 8);
-			cp_async4(sa + 12 * RROW, g + 12);
+			cp_async4(sa, g, pol);
+			cp_async4(sa + 4 * RROW, g + 4, pol);
+			cp_async4(sa + 8 * RROW, g + 8, pol);
+			cp_async4(sa + 12 * RROW, g + 12, pol);
 			if ((c & (RW / 4 - 1)) == 0)
-				cp_async4(saddr + RW * 4 * RROW, g);
+				cp_async4(saddr + RW * 4 * RROW, g, pol);
 		} else {
 			/* touches the end of the file (or of the blob): bytes at and past it read as zero,
 			 * which is the reference's "one zero byte, then nothing" (decode.c:57-61) */
@@ -358,9 +402,9 @@ struct ScanRing {
 				if (c < room16 && at < fe_byte)
 					n = fe_byte - at < 4u ? fe_byte - at : 4u;
 				const void *src = n ? (const void *)(g + 4 * k) : (const void *)base;
-				cp_async4z(sa + 4 * RROW * k, src, n);
+				cp_async4z(sa + 4 * RROW * k, src, n, pol);
 				if (k == 0 && (c & (RW / 4 - 1)) == 0)
-					cp_async4z(saddr + RW * 4 * RROW, src, n);
+					cp_async4z(saddr + RW * 4 * RROW, src, n, pol);
 			}
 		}
 	}
@@ -392,7 +436,7 @@ struct ScanRing {
 #pragma unroll
 		for (int k = 0; k < NHOLD; k++)
 			if (k < nreg)
-				hold[k] = __ldg(reinterpret_cast<const uint4 *>(base + (size_t)(f0 + k) * 16u));
+				hold[k] = ldg_keep_v4(base + (size_t)(f0 + k) * 16u, pol);
 		hold_c0 = f0;
 		hold_n = (uint32_t)nreg;
 #pragma unroll 1
@@ -1171,11 +1215,12 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 	const uint32_t lane4 = 4u * (uint32_t)(warp * 32 + lane);
 	ring.rw = &sm.ring[0][warp * 32 + lane];
 	ring.saddr = (uint32_t)__cvta_generic_to_shared(ring.rw);
+	ring.pol = l2_keep_policy();
 	ring.idle();
 	bool active = false, exhausted = !enabled;
 	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
 	unsigned long long waiting_since = 0ull;
-	uint32_t seen_hb = 0;
+	uint32_t seen_hb = 0, wait_ns = 250u;
 	uint4 c4n = make_uint4(0u, 0u, 0u, 0u);
 	bool fresh = false;
 	PROF_DECL;
@@ -1222,7 +1267,10 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			if (none && !__any_sync(0xFFFFFFFFu, active))
 				break;
 			if (none || (F2_HYST && !__any_sync(0xFFFFFFFFu, can && lead < (uint32_t)(RING_D / 2)))) {
-				__nanosleep(none ? 500 : 300);
+				/* back off: while the decode side is the bottleneck a scan warp spends most of its time
+				 * here, and a short sleep makes that a quarter of the kernel's executed instructions */
+				__nanosleep(wait_ns);
+				wait_ns = wait_ns < 2000u ? wait_ns * 2u : wait_ns;
 				PROF_MARK(1); /* 1: waiting for the decode side */
 				const uint32_t hb = *reinterpret_cast<volatile uint32_t *>(a.scan_done + 1);
 				if (waiting_since == 0ull || hb != seen_hb) {
@@ -1237,6 +1285,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			}
 		}
 		waiting_since = 0ull;
+		wait_ns = 250u;
 		if (lane == 0)
 			atomicAdd(a.scan_done + 1, 1u); /* heartbeat */
 		if (enabled) {
