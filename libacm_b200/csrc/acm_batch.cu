@@ -177,6 +177,9 @@ struct Segment {
 	size_t ctl_off;                   /* slot control words (offset in bytes) */
 	uint32_t n_scan, n_slots;         /* fast kernel geometry: scan CTAs, slots in use */
 	bool sparse;                      /* the kernels do not write every byte of [out_lo, out_hi) */
+	int walk_bound;                   /* fast kernel: the longest stream's walk bounds the launch (more scan CTAs) */
+	uint64_t item_first, n_items;     /* general path: this segment's decode work items */
+	uint64_t g2_first;                /* ... and its slice of the per-stream arrays */
 };
 
 struct acm_gpu_plan {
@@ -195,6 +198,8 @@ struct acm_gpu_plan {
 	acm_tables *d_tables;
 	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue, [4g+2] finished scan warps, [4g+3] heartbeat; [4*nseg] error flag */
 	GenericScratch scratch;
+	Gen2Args g2;         /* general path: block records, column offsets, work items (device pointers) */
+	size_t g2_state_bytes; /* nscan + first_bad: reset before every run */
 	uint32_t *d_hist;    /* fast kernel history, 256 words per stream slot */
 	uint8_t *d_ring;     /* fast kernel block-record rings */
 	uint8_t *d_pool;     /* the one device allocation all of the above point into (null: arena) */
@@ -248,6 +253,10 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	acm_gpu_opts defaults;
 	acm_gpu_plan *p = nullptr;
 	std::vector<DevStream> all;
+	std::vector<Gen2Stream> g2_streams; /* parallel to the generic streams, in `all` order */
+	std::vector<Gen2Item> g2_items;
+	uint64_t g2_blocks = 0, g2_coffs = 0;
+	constexpr uint32_t G2_RUN = 16;
 	int sm_count = 0, max_ctas = 0;
 	int err = ACM_ERR_OTHER, dev = 0;
 	uint32_t max_blen = 1, max_cols = 1;
@@ -270,6 +279,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 
 	p = new acm_gpu_plan();
 	memset(&p->scratch, 0, sizeof(p->scratch));
+	memset(&p->g2, 0, sizeof(p->g2));
+	p->g2_state_bytes = 0;
 	p->d_streams = nullptr; p->d_status = nullptr; p->d_words = nullptr; p->d_cks = nullptr;
 	p->d_tables = nullptr; p->d_counters = nullptr; p->ev0 = nullptr; p->ev1 = nullptr;
 	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
@@ -382,7 +393,11 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			 * run their final rounds with one or two busy lanes instead of 32.  The rest of the
 			 * queue stays longest-first. */
 			uint32_t n_scan = 0, n_work = 0, n_slots = 0;
-			fast2_geometry(fast.size(), sm_count, max_ctas, &n_scan, &n_work, &n_slots);
+			uint64_t blocks = 0;
+			for (const DevStream &d : fast)
+				blocks += d.n_attempt;
+			sg.walk_bound = fast2_walk_bound(fast[0].n_attempt, blocks, sm_count, max_ctas);
+			fast2_geometry(fast.size(), sm_count, max_ctas, &n_scan, &n_work, &n_slots, sg.walk_bound);
 			const size_t head = std::min<size_t>(n_slots, fast.size()) / 32 * 32, warps = head / 32;
 			if (warps > 1) {
 				std::vector<DevStream> dealt(head);
@@ -405,6 +420,34 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		sg.gen_first = all.size();
 		sg.n_gen = gen.size();
 		all.insert(all.end(), gen.begin(), gen.end());
+		/* general path: block records for every block the image can hold, and the decode work items:
+		 * runs of G2_RUN consecutive blocks, each with the warm-up blocks that rebuild the transform
+		 * history (the look-back is 2*cols-2 words) */
+		sg.item_first = g2_items.size();
+		sg.g2_first = g2_streams.size();
+		for (size_t k = 0; k < gen.size(); k++) {
+			const DevStream &d = gen[k];
+			Gen2Stream gs;
+			memset(&gs, 0, sizeof(gs));
+			const uint32_t cols = 1u << d.level, blen = d.rows << d.level;
+			gs.rec_base = g2_blocks;
+			gs.coff_base = g2_coffs;
+			gs.max_blocks = (uint32_t)gen2_max_blocks(d.n_attempt, d.file_end > d.bit0 ? d.file_end - d.bit0 : 0, d.level);
+			g2_blocks += gs.max_blocks;
+			g2_coffs += (uint64_t)gs.max_blocks * cols;
+			g2_streams.push_back(gs);
+			const uint32_t look = 2u * cols - 2u;
+			const uint32_t warm_full = look ? (look + blen - 1u) / blen : 0u;
+			for (uint32_t b0 = 0; b0 < gs.max_blocks; b0 += G2_RUN) {
+				Gen2Item it;
+				it.stream = (uint32_t)k;
+				it.b0 = b0;
+				it.nb = std::min<uint32_t>(G2_RUN, gs.max_blocks - b0);
+				it.warm = std::min(warm_full, b0);
+				g2_items.push_back(it);
+			}
+		}
+		sg.n_items = g2_items.size() - sg.item_first;
 		p->n_fast += sg.n_fast;
 		p->n_generic += sg.n_gen;
 		max_fast = std::max(max_fast, sg.n_fast);
@@ -429,15 +472,17 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			sg.fast_ctas = 0;
 			if (sg.n_fast) {
 				uint32_t n_work = 0;
-				fast2_geometry(sg.n_fast, p->sm_count, max_ctas, &sg.n_scan, &n_work, &sg.n_slots);
+				fast2_geometry(sg.n_fast, p->sm_count, max_ctas, &sg.n_scan, &n_work, &sg.n_slots, sg.walk_bound);
 				sg.fast_ctas = (int)(sg.n_scan + n_work);
 			}
 			hist_words += (size_t)sg.n_slots * fast2_hist_words_per_slot();
 			ring_bytes += (size_t)sg.n_slots * fast2_ring_bytes_per_slot();
 			ctl_bytes += ((size_t)sg.n_slots * fast2_ctl_bytes_per_slot() + 255u) & ~(size_t)255u;
-			int ctas = p->sm_count * generic_ctas_per_sm();
-			if ((uint64_t)ctas > sg.n_gen)
-				ctas = (int)sg.n_gen;
+			int ctas = p->sm_count * gen2_ctas_per_sm();
+			if ((uint64_t)ctas > sg.n_items)
+				ctas = (int)sg.n_items;
+			if (ctas < 1 && sg.n_gen)
+				ctas = 1;
 			while (ctas > 1 && (size_t)ctas * stride * 4 > budget)
 				ctas /= 2;
 			sg.gen_ctas = ctas;
@@ -461,6 +506,17 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		const size_t o_hist = carve(hist_words * 4 + 16);
 		const size_t o_ring = carve(ring_bytes + 16);
 		const size_t o_scratch = carve(max_gen ? scratch_words * 4 + 16 : 0);
+		const size_t n_g2 = g2_streams.size();
+		if ((g2_blocks * (sizeof(BlockRec) + 8) + g2_coffs * 4) >> 35) {
+			acm_set_error("general path: %llu blocks need more than 32 GB of block records", (unsigned long long)g2_blocks);
+			goto fail;
+		}
+		const size_t o_g2s = carve((n_g2 + 1) * sizeof(Gen2Stream));
+		const size_t o_g2items = carve((g2_items.size() + 1) * sizeof(Gen2Item));
+		const size_t o_g2state = carve((n_g2 + 1) * 8); /* nscan | first_bad */
+		const size_t o_g2rec = carve((g2_blocks + 1) * sizeof(BlockRec));
+		const size_t o_g2cks = carve((g2_blocks + 1) * 8);
+		const size_t o_g2coff = carve((g2_coffs + 4) * 4);
 		uint8_t *base = nullptr;
 		if (arena) {
 			if (arena->cap < total) {
@@ -492,6 +548,18 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			p->scratch.max_cols = max_cols;
 			p->scratch.buf = reinterpret_cast<uint32_t *>(base + o_scratch);
 		}
+		p->g2.gs = reinterpret_cast<const Gen2Stream *>(base + o_g2s);
+		p->g2.items = reinterpret_cast<const Gen2Item *>(base + o_g2items);
+		p->g2.nscan = reinterpret_cast<uint32_t *>(base + o_g2state);
+		p->g2.first_bad = p->g2.nscan + (n_g2 + 1);
+		p->g2_state_bytes = (n_g2 + 1) * 8;
+		p->g2.rec = reinterpret_cast<BlockRec *>(base + o_g2rec);
+		p->g2.cks_blk = reinterpret_cast<unsigned long long *>(base + o_g2cks);
+		p->g2.coff = reinterpret_cast<uint32_t *>(base + o_g2coff);
+		if (n_g2)
+			CU(cudaMemcpy(base + o_g2s, g2_streams.data(), n_g2 * sizeof(Gen2Stream), cudaMemcpyHostToDevice));
+		if (!g2_items.empty())
+			CU(cudaMemcpy(base + o_g2items, g2_items.data(), g2_items.size() * sizeof(Gen2Item), cudaMemcpyHostToDevice));
 		if (p->n_dev)
 			CU(cudaMemcpy(p->d_streams, all.data(), p->n_dev * sizeof(DevStream), cudaMemcpyHostToDevice));
 		CU(cudaMemset(base + o_results, 0, (n + 1) * 16));
@@ -554,7 +622,14 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 		a.streams = p->d_streams + sg.gen_first;
 		a.count = (uint32_t)sg.n_gen;
 		a.counter = p->d_counters + 4 * g + 1;
-		CU(launch_generic(a, sc, sg.gen_ctas, st));
+		Gen2Args g2 = p->g2;
+		g2.gs += sg.g2_first;
+		g2.nscan += sg.g2_first;
+		g2.first_bad += sg.g2_first;
+		g2.items += sg.item_first;
+		g2.n_items = (uint32_t)sg.n_items;
+		g2.item_counter = p->d_counters + 4 * g + 1;
+		CU(launch_gen2(a, g2, sc, sg.gen_ctas, st));
 	}
 	return ACM_OK;
 fail:
@@ -573,6 +648,10 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 	CU(cudaMemsetAsync(p->d_counters, 0, (4 * p->seg.size() + 4) * sizeof(uint32_t), st));
 	if (p->d_ctl)
 		CU(cudaMemsetAsync(p->d_ctl, 0, p->ctl_bytes, st));
+	if (p->n_generic) {
+		CU(cudaMemsetAsync(p->g2.nscan, 0, p->g2_state_bytes / 2, st));
+		CU(cudaMemsetAsync(p->g2.first_bad, 0xFF, p->g2_state_bytes / 2, st));
+	}
 	CU(cudaEventRecord(p->ev0, st));
 	for (size_t g = 0; g < p->seg.size(); g++)
 		if (plan_run_segment(p, g, d_blob, d_out, st) < 0)
@@ -624,7 +703,7 @@ extern "C" int acm_gpu_plan_launches(const acm_gpu_plan *p)
 {
 	int k = 0;
 	for (const Segment &sg : p->seg)
-		k += (sg.n_fast ? 1 : 0) + (sg.n_gen ? 1 : 0);
+		k += (sg.n_fast ? 1 : 0) + (sg.n_gen ? 2 + (sg.n_items ? 1 : 0) : 0); /* general path: scan, blocks, finish */
 	return k;
 }
 
@@ -655,7 +734,7 @@ extern "C" void acm_gpu_plan_destroy(acm_gpu_plan *p) { plan_free(p); }
  * (no device needed): lets the CPU-only test tier check the co-residency rules. */
 extern "C" void acm_gpu_debug_geometry(uint64_t n, int sms, int max_ctas, uint32_t *out3)
 {
-	fast2_geometry(n, sms, max_ctas, &out3[0], &out3[1], &out3[2]);
+	fast2_geometry(n, sms, max_ctas, &out3[0], &out3[1], &out3[2], 0);
 }
 
 /* the plan's 64 in-kernel counters, accumulated over its runs ([32]: blocks re-walked by the generic scan,
@@ -781,6 +860,10 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 	CUR(cudaMemsetAsync(plan->d_counters, 0, (4 * ns + 4) * sizeof(uint32_t), w.s_in));
 	if (plan->d_ctl)
 		CUR(cudaMemsetAsync(plan->d_ctl, 0, plan->ctl_bytes, w.s_in));
+	if (plan->n_generic) {
+		CUR(cudaMemsetAsync(plan->g2.nscan, 0, plan->g2_state_bytes / 2, w.s_in));
+		CUR(cudaMemsetAsync(plan->g2.first_bad, 0xFF, plan->g2_state_bytes / 2, w.s_in));
+	}
 	for (size_t g = 0; g < ns; g++) {
 		const Segment &sg = plan->seg[g];
 		cudaStream_t sk = w.s_k[g % MAX_SEG];

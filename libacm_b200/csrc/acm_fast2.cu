@@ -1590,7 +1590,8 @@ size_t fast2_smem_bytes() { return fast2::SMEM_BYTES; }
  * SM: all CTAs of a launch must be resident together, decode CTAs wait for records; the scan CTAs
  * have the lowest block indices, so they are placed first).  n_slots = slots in use.
  */
-void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots)
+void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots,
+		    int walk_bound)
 {
 #ifndef F2_SCAN_PCT
 #define F2_SCAN_PCT 22
@@ -1599,7 +1600,16 @@ void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uin
 	if (total < 2)
 		total = 2;
 	const uint64_t want_scan = (count + fast2::SLOTS - 1) / fast2::SLOTS;
-	uint32_t cap_scan = (uint32_t)((total * F2_SCAN_PCT + 50) / 100);
+	/* A batch whose longest stream takes as long to WALK as the whole batch takes to decode (few, long
+	 * streams: BASELINE configs[1]) gets more scan CTAs: with a lane for every stream from the start no
+	 * lane is refilled, the scan warps thin out as their shorter streams end, and a round of a warp with
+	 * few busy lanes is up to 30 % shorter -- which is what the longest streams, the launch's critical
+	 * path, see (4.67 -> 4.30 ms on config 2).  A decode-bound batch (many short streams) keeps the
+	 * smaller share: there every SM taken from the decode side costs throughput (19.1 -> 19.8 ms). */
+#ifndef F2_SCAN_PCT_WALK
+#define F2_SCAN_PCT_WALK 28
+#endif
+	uint32_t cap_scan = (uint32_t)((total * (walk_bound ? F2_SCAN_PCT_WALK : F2_SCAN_PCT) + 50) / 100);
 	if (cap_scan < 1)
 		cap_scan = 1;
 	uint32_t ns = want_scan < cap_scan ? (uint32_t)want_scan : cap_scan;
@@ -1625,6 +1635,16 @@ void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uin
 	*n_scan = ns;
 	*n_work = nw;
 	*n_slots = (uint32_t)slots;
+}
+
+/* Is a launch bound by the walk of its longest stream rather than by decode throughput?  Measured rates:
+ * a lock-step scan round (one block per lane) takes ~37 us, a decode CTA finishes ~1.3 blocks per us. */
+int fast2_walk_bound(uint64_t longest_blocks, uint64_t total_blocks, int sms, int max_ctas)
+{
+	const int total = max_ctas < sms ? max_ctas : sms;
+	const double n_work = total * (100 - F2_SCAN_PCT) / 100.0;
+	const double t_walk = (double)longest_blocks * 37.0, t_decode = (double)total_blocks / (n_work * 1.3);
+	return t_walk * 1.25 > t_decode;
 }
 
 size_t fast2_hist_words_per_slot() { return fast2::HIST_WORDS; }

@@ -58,10 +58,58 @@ cudaError_t launch_generic(const KernelArgs &a, const GenericScratch &s, int n_c
 			   cudaStream_t st);
 int generic_ctas_per_sm();
 
+/* ---- the general path as scan -> block records -> block-parallel decode -> finalise (acm_gen2.cu) */
+
+struct BlockRec {
+	uint32_t P, end;  /* bit position of the block header / just past the block (or where the scan stopped) */
+	int32_t val;      /* block multiplier (decode.c:589) */
+	int32_t status;   /* SCAN_OK / SCAN_EOF / ACM_ERR_* */
+	uint32_t ncols;   /* columns whose payload was scanned completely */
+	uint32_t pad0, pad1, pad2;
+};
+
+struct Gen2Stream {
+	uint64_t rec_base;   /* index of the stream's first BlockRec (and per-block checksum) */
+	uint64_t coff_base;  /* index of its first column offset: block b's are at coff_base + b * cols */
+	uint32_t max_blocks; /* records reserved: min(n_attempt, what the image can hold) */
+	uint32_t pad;
+};
+
+struct Gen2Item {
+	uint32_t stream; /* index into the kernel's descriptor slice */
+	uint32_t b0, nb; /* blocks [b0, b0 + nb) are this item's output */
+	uint32_t warm;   /* blocks before b0 decoded only to rebuild the transform history */
+};
+
+struct Gen2Args {
+	const Gen2Stream *gs;
+	BlockRec *rec;
+	uint32_t *coff;              /* P of every column selector */
+	unsigned long long *cks_blk; /* per-block checksum contributions */
+	uint32_t *nscan;             /* per stream: records written by the scan */
+	uint32_t *first_bad;         /* per stream: first block with an out-of-range radix code (0xFFFFFFFF: none) */
+	const Gen2Item *items;
+	uint32_t n_items;
+	uint32_t *item_counter;      /* zeroed before launch */
+};
+
+cudaError_t launch_gen2(const KernelArgs &a, const Gen2Args &g, const GenericScratch &s, int n_ctas, cudaStream_t st);
+int gen2_ctas_per_sm();
+/* blocks an image of data_bits bits can hold at most (a block is at least 20 + 5 * cols bits) */
+inline uint64_t gen2_max_blocks(uint64_t n_attempt, uint64_t data_bits, uint32_t level)
+{
+	const uint64_t minb = 20u + 5u * ((uint64_t)1 << level);
+	const uint64_t fit = (data_bits + 8u) / minb + 2u;
+	return n_attempt < fit ? n_attempt : fit;
+}
+
 /* level-7 / 16-row kernel (acm_fast2.cu): scan CTAs + decode CTAs; 16-bit output formats only */
 bool fast_shape(uint32_t level, uint32_t rows);
 size_t fast2_smem_bytes();
-void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots);
+/* walk_bound: the batch's longest stream takes about as long to walk as the batch to decode (see fast2_walk_bound) */
+void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots,
+		    int walk_bound);
+int fast2_walk_bound(uint64_t longest_blocks, uint64_t total_blocks, int sms, int max_ctas);
 size_t fast2_hist_words_per_slot();
 size_t fast2_ring_bytes_per_slot();
 size_t fast2_ctl_bytes_per_slot();
