@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v",
 ]
-CUDA_SOURCES = ["acm_batch.cu", "acm_kernels.cu", "acm_gen2.cu", "acm_fast2.cu", "acm_stream.cu", "acm_gen.cu"]
+CUDA_SOURCES = ["acm_batch.cu", "acm_kernels.cu", "acm_gen2.cu", "acm_fast2.cu", "acm_split.cu", "acm_stream.cu", "acm_gen.cu"]
 C_SOURCES = ["acm_tables.c", "acm_hostlogic.cpp"]
 
 

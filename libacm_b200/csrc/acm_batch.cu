@@ -8,6 +8,7 @@
  * reference does per block runs on the device.
  */
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -180,6 +181,10 @@ struct Segment {
 	int walk_bound;                   /* fast kernel: the longest stream's walk bounds the launch (more scan CTAs) */
 	uint64_t item_first, n_items;     /* general path: this segment's decode work items */
 	uint64_t g2_first;                /* ... and its slice of the per-stream arrays */
+	uint64_t split_first, n_split;    /* split path (acm_split.cu): slice of d_streams, */
+	uint64_t sp_item_first, sp_n_items; /* lift work items, */
+	uint64_t sp_first;                /* slice of the per-stream arrays, */
+	uint64_t sp_block0, sp_blocks;    /* and of the per-block arrays */
 };
 
 struct acm_gpu_plan {
@@ -200,6 +205,9 @@ struct acm_gpu_plan {
 	GenericScratch scratch;
 	Gen2Args g2;         /* general path: block records, column offsets, work items (device pointers) */
 	size_t g2_state_bytes; /* nscan + first_bad: reset before every run */
+	SplitArgs sp;        /* split path: the same for its streams, plus the intermediates between its kernels */
+	size_t sp_state_bytes;
+	uint64_t n_split;
 	uint32_t *d_hist;    /* fast kernel history, 256 words per stream slot */
 	uint8_t *d_ring;     /* fast kernel block-record rings */
 	uint8_t *d_pool;     /* the one device allocation all of the above point into (null: arena) */
@@ -255,8 +263,11 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	std::vector<DevStream> all;
 	std::vector<Gen2Stream> g2_streams; /* parallel to the generic streams, in `all` order */
 	std::vector<Gen2Item> g2_items;
-	uint64_t g2_blocks = 0, g2_coffs = 0;
+	std::vector<Gen2Stream> sp_streams; /* the same for the split path's streams */
+	std::vector<Gen2Item> sp_items;
+	uint64_t g2_blocks = 0, g2_coffs = 0, sp_blocks = 0;
 	constexpr uint32_t G2_RUN = 16;
+	constexpr uint32_t SP_RUN = 8; /* blocks per lift work item */
 	int sm_count = 0, max_ctas = 0;
 	int err = ACM_ERR_OTHER, dev = 0;
 	uint32_t max_blen = 1, max_cols = 1;
@@ -281,6 +292,9 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	memset(&p->scratch, 0, sizeof(p->scratch));
 	memset(&p->g2, 0, sizeof(p->g2));
 	p->g2_state_bytes = 0;
+	memset(&p->sp, 0, sizeof(p->sp));
+	p->sp_state_bytes = 0;
+	p->n_split = 0;
 	p->d_streams = nullptr; p->d_status = nullptr; p->d_words = nullptr; p->d_cks = nullptr;
 	p->d_tables = nullptr; p->d_counters = nullptr; p->ev0 = nullptr; p->ev1 = nullptr;
 	p->d_hist = nullptr; p->fast_ctas = 0; p->generic_ctas = 0;
@@ -336,7 +350,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		}
 	}
 	for (Segment &sg : p->seg) {
-		std::vector<DevStream> fast, gen;
+		std::vector<DevStream> fast, gen, spl;
 		uint64_t slot_bytes = 0;
 		sg.blob_lo = sg.out_lo = ~(uint64_t)0;
 		sg.sparse = !opts->pad_tail;
@@ -363,7 +377,9 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			sg.out_lo = std::min(sg.out_lo, g.out_off);
 			sg.out_hi = std::max(sg.out_hi, o_hi);
 			slot_bytes += o_hi - g.out_off;
-			if (opts->kernel != 1 && fast_eligible(g, opts)) {
+			if (opts->kernel == 2 && opts->wordlen == 2 && split_shape(g.level, g.rows)) {
+				spl.push_back(d);
+			} else if (opts->kernel != 1 && fast_eligible(g, opts)) {
 				fast.push_back(d);
 			} else {
 				gen.push_back(d);
@@ -414,9 +430,49 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			return a.index < b.index;
 		};
 		std::sort(gen.begin(), gen.end(), by_work);
+		std::sort(spl.begin(), spl.end(), by_len);
 		sg.fast_first = all.size();
 		sg.n_fast = fast.size();
 		all.insert(all.end(), fast.begin(), fast.end());
+		sg.split_first = all.size();
+		sg.n_split = spl.size();
+		all.insert(all.end(), spl.begin(), spl.end());
+		/* split path: a record per block the image can hold; lift work items = runs of SP_RUN
+		 * consecutive blocks (a run rebuilds the transform history from the block before it) */
+		sg.sp_first = sp_streams.size();
+		sg.sp_item_first = sp_items.size();
+		sg.sp_block0 = sp_blocks;
+		for (size_t k = 0; k < spl.size(); k++) {
+			const DevStream &d = spl[k];
+			Gen2Stream gs;
+			memset(&gs, 0, sizeof(gs));
+			gs.rec_base = sp_blocks - sg.sp_block0;
+			gs.max_blocks = (uint32_t)gen2_max_blocks(d.n_attempt, d.file_end > d.bit0 ? d.file_end - d.bit0 : 0, d.level);
+			sp_blocks += gs.max_blocks;
+			sp_streams.push_back(gs);
+		}
+		/* items block-range major: the first runs of all streams, then the second runs, ...: neighbours in
+		 * the queue read neighbouring records, and the longest streams' last runs are the last items */
+		{
+			uint32_t longest = 0;
+			for (size_t k = 0; k < spl.size(); k++)
+				longest = std::max(longest, sp_streams[sg.sp_first + k].max_blocks);
+			for (uint32_t b0 = 0; b0 < longest; b0 += SP_RUN)
+				for (size_t k = 0; k < spl.size(); k++) {
+					const uint32_t mb = sp_streams[sg.sp_first + k].max_blocks;
+					if (b0 >= mb)
+						continue;
+					Gen2Item it;
+					it.stream = (uint32_t)k;
+					it.b0 = b0;
+					it.nb = std::min<uint32_t>(SP_RUN, mb - b0);
+					it.warm = 0;
+					sp_items.push_back(it);
+				}
+		}
+		sg.sp_n_items = sp_items.size() - sg.sp_item_first;
+		sg.sp_blocks = sp_blocks - sg.sp_block0;
+		p->n_split += sg.n_split;
 		sg.gen_first = all.size();
 		sg.n_gen = gen.size();
 		all.insert(all.end(), gen.begin(), gen.end());
@@ -517,6 +573,22 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		const size_t o_g2rec = carve((g2_blocks + 1) * sizeof(BlockRec));
 		const size_t o_g2cks = carve((g2_blocks + 1) * 8);
 		const size_t o_g2coff = carve((g2_coffs + 4) * 4);
+		/* split path: per-stream tables and state, work items, and per block: record, checksum,
+		 * column offsets, index bytes, wide mask, side array */
+		const size_t n_sp = sp_streams.size();
+		if ((sp_blocks * split_bytes_per_block()) >> 37) {
+			acm_set_error("split path: %llu blocks need more than 128 GB of intermediates", (unsigned long long)sp_blocks);
+			goto fail;
+		}
+		const size_t o_sps = carve((n_sp + 1) * sizeof(Gen2Stream));
+		const size_t o_spitems = carve((sp_items.size() + 1) * sizeof(Gen2Item));
+		const size_t o_spstate = carve((n_sp + 1) * 8);
+		const size_t o_sprec = carve((sp_blocks + 1) * sizeof(BlockRec));
+		const size_t o_spcks = carve((sp_blocks + 1) * 8);
+		const size_t o_spcoff = carve((sp_blocks + 1) * 256);
+		const size_t o_spwmask = carve((sp_blocks + 1) * 16);
+		const size_t o_spinter = carve(n_sp ? (sp_blocks + 1) * 2048 : 0);
+		const size_t o_spwide = carve(n_sp ? (sp_blocks + 1) * 4096 : 0);
 		uint8_t *base = nullptr;
 		if (arena) {
 			if (arena->cap < total) {
@@ -556,6 +628,21 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		p->g2.rec = reinterpret_cast<BlockRec *>(base + o_g2rec);
 		p->g2.cks_blk = reinterpret_cast<unsigned long long *>(base + o_g2cks);
 		p->g2.coff = reinterpret_cast<uint32_t *>(base + o_g2coff);
+		p->sp.gs = reinterpret_cast<const Gen2Stream *>(base + o_sps);
+		p->sp.items = reinterpret_cast<const Gen2Item *>(base + o_spitems);
+		p->sp.nscan = reinterpret_cast<uint32_t *>(base + o_spstate);
+		p->sp.first_bad = p->sp.nscan + (n_sp + 1);
+		p->sp_state_bytes = (n_sp + 1) * 8;
+		p->sp.rec = reinterpret_cast<BlockRec *>(base + o_sprec);
+		p->sp.cks_blk = reinterpret_cast<unsigned long long *>(base + o_spcks);
+		p->sp.coff16 = reinterpret_cast<uint16_t *>(base + o_spcoff);
+		p->sp.wmask = reinterpret_cast<uint32_t *>(base + o_spwmask);
+		p->sp.inter = base + o_spinter;
+		p->sp.wide = reinterpret_cast<uint16_t *>(base + o_spwide);
+		if (n_sp)
+			CU(cudaMemcpy(base + o_sps, sp_streams.data(), n_sp * sizeof(Gen2Stream), cudaMemcpyHostToDevice));
+		if (!sp_items.empty())
+			CU(cudaMemcpy(base + o_spitems, sp_items.data(), sp_items.size() * sizeof(Gen2Item), cudaMemcpyHostToDevice));
 		if (n_g2)
 			CU(cudaMemcpy(base + o_g2s, g2_streams.data(), n_g2 * sizeof(Gen2Stream), cudaMemcpyHostToDevice));
 		if (!g2_items.empty())
@@ -616,6 +703,29 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 		a.counter = p->d_counters + 4 * g;
 		CU(launch_fast2(a, sg.fast_ctas, st));
 	}
+	if (sg.n_split) {
+		/* records of one run are told from stale ones by the run's epoch: unique per process */
+		static std::atomic<uint32_t> epoch_counter{1};
+		SplitArgs sp = p->sp;
+		a.streams = p->d_streams + sg.split_first;
+		a.count = (uint32_t)sg.n_split;
+		a.counter = p->d_counters + 4 * g;
+		sp.gs += sg.sp_first;
+		sp.nscan += sg.sp_first;
+		sp.first_bad += sg.sp_first;
+		sp.items += sg.sp_item_first;
+		sp.n_items = (uint32_t)sg.sp_n_items;
+		sp.item_counter = p->d_counters + 4 * g + 2;
+		sp.rec += sg.sp_block0;
+		sp.cks_blk += sg.sp_block0;
+		sp.coff16 += sg.sp_block0 * 128u;
+		sp.wmask += sg.sp_block0 * 4u;
+		sp.inter += sg.sp_block0 * 2048u;
+		sp.wide += sg.sp_block0 * 2048u;
+		sp.n_blocks = sg.sp_blocks;
+		sp.epoch = epoch_counter.fetch_add(1);
+		CU(launch_split(a, sp, p->sm_count, st));
+	}
 	if (sg.n_gen) {
 		GenericScratch sc = p->scratch;
 		sc.buf += sg.scratch_off;
@@ -651,6 +761,10 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 	if (p->n_generic) {
 		CU(cudaMemsetAsync(p->g2.nscan, 0, p->g2_state_bytes / 2, st));
 		CU(cudaMemsetAsync(p->g2.first_bad, 0xFF, p->g2_state_bytes / 2, st));
+	}
+	if (p->n_split) {
+		CU(cudaMemsetAsync(p->sp.nscan, 0, p->sp_state_bytes / 2, st));
+		CU(cudaMemsetAsync(p->sp.first_bad, 0xFF, p->sp_state_bytes / 2, st));
 	}
 	CU(cudaEventRecord(p->ev0, st));
 	for (size_t g = 0; g < p->seg.size(); g++)
@@ -703,14 +817,15 @@ extern "C" int acm_gpu_plan_launches(const acm_gpu_plan *p)
 {
 	int k = 0;
 	for (const Segment &sg : p->seg)
-		k += (sg.n_fast ? 1 : 0) + (sg.n_gen ? 2 + (sg.n_items ? 1 : 0) : 0); /* general path: scan, blocks, finish */
+		k += (sg.n_fast ? 1 : 0) + (sg.n_gen ? 2 + (sg.n_items ? 1 : 0) : 0) /* general path: scan, blocks, finish */
+		     + (sg.n_split ? 3 + (sg.sp_n_items ? 1 : 0) : 0);                /* split path: walk, unpack, lift, finish */
 	return k;
 }
 
 extern "C" void acm_gpu_plan_split(const acm_gpu_plan *p, uint64_t *n_fast, uint64_t *n_generic)
 {
 	if (n_fast)
-		*n_fast = p->n_fast;
+		*n_fast = p->n_fast + p->n_split;
 	if (n_generic)
 		*n_generic = p->n_generic;
 }
@@ -863,6 +978,10 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 	if (plan->n_generic) {
 		CUR(cudaMemsetAsync(plan->g2.nscan, 0, plan->g2_state_bytes / 2, w.s_in));
 		CUR(cudaMemsetAsync(plan->g2.first_bad, 0xFF, plan->g2_state_bytes / 2, w.s_in));
+	}
+	if (plan->n_split) {
+		CUR(cudaMemsetAsync(plan->sp.nscan, 0, plan->sp_state_bytes / 2, w.s_in));
+		CUR(cudaMemsetAsync(plan->sp.first_bad, 0xFF, plan->sp_state_bytes / 2, w.s_in));
 	}
 	for (size_t g = 0; g < ns; g++) {
 		const Segment &sg = plan->seg[g];

@@ -278,6 +278,13 @@ cudaError_t launch_gen2(const KernelArgs &a, const Gen2Args &g, const GenericScr
 	acm_scan_kernel<<<scan_grid, 32 * G2_SCAN_WARPS, 0, st>>>(a, g);
 	if (g.n_items)
 		acm_blocks_kernel<<<n_ctas, G2_THREADS, 0, st>>>(a, g, s);
+	return launch_gen2_finish(a, g, st);
+}
+
+cudaError_t launch_gen2_finish(const KernelArgs &a, const Gen2Args &g, cudaStream_t st)
+{
+	if (a.count == 0)
+		return cudaSuccess;
 	unsigned fin = a.count < 4096u ? a.count : 4096u;
 	acm_finish_kernel<<<fin, G2_THREADS, 0, st>>>(a, g);
 	return cudaGetLastError();

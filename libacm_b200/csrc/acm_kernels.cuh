@@ -94,6 +94,8 @@ struct Gen2Args {
 };
 
 cudaError_t launch_gen2(const KernelArgs &a, const Gen2Args &g, const GenericScratch &s, int n_ctas, cudaStream_t st);
+/* the finalise kernel alone (also the last stage of the split path) */
+cudaError_t launch_gen2_finish(const KernelArgs &a, const Gen2Args &g, cudaStream_t st);
 int gen2_ctas_per_sm();
 /* blocks an image of data_bits bits can hold at most (a block is at least 20 + 5 * cols bits) */
 inline uint64_t gen2_max_blocks(uint64_t n_attempt, uint64_t data_bits, uint32_t level)
@@ -102,6 +104,23 @@ inline uint64_t gen2_max_blocks(uint64_t n_attempt, uint64_t data_bits, uint32_t
 	const uint64_t fit = (data_bits + 8u) / minb + 2u;
 	return n_attempt < fit ? n_attempt : fit;
 }
+
+/* ---- the throughput path for 16-row blocks of 128 columns: walk -> unpack -> lift -> finalise (acm_split.cu).
+ * Shares the general path's records (BlockRec: pad0 = stream, pad1 = block number, pad2 = the run's epoch),
+ * per-stream tables and work items; items carry no warm-up blocks (a run rebuilds its history from the
+ * previous block's last two rows of indices). */
+struct SplitArgs : Gen2Args {
+	uint16_t *coff16;   /* [block][128]: selector positions relative to the block's P */
+	uint8_t *inter;     /* [block][2048]: quantiser indices times 2 as signed bytes, lane-major (lane l = columns l, l+32, l+64, l+96: 16 bytes each) */
+	uint16_t *wide;     /* [block][128][16]: int16 indices of the columns flagged in wmask */
+	uint32_t *wmask;    /* [block][4]: bit l of word p = column 32 p + l is in `wide` */
+	uint64_t n_blocks;  /* records of this launch: [0, n_blocks) */
+	uint32_t epoch;     /* marks the records written by this run */
+	uint32_t pad;
+};
+bool split_shape(uint32_t level, uint32_t rows);
+size_t split_bytes_per_block();
+cudaError_t launch_split(const KernelArgs &a, const SplitArgs &g, int sms, cudaStream_t st);
 
 /* level-7 / 16-row kernel (acm_fast2.cu): scan CTAs + decode CTAs; 16-bit output formats only */
 bool fast_shape(uint32_t level, uint32_t rows);

@@ -1,0 +1,909 @@
+/*
+ * acm_split.cu -- the THROUGHPUT path for 16-row blocks of 128 columns (level 7: the shape of
+ * BASELINE configs 1, 2, 4): decode_block (decode.c:580-611) split into its three stages, one
+ * kernel each, with a table of block records between them:
+ *
+ *   walk    acm_walk_kernel: fill_block's control flow (decode.c:491-502) without its data flow.
+ *           One stream per LANE, warps in lock step, the walk one table-driven state machine
+ *           (acm_walk.cuh).  A lane that finishes a block retires it on its own (record + 128
+ *           column offsets, written as coalesced rows by the whole warp) and goes on with the
+ *           next block; a lane out of blocks takes the next stream from the queue.  The walk is
+ *           the only serial part of the path; it is latency bound, so a batch of
+ *           few long streams is spread thin over all SMs (one warp per sub-partition).
+ *   unpack  acm_unpack_kernel: fill_block's data flow, the 14 fillers (decode.c:181-476).  With
+ *           the column positions known every COLUMN is an independent unit of work.  A CTA takes
+ *           a tile of 16 blocks = 2048 columns, sorts them by filler class (and the prefix-coded
+ *           ones by length) with a counting sort in shared memory, and runs every class as
+ *           straight-line code on full warps -- no divergence between a zero, a linear, a radix
+ *           and a prefix-coded column, and lanes of one warp finish together.  A column leaves as
+ *           sixteen signed bytes (the quantiser index, decode.c:174-177, times 2) in the layout
+ *           the transform's lanes read; the rare index that does not fit a byte (linear columns
+ *           of 8 bits and more) goes to a side array as int16 and is flagged in a per-block mask.
+ *   lift    acm_lift_kernel: midbuf dequantisation (decode.c:591-600), juggle_block
+ *           (decode.c:528-577) and output_values (decode.c:617-677) for runs of consecutive
+ *           blocks of one stream, one warp per run.  The transform is a 7-stage FIR cascade in
+ *           flat form: what a block needs of its predecessor is the
+ *           last two rows of quantiser indices, so a run rebuilds the reference's wrapbuf
+ *           (decode.c:803) from the previous block's bytes and runs are independent of each
+ *           other.  Inside a run the history stays in registers.  Stages 1-2 (C = 64, 32) with
+ *           lane j owning the words m = j mod 32, one transpose through shared memory, stages
+ *           3-7 over a recomputed halo, 128-bit PCM stores.
+ *   finish  acm_finish_kernel (acm_gen2.cu): per stream, what the reference's read loop reports.
+ *
+ * Nothing here waits for anything inside a kernel: the stages are ordered by the CUDA stream.
+ * Intermediates (block records, column offsets, index bytes: 2.3 KB per block + the side array)
+ * live in an arena that a plan sizes for one GROUP of streams and reuses from group to group.
+ */
+#include "acm_walk.cuh"
+#include "acm_kernels.cuh"
+
+namespace acm {
+
+namespace split {
+
+constexpr int LEVEL = 7;
+constexpr int COLS = 128;
+constexpr int ROWS = 16;
+constexpr int BLEN = COLS * ROWS;
+/* Everything the transform touches is carried times 2^QS: the lifting is linear modulo 2^32
+ * (decode.c:512), and with QS = 1 the 16 bits the output wants -- bits LEVEL..LEVEL+15 of the
+ * reference's word, decode.c:620 -- are bytes 1 and 2 of ours: two results are packed by one
+ * byte permute.  The factor rides in the index bytes (unpack stores 2 * idx), so that the
+ * dequantisation is ONE two-way dot product per word: byte x val. */
+constexpr int QS = 1;
+constexpr int OSH = LEVEL + QS; /* 8 */
+
+/* ================================================================== walk */
+
+using namespace walk;
+
+constexpr int WALK_THREADS_MAX = 32 * SW;
+
+__global__ void __launch_bounds__(WALK_THREADS_MAX, 1) acm_walk_kernel(KernelArgs a, SplitArgs g)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	SmemWalk &sm = *reinterpret_cast<SmemWalk *>(smem_raw);
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	for (int i = tid; i < ACM_UNI_PAGES * ACM_UNI_PSIZE / 2; i += blockDim.x)
+		reinterpret_cast<uint32_t *>(sm.uni16)[i] = reinterpret_cast<const uint32_t *>(a.tables->uni16)[i];
+	for (int i = tid; i < (RW + 5) * RROW; i += blockDim.x)
+		(&sm.ring[0][0])[i] = 0u;
+	__syncthreads();
+
+	Ring ring;
+	const uint32_t lane4 = 4u * (uint32_t)(warp * 32 + lane);
+	ring.rw = &sm.ring[0][warp * 32 + lane];
+	ring.pol = l2_keep_policy();
+	ring.safe = a.blob;
+	ring.hold_c0 = 0u;
+	ring.idle();
+	uint16_t *const off0 = reinterpret_cast<uint16_t *>(&sm.off[warp][lane * OFFP]);
+	const uint32_t cp0 = (uint32_t)__cvta_generic_to_shared(off0);
+	const unsigned char *uni = reinterpret_cast<const unsigned char *>(sm.uni16);
+
+	/* mode: 0 no stream, 1 block header pending, 2 walking, 3 block walked (to retire) */
+	int mode = 0;
+	bool exhausted = false, hdr_eof = false;
+	uint32_t cur = 0, P = 0, blk = 0, limit = 0, nmax = 0, val = 0;
+	uint64_t rec_base = 0;
+	uint32_t cp = cp0;
+	const uint32_t cpend = cp0 + 2u * COLS;
+	Walk s;
+	s.Q = 0u;
+	s.Q32 = 0u;
+	s.s8 = UNI_HALT8;
+	s.msk = MSK_K;
+
+	for (;;) {
+		/* ---- retire walked blocks: verdict, record, the 128 column offsets as one 256-byte row */
+		int status = SCAN_EOF;
+		uint32_t ncols = 0, pend = P;
+		if (mode == 3) {
+			if (hdr_eof) {
+				/* pwr / val cannot be read: GET_BITS_EXPECT_EOF decode.c:588-589 */
+			} else if (s.s8 == UNI_HALT8 && s.Q + 1u <= limit) {
+				status = SCAN_OK; /* 128 columns, every read inside the stream */
+				ncols = COLS;
+				pend = s.Q + 1u;
+			} else {
+				/* bad selector, or the stream ended inside the block: walk it again with the
+				 * reference's verdicts (at most once per stream) */
+				const DevStream d = a.streams[cur];
+				BitReader br;
+				br.init(reinterpret_cast<const uint32_t *>(a.blob + d.base_off), d.file_end);
+				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS, off0, P,
+								 a.tables->kind, a.tables->k8);
+				status = sc.status;
+				ncols = sc.ncols;
+				pend = sc.end;
+				val = (uint32_t)sc.val;
+				if (a.prof)
+					atomicAdd(a.prof + 33, 1ull);
+			}
+		}
+		{
+			const unsigned wm = __ballot_sync(0xFFFFFFFFu, mode == 3);
+			uint16_t *const row = g.coff16 + (rec_base + blk) * (uint64_t)COLS;
+			const unsigned long long row64 = (unsigned long long)(uintptr_t)row;
+			__syncwarp();
+			for (unsigned mm = wm; mm; mm &= mm - 1u) {
+				const int i = __ffs((int)mm) - 1;
+				const unsigned long long r = __shfl_sync(0xFFFFFFFFu, row64, i);
+				const uint2 v = *reinterpret_cast<const uint2 *>(&sm.off[warp][i * OFFP + 8 * lane]);
+				reinterpret_cast<uint2 *>((uintptr_t)r)[lane] = v;
+			}
+			__syncwarp();
+		}
+		if (mode == 3) {
+			uint4 *rp = reinterpret_cast<uint4 *>(g.rec + rec_base + blk);
+			rp[0] = make_uint4(P, pend, val, (uint32_t)status);
+			rp[1] = make_uint4(ncols, cur, blk, g.epoch);
+			blk++;
+			if (status != SCAN_OK || blk >= nmax) {
+				g.nscan[cur] = blk; /* the stream ends with this block */
+				mode = 0;
+			} else {
+				P = pend;
+				mode = 1;
+			}
+		}
+		/* ---- a lane without a stream takes the next one from the queue */
+		if (mode == 0 && !exhausted) {
+			const uint32_t idx = atomicAdd(a.counter, 1u);
+			if (idx < a.count) {
+				const DevStream d = a.streams[idx];
+				const Gen2Stream gs = g.gs[idx];
+				cur = idx;
+				P = d.bit0;
+				blk = 0;
+				limit = d.file_end + 8u;
+				nmax = d.n_attempt < gs.max_blocks ? d.n_attempt : gs.max_blocks;
+				rec_base = gs.rec_base;
+				if (nmax == 0) {
+					g.nscan[cur] = 0u;
+				} else {
+					ring.start(a.blob + d.base_off, a.blob_room > d.base_off ? a.blob_room - d.base_off : 0,
+						   d.file_end, P);
+					mode = 1;
+				}
+			} else {
+				exhausted = true;
+				ring.idle();
+				P = 0;
+			}
+		} else if (mode == 0) {
+			/* out of streams: over the two zero ring words, on the HALT page */
+		}
+		if (mode == 1) {
+			s.Q = P - 1u; /* P = 0 is a position like any other (Q wraps) */
+			s.Q32 = s.Q << 5;
+			s.s8 = UNI_HALT8;
+			s.msk = MSK_K;
+			cp = cp0;
+			hdr_eof = false;
+		} else if (mode == 0) {
+			s.Q = 0u;
+			s.Q32 = 0u;
+			s.s8 = UNI_HALT8;
+			s.msk = MSK_K;
+		}
+		if (!__any_sync(0xFFFFFFFFu, mode != 0 || !exhausted))
+			break;
+		/* ---- walk until some lane has a block to retire */
+		do {
+			ring.topup(s.Q + 1u);
+			if (mode == 1) {
+				/* pwr(4) / val(16): decode.c:588-589 */
+				if (s.Q + 21u > limit) {
+					hdr_eof = true;
+					mode = 3;
+				} else if (s.Q + 1u <= ring.ready_p) {
+					const uint32_t *rp = ring_word(&sm.ring[0][0], lane4, s.Q32);
+					const uint32_t w1 = fsr(rp[0], rp[RROW], s.Q);
+					val = (w1 >> 5) & 0xFFFFu;
+					s.Q += 20u;
+					s.Q32 = s.Q << 5;
+					s.s8 = 0u;
+					s.msk = MSK_SEL;
+					mode = 2;
+				}
+			}
+#pragma unroll 4
+			for (int k = 0; k < PERIOD; k++)
+				step(s, cp, cpend, P - 1u, &sm.ring[0][0], lane4, ring.ready_p, uni);
+			if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
+				mode = 3;
+		} while (!__any_sync(0xFFFFFFFFu, mode == 3 || (mode == 0 && !exhausted)));
+	}
+}
+
+/* ================================================================== unpack */
+
+constexpr int UB = 16;              /* blocks per tile */
+constexpr int U_THREADS = 256;
+constexpr int U_COLS = UB * COLS;   /* 2048 columns per tile */
+constexpr int U_PER = U_COLS / U_THREADS;
+/* work classes, in the order the tile's columns are processed */
+enum { B_ZERO = 0, B_LIN = 1, B_WIDE = 2, B_T0 = 3, B_K0 = 6, B_NONE = 14, NBUCKET = 15 };
+
+struct SmemUnpack {
+	uint64_t k8w[ACM_K8_SIZE];
+	uint16_t t[ACM_T_SIZE];
+	uint8_t kind[32];
+	uint32_t pos[U_COLS];        /* P of the column's selector */
+	uint16_t list[U_COLS];       /* the tile's columns, sorted by class: column | class << 11 */
+	uint8_t sel[U_COLS];
+	uint32_t cnt[NBUCKET + 1], base[NBUCKET + 1];
+	uint32_t wmask[UB][4];
+	const uint32_t *bbase[UB];   /* per block of the tile: stream base */
+	uint32_t bP[UB], bfe[UB], bstream[UB], bno[UB], bcheck[UB], bok[UB];
+};
+
+/* word i of a stream, with the reference's end-of-file rule (bits at and past file_end read as
+ * zero, decode.c:57-61); never touches memory past the word that holds the file's last bit */
+struct StreamWords {
+	const uint32_t *w;
+	uint32_t fe_word, fe_tail;
+	__device__ __forceinline__ uint32_t word(uint32_t i) const
+	{
+		if (i < fe_word)
+			return __ldg(w + i);
+		if (i == fe_word && fe_tail)
+			return __ldg(w + i) & ((1u << fe_tail) - 1u);
+		return 0u;
+	}
+};
+
+/* eight 4-bit two's complement values -> eight signed bytes, times 2^QS */
+__device__ __forceinline__ void nib_to_bytes(uint32_t a, uint32_t &b0, uint32_t &b1)
+{
+	const uint32_t lo4 = a & 0x0F0F0F0Fu, hi4 = (a >> 4) & 0x0F0F0F0Fu;
+	const uint32_t n0 = __byte_perm(lo4, hi4, 0x5140), n1 = __byte_perm(lo4, hi4, 0x7362);
+	/* sign fill: bit 3 of the nibble, times (0xF0 << QS & 0xFF) / 8 */
+	constexpr uint32_t FILL = ((0xF0u << QS) & 0xFFu) >> 3;
+	b0 = (n0 << QS) | ((n0 & 0x08080808u) * FILL);
+	b1 = (n1 << QS) | ((n1 & 0x08080808u) * FILL);
+}
+
+__global__ void __launch_bounds__(U_THREADS) acm_unpack_kernel(KernelArgs a, SplitArgs g)
+{
+	__shared__ SmemUnpack sm;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	for (int i = tid; i < ACM_K8_SIZE; i += U_THREADS)
+		sm.k8w[i] = a.tables->k8w[i];
+	for (int i = tid; i < ACM_T_SIZE; i += U_THREADS)
+		sm.t[i] = a.tables->t[i];
+	if (tid < 32)
+		sm.kind[tid] = a.tables->kind[tid];
+
+	for (uint64_t tile = blockIdx.x; tile * UB < g.n_blocks; tile += gridDim.x) {
+		const uint64_t g0 = tile * UB;
+		__syncthreads(); /* the previous tile is done with the shared state */
+		/* ---- the tile's blocks */
+		if (tid < UB) {
+			const uint64_t gb = g0 + tid;
+			uint32_t check = 0, ok = 0;
+			if (gb < g.n_blocks) {
+				const uint4 r0 = __ldcg(reinterpret_cast<const uint4 *>(g.rec + gb));
+				const uint4 r1 = __ldcg(reinterpret_cast<const uint4 *>(g.rec + gb) + 1);
+				if (r1.w == g.epoch) { /* walked in this run */
+					const int status = (int)r0.w;
+					const DevStream d = a.streams[r1.y];
+					ok = status == SCAN_OK;
+					/* column ncols is included when its payload ran past the limit: a radix code
+					 * that still fits may be out of range first (decode.c:412/:438/:464) */
+					check = ok ? (uint32_t)COLS : r1.x + (status == -7 ? 1u : 0u);
+					sm.bP[tid] = r0.x;
+					sm.bfe[tid] = d.file_end;
+					sm.bstream[tid] = r1.y;
+					sm.bno[tid] = r1.z;
+					sm.bbase[tid] = reinterpret_cast<const uint32_t *>(a.blob + d.base_off);
+				}
+			}
+			sm.bcheck[tid] = check;
+			sm.bok[tid] = ok;
+		}
+		if (tid < NBUCKET + 1)
+			sm.cnt[tid] = 0u;
+		if (tid < UB * 4)
+			(&sm.wmask[0][0])[tid] = 0u;
+		__syncthreads();
+
+		/* ---- classify: where the column's selector sits, what it says, the class's running count */
+		uint32_t mine[U_PER]; /* class << 16 | rank */
+#pragma unroll
+		for (int k = 0; k < U_PER; k++) {
+			const uint32_t cid = (uint32_t)tid + (uint32_t)k * U_THREADS;
+			const uint32_t bi = cid >> 7, col = cid & 127u;
+			uint32_t cls = B_NONE;
+			if (col < sm.bcheck[bi]) {
+				const uint32_t off = g.coff16[(g0 + bi) * (uint64_t)COLS + col];
+				const uint32_t Pc = sm.bP[bi] + off;
+				StreamWords sw;
+				sw.w = sm.bbase[bi];
+				sw.fe_word = sm.bfe[bi] >> 5;
+				sw.fe_tail = sm.bfe[bi] & 31u;
+				const uint32_t iw = Pc >> 5;
+				const uint32_t w0 = sw.word(iw), w1 = (Pc & 31u) > 27u ? sw.word(iw + 1) : 0u;
+				const uint32_t ind = fsr(w0, w1, Pc) & 31u;
+				const uint32_t kind = sm.kind[ind];
+				const uint32_t c = kind & 7u, sub = kind >> 3;
+				sm.pos[cid] = Pc;
+				sm.sel[cid] = (uint8_t)ind;
+				if (c == ACM_CLS_T) {
+					cls = B_T0 + sub;
+				} else if (sm.bok[bi]) {
+					if (c == ACM_CLS_ZERO) {
+						cls = B_ZERO;
+					} else if (c == ACM_CLS_LINEAR) {
+						cls = ind <= 8u - QS ? B_LIN : B_WIDE;
+					} else if (c == ACM_CLS_K) {
+						/* by payload length: lanes of a warp then run about the same number of steps */
+						const uint32_t nxt = col + 1u < (uint32_t)COLS
+									     ? g.coff16[(g0 + bi) * (uint64_t)COLS + col + 1u]
+									     : 0xFFFFu;
+						uint32_t len = nxt - off - 5u; /* 8 .. 80 bits; the last column: unknown, long */
+						len = len > 80u ? 80u : len;
+						cls = B_K0 + (len > 16u ? (len - 9u) >> 3 : 0u); /* 0 .. 8 -> eight classes */
+						cls = cls > B_K0 + 7u ? B_K0 + 7u : cls;
+					}
+				}
+			}
+			/* rank within the class: one shared-memory atomic per class and warp */
+			const unsigned peers = __match_any_sync(0xFFFFFFFFu, cls);
+			uint32_t base = 0;
+			const int leader = __ffs((int)peers) - 1;
+			if (lane == leader)
+				base = atomicAdd(&sm.cnt[cls], (uint32_t)__popc(peers));
+			base = __shfl_sync(0xFFFFFFFFu, base, leader);
+			mine[k] = (cls << 16) | (base + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+		}
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t acc = 0;
+			for (int b = 0; b < NBUCKET; b++) {
+				sm.base[b] = acc;
+				acc += b == B_NONE ? 0u : sm.cnt[b];
+			}
+			sm.base[NBUCKET] = acc;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < U_PER; k++) {
+			const uint32_t cid = (uint32_t)tid + (uint32_t)k * U_THREADS;
+			const uint32_t cls = mine[k] >> 16, rank = mine[k] & 0xFFFFu;
+			if (cls != B_NONE)
+				sm.list[sm.base[cls] + rank] = (uint16_t)(cid | (cls << 11));
+		}
+		__syncthreads();
+
+		/* ---- unpack, class by class, 32 columns per warp and turn */
+		const uint32_t n_items = sm.base[NBUCKET];
+		for (uint32_t it0 = 32u * (uint32_t)warp; it0 < n_items; it0 += 32u * (U_THREADS / 32)) {
+			const uint32_t it = it0 + (uint32_t)lane;
+			const bool have = it < n_items;
+			const uint32_t ent = have ? sm.list[it] : 0u;
+			const uint32_t cid = ent & 2047u, cls = have ? ent >> 11 : (uint32_t)B_NONE;
+			const uint32_t bi = cid >> 7, col = cid & 127u;
+			const uint32_t PP = sm.pos[cid] + 5u; /* payload */
+			const uint64_t gb = g0 + bi;
+			StreamWords sw;
+			sw.w = sm.bbase[bi];
+			sw.fe_word = sm.bfe[bi] >> 5;
+			sw.fe_tail = sm.bfe[bi] & 31u;
+			uint4 *const dst = reinterpret_cast<uint4 *>(g.inter + gb * (uint64_t)BLEN + (col & 31u) * 64u + (col >> 5) * 16u);
+			uint32_t a0 = 0u, a1 = 0u;
+			bool nib = false;
+			const bool isk = cls >= B_K0 && cls < B_NONE, ist = cls >= B_T0 && cls < B_K0;
+			if (__any_sync(0xFFFFFFFFu, isk)) {
+				if (isk) {
+					const uint32_t iw = PP >> 5;
+					uint32_t w0, w1, w2, w3;
+					if (iw + 4u < sw.fe_word) {
+						w0 = __ldg(sw.w + iw); w1 = __ldg(sw.w + iw + 1); w2 = __ldg(sw.w + iw + 2); w3 = __ldg(sw.w + iw + 3);
+					} else {
+						w0 = sw.word(iw); w1 = sw.word(iw + 1); w2 = sw.word(iw + 2); w3 = sw.word(iw + 3);
+					}
+					const uint32_t lo = fsr(w0, w1, PP), mid = fsr(w1, w2, PP), hi = fsr(w2, w3, PP);
+					fast2::unpack_k(lo, mid, hi, sm.kind[sm.sel[cid]] >> 3, sm.k8w, a0, a1);
+					nib = true;
+				}
+				__syncwarp();
+			}
+			if (__any_sync(0xFFFFFFFFu, ist)) {
+				if (ist) {
+					const uint32_t iw = PP >> 5;
+					const uint32_t w0 = sw.word(iw), w1 = sw.word(iw + 1), w2 = sw.word(iw + 2);
+					const uint32_t lo = fsr(w0, w1, PP), mid = fsr(w1, w2, PP);
+					const int bad = fast2::unpack_t(lo, mid, PP, sm.bfe[bi] + 8u, cls - B_T0, sm.t, a0, a1);
+					if (bad)
+						atomicMin(g.first_bad + sm.bstream[bi], sm.bno[bi]);
+					nib = sm.bok[bi] != 0u;
+				}
+				__syncwarp();
+			}
+			if (nib) {
+				uint4 v;
+				nib_to_bytes(a0, v.x, v.y);
+				nib_to_bytes(a1, v.z, v.w);
+				*dst = v;
+			}
+			if (cls == B_ZERO)
+				*dst = make_uint4(0u, 0u, 0u, 0u); /* f_zero decode.c:181-188 */
+			const bool isl = cls == B_LIN || cls == B_WIDE;
+			if (__any_sync(0xFFFFFFFFu, isl)) {
+				if (isl) {
+					/* f_linear decode.c:196-206: code - 2^(ind-1) */
+					uint32_t v[ROWS];
+					fast2::unpack_linear(sw, PP, (uint32_t)sm.sel[cid], 1, v);
+					if (cls == B_LIN) {
+						uint32_t q[4];
+#pragma unroll
+						for (int j = 0; j < 4; j++) {
+							const uint32_t p01 = __byte_perm(v[4 * j] << QS, v[4 * j + 1] << QS, 0x0040);
+							const uint32_t p23 = __byte_perm(v[4 * j + 2] << QS, v[4 * j + 3] << QS, 0x0040);
+							q[j] = __byte_perm(p01, p23, 0x5410);
+						}
+						*dst = make_uint4(q[0], q[1], q[2], q[3]);
+					} else {
+						uint32_t q[8];
+#pragma unroll
+						for (int j = 0; j < 8; j++)
+							q[j] = __byte_perm(v[2 * j], v[2 * j + 1], 0x5410);
+						uint4 *wd = reinterpret_cast<uint4 *>(g.wide + (gb * COLS + col) * (uint64_t)ROWS);
+						wd[0] = make_uint4(q[0], q[1], q[2], q[3]);
+						wd[1] = make_uint4(q[4], q[5], q[6], q[7]);
+						atomicOr(&sm.wmask[bi][col >> 5], 1u << (col & 31u));
+					}
+				}
+				__syncwarp();
+			}
+		}
+		__syncthreads();
+		if (tid < UB * 4) {
+			const uint64_t gb = g0 + (tid >> 2);
+			if (gb < g.n_blocks && sm.bok[tid >> 2])
+				g.wmask[gb * 4u + (tid & 3)] = sm.wmask[tid >> 2][tid & 3];
+		}
+	}
+}
+
+/* ================================================================== lift */
+
+constexpr int L_WARPS = 8;
+constexpr int L_THREADS = 32 * L_WARPS;
+constexpr int XPRE = 68;                     /* chunk -1: the previous block's last 64 stage-2 words (+4 pad) */
+constexpr int XWORDS = XPRE + BLEN + 4 * 32; /* transpose layout: 4 pad words per 64 */
+constexpr int LSTAGE_W = BLEN / 4 + 16;      /* the block's index bytes, its record (8 words) and wide mask (4 words) */
+constexpr int LB_WORDS = XWORDS + LSTAGE_W;  /* per warp */
+constexpr size_t LIFT_SMEM = (size_t)L_WARPS * LB_WORDS * 4;
+
+static_assert((XWORDS * 4) % 16 == 0 && (LB_WORDS * 4) % 16 == 0, "16-byte aligned staging");
+
+__device__ __forceinline__ uint32_t lift(uint32_t a, uint32_t p1, uint32_t p2, bool odd)
+{
+	/* decode.c:518-519 */
+	const uint32_t s = a + p2;
+	return odd ? 2u * p1 - s : 2u * p1 + s;
+}
+
+/* two results -> one 32-bit word of 16-bit PCM: bytes 1, 2 of a and of b (OSH = 8) */
+__device__ __forceinline__ uint32_t pack2(uint32_t a, uint32_t b, uint32_t sel, uint32_t flip)
+{
+	return __byte_perm(a, b, sel) ^ flip;
+}
+
+/* what a block needs of its predecessor, per lane (the reference's wrapbuf, decode.c:803, in the
+ * basis of the flat form): the last four stage-1 inputs, the last two stage-1 and stage-2 outputs */
+struct Hist {
+	uint32_t hx[4], hy[2], hz[2];
+};
+
+/* byte `j` (0..3) of w times val, as a two-way dot product: lo/hi picks the byte pair, the
+ * 16-bit operand (val, 0) or (0, val) the byte of the pair.  val is unsigned, the byte signed. */
+template <int J>
+__device__ __forceinline__ uint32_t byte_mul(uint32_t w, uint32_t v_lo, uint32_t v_hi)
+{
+	uint32_t d;
+	if (J == 0)
+		asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(v_lo), "r"(w), "r"(0));
+	else if (J == 1)
+		asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(v_hi), "r"(w), "r"(0));
+	else if (J == 2)
+		asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(v_lo), "r"(w), "r"(0));
+	else
+		asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(v_hi), "r"(w), "r"(0));
+	return d;
+}
+
+/*
+ * One 16-word piece (window words t = 16 K .. 16 K + 15) of lifting stages 3..7.  Stage 3 runs
+ * from K = 2, stages 4-6 (S46) from K = 3, stage 7 and the output (OUT) from K = 4; ODD = K & 1 is
+ * the row parity of stage 3.  P1 = the stage-3 inputs of piece K - 1, A3..A6 = what the later
+ * stages need of piece K - 1; all are replaced by this piece's.  The caller runs the pieces in
+ * pairs (even, odd): within a pair nothing is copied and the stage-3 sign is a constant.
+ */
+template <int ODD, bool S46, bool OUT, bool CKS>
+__device__ __forceinline__ void s37_piece(const int K, const uint32_t *win, uint32_t (&P1)[16], uint32_t (&A3)[16],
+					  uint32_t (&A4)[8], uint32_t (&A5)[4], uint32_t (&A6)[2], uint4 *dst, bool full,
+					  uint32_t n, int lane, uint32_t pos0, uint32_t sel, uint32_t flip, uint32_t bias,
+					  unsigned long long &cks)
+{
+	/* word t of the window lives at t + (t >= 64 ? 4 : 0) */
+	const uint4 *p0 = reinterpret_cast<const uint4 *>(win + 16 * K + (K >= 4 ? 4 : 0));
+	const uint4 *p2 = reinterpret_cast<const uint4 *>(win + 16 * (K - 2) + (K >= 6 ? 4 : 0));
+	uint32_t a3[16], c0[16];
+#pragma unroll
+	for (int q = 0; q < 4; q++) {
+		const uint4 v0 = p0[q], v2 = p2[q];
+		c0[4 * q] = v0.x; c0[4 * q + 1] = v0.y; c0[4 * q + 2] = v0.z; c0[4 * q + 3] = v0.w;
+		/* C = 16: 2*in[t-16] +- (in[t] + in[t-32]); row parity = K & 1 */
+		a3[4 * q + 0] = lift(v0.x, P1[4 * q + 0], v2.x, ODD);
+		a3[4 * q + 1] = lift(v0.y, P1[4 * q + 1], v2.y, ODD);
+		a3[4 * q + 2] = lift(v0.z, P1[4 * q + 2], v2.z, ODD);
+		a3[4 * q + 3] = lift(v0.w, P1[4 * q + 3], v2.w, ODD);
+	}
+	if (S46) {
+		uint32_t a4[16], a5[16], a6[16];
+#pragma unroll
+		for (int j = 0; j < 16; j++) /* C = 8 */
+			a4[j] = lift(a3[j], j >= 8 ? a3[j - 8] : A3[j + 8], A3[j], (j >> 3) & 1);
+#pragma unroll
+		for (int j = 0; j < 16; j++) /* C = 4 */
+			a5[j] = lift(a4[j], j >= 4 ? a4[j - 4] : A4[j + 4], j >= 8 ? a4[j - 8] : A4[j], (j >> 2) & 1);
+#pragma unroll
+		for (int j = 0; j < 16; j++) /* C = 2 */
+			a6[j] = lift(a5[j], j >= 2 ? a5[j - 2] : A5[j + 2], j >= 4 ? a5[j - 4] : A5[j], (j >> 1) & 1);
+		if (OUT) {
+			uint32_t pk[8];
+#pragma unroll
+			for (int j = 0; j < 16; j += 2) { /* C = 1 */
+				const uint32_t v0 = lift(a6[j], j >= 1 ? a6[j - 1] : A6[1], j >= 2 ? a6[j - 2] : A6[0], 0);
+				const uint32_t v1 = lift(a6[j + 1], a6[j], j >= 1 ? a6[j - 1] : A6[1], 1);
+				pk[j >> 1] = pack2(v0, v1, sel, flip);
+				if (CKS) {
+					/* u_i as an unsigned 16-bit value, independent of byte order */
+					const uint32_t m = pos0 + 64u * lane + 16u * (uint32_t)(K - 4) + (uint32_t)j;
+					const uint32_t w0 = ((v0 >> OSH) + bias) & 0xFFFFu;
+					const uint32_t w1 = ((v1 >> OSH) + bias) & 0xFFFFu;
+					if (m - pos0 < n)
+						cks += (unsigned long long)(m + 1u) * (w0 + 1ull);
+					if (m + 1u - pos0 < n)
+						cks += (unsigned long long)(m + 2u) * (w1 + 1ull);
+				}
+			}
+			const int q = 2 * (K - 4);
+			if (full) {
+				__stcs(dst + q, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+				__stcs(dst + q + 1, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+			} else {
+				/* last block of a stream: word-granular tail */
+				uint16_t *d16 = reinterpret_cast<uint16_t *>(dst + q);
+#pragma unroll 1
+				for (int e = 0; e < 16; e++) {
+					const uint32_t m = 64u * lane + 8u * q + e;
+					const uint32_t w = e < 8 ? (e < 4 ? (e < 2 ? pk[0] : pk[1]) : (e < 6 ? pk[2] : pk[3]))
+								 : (e < 12 ? (e < 10 ? pk[4] : pk[5]) : (e < 14 ? pk[6] : pk[7]));
+					if (m < n)
+						d16[e] = (uint16_t)(w >> (16 * (e & 1)));
+				}
+			}
+		}
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+			A4[j] = a4[8 + j];
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+			A5[j] = a5[12 + j];
+		A6[0] = a6[14];
+		A6[1] = a6[15];
+	}
+#pragma unroll
+	for (int j = 0; j < 16; j++) {
+		A3[j] = a3[j];
+		P1[j] = c0[j];
+	}
+}
+
+/* stage 1 (C = 64) output i of the lane: m-64 -> i-2, m-128 -> i-4; row parity = (i >> 1) & 1; the
+ * "+1" of decode.c:561-564 (m % 64 == 0: lane 0, even i) rides in the first add */
+__device__ __forceinline__ uint32_t stage1(uint32_t xi, uint32_t p1, uint32_t p2, int i, uint32_t one0)
+{
+	const bool odd = (i >> 1) & 1;
+	const uint32_t sum = (i & 1) ? xi + p2 : odd ? xi + p2 - one0 : xi + p2 + one0;
+	return odd ? 2u * p1 - sum : 2u * p1 + sum;
+}
+
+/*
+ * Transform + output of one block by one warp.  x[i] = the dequantised word m = 32 i + lane of the
+ * block (row i / 4, column 32 (i % 4) + lane); xs0 = the warp's transpose buffer; h = the history
+ * left by the previous block, replaced by this block's.  n = words to emit (<= 2048; 0: history
+ * only).  Returns this lane's checksum contribution.
+ */
+template <bool CKS>
+__device__ __forceinline__ unsigned long long juggle_and_store(uint32_t (&x)[64], Hist &h, uint32_t *xs0, int lane,
+							       uint8_t *out, uint32_t pos0, uint32_t n, const Format fmt)
+{
+	uint32_t *xs = xs0 + XPRE;
+	unsigned long long cks = 0ull;
+	const uint32_t one0 = lane == 0 ? 1u << QS : 0u;
+	uint32_t y[64];
+#pragma unroll
+	for (int i = 0; i < 64; i++) {
+		const uint32_t p1 = i >= 2 ? x[i - 2] : h.hx[i + 2];
+		const uint32_t p2 = i >= 4 ? x[i - 4] : h.hx[i];
+		y[i] = stage1(x[i], p1, p2, i, one0);
+	}
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+		h.hx[k] = x[60 + k];
+	/* chunk -1 = the previous block's last 64 stage-2 words */
+	xs[-XPRE + lane] = h.hz[0];
+	xs[-XPRE + 32 + lane] = h.hz[1];
+#pragma unroll
+	for (int i = 0; i < 64; i++) {
+		/* C = 32: m-32 -> i-1, m-64 -> i-2; row parity = i & 1 */
+		const uint32_t p1 = i >= 1 ? y[i - 1] : h.hy[1];
+		const uint32_t p2 = i >= 2 ? y[i - 2] : h.hy[i];
+		const uint32_t z = lift(y[i], p1, p2, i & 1);
+		/* transpose layout: word m lives at m + 4 * (m / 64); m / 64 = i / 2 for every lane */
+		xs[32 * i + lane + 4 * (i >> 1)] = z;
+		if (i == 62)
+			h.hz[0] = z;
+		if (i == 63)
+			h.hz[1] = z;
+	}
+	h.hy[0] = y[62];
+	h.hy[1] = y[63];
+	__syncwarp();
+
+	/* ---- stages 3..7: lane owns m in [64 lane, 64 lane + 64) and walks the 128-word window made
+	 * of the 64 words before it (the halo: the previous lane's chunk, chunk -1 for lane 0) and its
+	 * own, in 16-word pieces k = 2..7.  A stage is only run where its inputs are complete: stage 3
+	 * from t = 32, stages 4-6 from t = 48, stage 7 (= the output) from t = 64. */
+	const uint32_t sel = fmt.be ? 0x5612u : 0x6521u;
+	const uint32_t flip = fmt.bias ? (fmt.be ? 0x00800080u : 0x80008000u) : 0u;
+	const bool full = (uint32_t)(64 * lane + 64) <= n;
+	uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)pos0 + 64u * lane) * 2u);
+	const uint32_t *win = xs + 68 * (lane - 1);
+	if (n) {
+		uint32_t A3[16], A4[8], A5[4], A6[2], P1[16];
+#pragma unroll
+		for (int j = 0; j < 16; j++)
+			A3[j] = 0u;
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+			A4[j] = 0u;
+		A5[0] = A5[1] = A5[2] = A5[3] = 0u;
+		A6[0] = A6[1] = 0u;
+#pragma unroll
+		for (int q = 0; q < 4; q++) {
+			const uint4 v = reinterpret_cast<const uint4 *>(win + 16)[q];
+			P1[4 * q] = v.x; P1[4 * q + 1] = v.y; P1[4 * q + 2] = v.z; P1[4 * q + 3] = v.w;
+		}
+		s37_piece<0, false, false, CKS>(2, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+		s37_piece<1, true, false, CKS>(3, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+#pragma unroll 1
+		for (int k = 4; k < 8; k += 2) {
+			s37_piece<0, true, true, CKS>(k, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+			s37_piece<1, true, true, CKS>(k + 1, win, P1, A3, A4, A5, A6, dst, full, n, lane, pos0, sel, flip, fmt.bias, cks);
+		}
+	}
+	__syncwarp(); /* all shared-memory reads of this block are done */
+	return cks;
+}
+
+/* the lane's 64 dequantised words of a block from its staged index bytes (column p = 32 p + lane
+ * is the p-th 16 bytes: row r is byte r), val = the block's multiplier; the columns flagged in wm
+ * come from the side array as int16 */
+__device__ __forceinline__ void dequant(uint32_t (&x)[64], const uint4 *bytes, uint32_t val, const uint4 wm,
+					const uint16_t *wide_blk, int lane)
+{
+	const uint32_t v_lo = val & 0xFFFFu, v_hi = val << 16;
+#pragma unroll
+	for (int p = 0; p < 4; p++) {
+		const uint4 q = bytes[p];
+		const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			x[4 * (4 * j + 0) + p] = byte_mul<0>(w[j], v_lo, v_hi);
+			x[4 * (4 * j + 1) + p] = byte_mul<1>(w[j], v_lo, v_hi);
+			x[4 * (4 * j + 2) + p] = byte_mul<2>(w[j], v_lo, v_hi);
+			x[4 * (4 * j + 3) + p] = byte_mul<3>(w[j], v_lo, v_hi);
+		}
+	}
+	const uint32_t any = wm.x | wm.y | wm.z | wm.w;
+	if (any) { /* uniform */
+		const uint32_t vq = val << QS;
+#pragma unroll
+		for (int p = 0; p < 4; p++) {
+			const uint32_t m = p == 0 ? wm.x : p == 1 ? wm.y : p == 2 ? wm.z : wm.w;
+			if (m) { /* uniform: a real branch per pass with a wide column */
+				const bool mine = (m >> lane) & 1u;
+				const uint4 *src = reinterpret_cast<const uint4 *>(wide_blk + (size_t)(32 * p + lane) * ROWS);
+				uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;
+				if (mine) {
+					q0 = __ldcg(src);
+					q1 = __ldcg(src + 1);
+				}
+				const uint32_t w[8] = { q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w };
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					const uint32_t e0 = (uint32_t)((int32_t)(int16_t)(w[j] & 0xFFFFu)) * vq;
+					const uint32_t e1 = (uint32_t)((int32_t)w[j] >> 16) * vq;
+					x[4 * (2 * j) + p] = mine ? e0 : x[4 * (2 * j) + p];
+					x[4 * (2 * j + 1) + p] = mine ? e1 : x[4 * (2 * j + 1) + p];
+				}
+			}
+		}
+	}
+}
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *gp)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gp) : "memory");
+}
+
+/* asks for block gb's index bytes (every lane its own 64), record and wide mask */
+__device__ __forceinline__ void stage_block(const SplitArgs &g, uint64_t gb, uint32_t *stg, int lane)
+{
+	const uint32_t sa = (uint32_t)__cvta_generic_to_shared(stg);
+	const uint8_t *src = g.inter + gb * (uint64_t)BLEN + (uint32_t)lane * 64u;
+#pragma unroll
+	for (int p = 0; p < 4; p++)
+		cp_async16(sa + (uint32_t)lane * 64u + 16u * p, src + 16 * p);
+	if (lane < 2)
+		cp_async16(sa + BLEN + 16u * lane, reinterpret_cast<const uint8_t *>(g.rec + gb) + 16 * lane);
+	if (lane == 2)
+		cp_async16(sa + BLEN + 32u, g.wmask + gb * 4u);
+	cp_async_commit();
+}
+
+template <bool CKS>
+__global__ void __launch_bounds__(L_THREADS, 2) acm_lift_kernel(KernelArgs a, SplitArgs g)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t *wb = reinterpret_cast<uint32_t *>(smem_raw) + (size_t)warp * LB_WORDS;
+	uint32_t *stg = wb + XWORDS;
+
+	for (;;) {
+		uint32_t it = 0;
+		if (lane == 0)
+			it = atomicAdd(g.item_counter, 1u);
+		it = __shfl_sync(0xFFFFFFFFu, it, 0);
+		if (it >= g.n_items)
+			break;
+		const Gen2Item item = g.items[it];
+		const DevStream d = a.streams[item.stream];
+		const Gen2Stream gs = g.gs[item.stream];
+		const uint32_t nscan = g.nscan[item.stream];
+		uint32_t bend = item.b0 + item.nb;
+		bend = bend < nscan ? bend : nscan;
+		if (item.b0 >= bend)
+			continue;
+		uint8_t *out = a.out + d.out_off;
+		Hist h;
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			h.hx[k] = 0u;
+		h.hy[0] = h.hy[1] = h.hz[0] = h.hz[1] = 0u; /* decode.c:812: a stream starts from zero history */
+		__syncwarp();
+		if (item.b0) {
+			/* rebuild the history from the previous block's last two rows of indices (it was walked
+			 * and unpacked: a stream's records end at its first failing block) */
+			const uint64_t gp = gs.rec_base + item.b0 - 1u;
+			stage_block(g, gp, stg, lane);
+			cp_async_wait_all();
+			__syncwarp();
+			uint32_t x[64];
+			const uint4 wm = *reinterpret_cast<const uint4 *>(stg + BLEN / 4 + 8);
+			dequant(x, reinterpret_cast<const uint4 *>(stg) + 4 * lane, stg[BLEN / 4 + 2], wm,
+				g.wide + gp * (uint64_t)BLEN, lane);
+			const uint32_t one0 = lane == 0 ? 1u << QS : 0u;
+			uint32_t y[4];
+#pragma unroll
+			for (int i = 60; i < 64; i++)
+				y[i - 60] = stage1(x[i], x[i - 2], x[i - 4], i, one0);
+			h.hz[0] = lift(y[2], y[1], y[0], 0);
+			h.hz[1] = lift(y[3], y[2], y[1], 1);
+			h.hy[0] = y[2];
+			h.hy[1] = y[3];
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				h.hx[k] = x[60 + k];
+			__syncwarp();
+		}
+		stage_block(g, gs.rec_base + item.b0, stg, lane);
+		for (uint32_t b = item.b0; b < bend; b++) {
+			const uint64_t gb = gs.rec_base + b;
+			cp_async_wait_all();
+			__syncwarp();
+			const int status = (int)stg[BLEN / 4 + 3];
+			if (status != SCAN_OK)
+				break; /* the stream's last record: nothing to deliver */
+			uint32_t x[64];
+			{
+				const uint4 wm = *reinterpret_cast<const uint4 *>(stg + BLEN / 4 + 8);
+				dequant(x, reinterpret_cast<const uint4 *>(stg) + 4 * lane, stg[BLEN / 4 + 2], wm,
+					g.wide + gb * (uint64_t)BLEN, lane);
+			}
+			__syncwarp(); /* the staged bytes have been read */
+			if (b + 1u < bend)
+				stage_block(g, gb + 1u, stg, lane); /* travels while this block is transformed */
+			const uint64_t pos = (uint64_t)b * BLEN;
+			const uint32_t n = pos < d.words_limit ? (d.words_limit - pos < (uint64_t)BLEN ? (uint32_t)(d.words_limit - pos) : (uint32_t)BLEN) : 0u;
+			unsigned long long c2 = juggle_and_store<CKS>(x, h, wb, lane, out, (uint32_t)pos, n, a.fmt);
+			if (CKS) {
+				for (int o = 16; o; o >>= 1)
+					c2 += __shfl_xor_sync(0xFFFFFFFFu, c2, o);
+				if (lane == 0)
+					g.cks_blk[gb] = c2;
+			}
+		}
+		cp_async_wait_all();
+		__syncwarp();
+	}
+}
+
+} // namespace split
+
+/* ================================================================== launch */
+
+bool split_shape(uint32_t level, uint32_t rows) { return level == split::LEVEL && rows == (uint32_t)split::ROWS; }
+
+size_t split_bytes_per_block()
+{
+	return sizeof(BlockRec) + 8 + 2 * split::COLS + split::BLEN + 2 * split::BLEN + 16;
+}
+
+cudaError_t launch_split(const KernelArgs &a, const SplitArgs &g, int sms, cudaStream_t st)
+{
+	if (a.count == 0)
+		return cudaSuccess;
+	static bool configured[64] = {};
+	int dev = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	if (!configured[dev & 63]) {
+		e = cudaFuncSetAttribute(split::acm_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+					 (int)sizeof(walk::SmemWalk));
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute(split::acm_lift_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+						 (int)split::LIFT_SMEM);
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute(split::acm_lift_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+						 (int)split::LIFT_SMEM);
+		if (e != cudaSuccess)
+			return e;
+		configured[dev & 63] = true;
+	}
+	/* walk: one stream per lane; few streams are spread thin (the walk is latency bound: a warp
+	 * that has its sub-partition to itself steps almost twice as fast), many fill 8 warps per SM */
+	const uint32_t warps = (a.count + 31u) / 32u;
+	uint32_t nw = (warps + (uint32_t)sms - 1u) / (uint32_t)sms;
+	nw = nw < 1u ? 1u : nw > (uint32_t)walk::SW ? (uint32_t)walk::SW : nw;
+	uint32_t ctas = (warps + nw - 1u) / nw;
+	ctas = ctas > (uint32_t)sms ? (uint32_t)sms : ctas;
+	split::acm_walk_kernel<<<ctas, 32 * nw, sizeof(walk::SmemWalk), st>>>(a, g);
+	/* unpack: tiles of 16 blocks */
+	const uint64_t tiles = (g.n_blocks + split::UB - 1) / split::UB;
+	const uint32_t ugrid = (uint32_t)(tiles < (uint64_t)sms * 16u ? tiles : (uint64_t)sms * 16u);
+	if (ugrid)
+		split::acm_unpack_kernel<<<ugrid, split::U_THREADS, 0, st>>>(a, g);
+	/* lift: persistent CTAs, two per SM */
+	if (g.n_items) {
+		const uint32_t want = (g.n_items + split::L_WARPS - 1) / split::L_WARPS;
+		const uint32_t lgrid = want < 2u * (uint32_t)sms ? want : 2u * (uint32_t)sms;
+		if (a.fmt.checksums)
+			split::acm_lift_kernel<true><<<lgrid, split::L_THREADS, split::LIFT_SMEM, st>>>(a, g);
+		else
+			split::acm_lift_kernel<false><<<lgrid, split::L_THREADS, split::LIFT_SMEM, st>>>(a, g);
+	}
+	return launch_gen2_finish(a, g, st);
+}
+
+} // namespace acm

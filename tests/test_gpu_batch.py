@@ -9,7 +9,7 @@ from tests import corpus, gpu_util as gu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_stress_corpus_host_buffers(checker, kernel):
     imgs = corpus.images(corpus.stress_params(max_values=60_000))
     s, out = gu.decode_host(imgs, want_checksums=1, kernel=kernel)
@@ -23,7 +23,7 @@ def test_formats_device_resident(checker, be, sgned):
     assert gu.compare(imgs, s, out, checker, be=be, sgned=sgned, checksums=True) == []
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_unaligned_back_to_back_images(checker, kernel):
     imgs = corpus.images(corpus.stress_params(max_values=8_000)[::2] + corpus.fallout_params(40, seed=9, hi=30_000))
     for lead in (0, 1, 2, 3):
@@ -31,7 +31,7 @@ def test_unaligned_back_to_back_images(checker, kernel):
         assert gu.compare(imgs, s, out, checker) == []
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_single_fillers_and_negatives(checker, kernel):
     imgs = corpus.images(corpus.single_filler_params() + corpus.single_filler_params(level=7, rows=16) +
                          corpus.negative_params())
@@ -40,7 +40,7 @@ def test_single_fillers_and_negatives(checker, kernel):
     assert set(s["status"].tolist()) == {0, -6}
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(5, 7, 2), (7, 16, 1)])
 def test_truncations(checker, kernel, shape):
     level, rows, ch = shape
@@ -241,7 +241,7 @@ def test_replication_by_descriptor():
             assert np.array_equal(out[o:o + nb], first)
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_garbage_payloads_status_and_words(checker, kernel):
     """Arbitrary bytes behind a valid level-7 / 16-row header.  The PCM of such streams is not defined by
     the reference (a dequantisation index outside the block's table reads stale memory), but
@@ -300,7 +300,7 @@ def test_healthy_streams_never_take_the_re_walk_path(checker):
     plan.close()
 
 
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 2])
 def test_decode_twice_same_stream_array(checker, kernel):
     """acm_gpu_stream.status is an output: a stream array that has been through a decode -- with
     streams that ended ACM_ERR_CORRUPT (-6), ACM_ERR_UNEXPECTED_EOF (-7) and a rejected header (-3)

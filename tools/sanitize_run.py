@@ -12,6 +12,7 @@ plist = corpus.fallout_params(96, seed=3, hi=30_000) + corpus.stress_params(max_
 imgs = corpus.images(plist)
 img = gen.make_stream(level=7, rows=16, channels=1, total_values=2048 * 3 + 9, dist=gen.DIST_STRESS, seed=5)
 imgs += [img[:c] for c in (20, 300, 1500, len(img) - 2)]
-s, out = gu.decode_device(imgs, want_checksums=1)
-s2, out2 = gu.decode_host(imgs, align=1, lead=3)
+kernel = int(os.environ.get("ACM_KERNEL", "0"))
+s, out = gu.decode_device(imgs, want_checksums=1, kernel=kernel)
+s2, out2 = gu.decode_host(imgs, align=1, lead=3, kernel=kernel)
 print("statuses", sorted(set(s["status"].tolist())), "ok")
