@@ -121,6 +121,9 @@ struct SplitArgs : Gen2Args {
 bool split_shape(uint32_t level, uint32_t rows);
 size_t split_bytes_per_block();
 cudaError_t launch_split(const KernelArgs &a, const SplitArgs &g, int sms, cudaStream_t st);
+/* one stream, a range of its blocks (streaming API): see acm_split.cu */
+cudaError_t launch_split_range(const KernelArgs &a, const SplitArgs &g, uint32_t b0, uint32_t nb, uint32_t P0,
+			       int lift, int sms, cudaStream_t st);
 
 /* level-7 / 16-row kernel (acm_fast2.cu): scan CTAs + decode CTAs; 16-bit output formats only */
 bool fast_shape(uint32_t level, uint32_t rows);

@@ -94,7 +94,19 @@ __global__ void __launch_bounds__(WALK_THREADS_MAX, 1) acm_walk_kernel(KernelArg
 	s.s8 = UNI_HALT8;
 	s.msk = MSK_K;
 
+#ifdef WALK_PROF
+	/* tuning build: cycles of warp 0 of CTA 0 (the batch's longest streams) per phase -> prof[40..] */
+	unsigned long long pt0 = clock64(), pacc[5] = { 0, 0, 0, 0, 0 };
+	unsigned long long pperiods = 0, pouter = 0;
+#define WPROF(k) do { const unsigned long long t_ = clock64(); pacc[k] += t_ - pt0; pt0 = t_; } while (0)
+#else
+#define WPROF(k) do { } while (0)
+#endif
 	for (;;) {
+		WPROF(4);
+#ifdef WALK_PROF
+		pouter++;
+#endif
 		/* ---- retire walked blocks: verdict, record, the 128 column offsets as one 256-byte row */
 		int status = SCAN_EOF;
 		uint32_t ncols = 0, pend = P;
@@ -189,9 +201,14 @@ __global__ void __launch_bounds__(WALK_THREADS_MAX, 1) acm_walk_kernel(KernelArg
 		}
 		if (!__any_sync(0xFFFFFFFFu, mode != 0 || !exhausted))
 			break;
+		WPROF(0); /* 0: retire + fetch */
 		/* ---- walk until some lane has a block to retire */
 		do {
+#ifdef WALK_PROF
+			pperiods++;
+#endif
 			ring.topup(s.Q + 1u);
+			WPROF(1); /* 1: top-up */
 			if (mode == 1) {
 				/* pwr(4) / val(16): decode.c:588-589 */
 				if (s.Q + 21u > limit) {
@@ -208,13 +225,155 @@ __global__ void __launch_bounds__(WALK_THREADS_MAX, 1) acm_walk_kernel(KernelArg
 					mode = 2;
 				}
 			}
+			WPROF(2); /* 2: header */
 #pragma unroll 4
 			for (int k = 0; k < PERIOD; k++)
 				step(s, cp, cpend, P - 1u, &sm.ring[0][0], lane4, ring.ready_p, uni);
 			if (mode == 2 && (s.s8 == UNI_HALT8 || s.s8 == UNI_BAD8))
 				mode = 3;
+			WPROF(3); /* 3: steps */
 		} while (!__any_sync(0xFFFFFFFFu, mode == 3 || (mode == 0 && !exhausted)));
 	}
+#ifdef WALK_PROF
+	if (blockIdx.x == 0 && tid == 0 && a.prof) {
+		for (int k = 0; k < 5; k++)
+			a.prof[40 + k] = pacc[k];
+		a.prof[45] = pperiods;
+		a.prof[46] = pouter;
+	}
+#endif
+}
+
+/* ================================================================== walk, one stream */
+
+/*
+ * The walk of ONE stream, for the streaming API (acm_stream.cu): what bounds acm_read on a single
+ * stream is the latency of this serial walk, so here it is a scalar routine on one lane, with
+ * branches, instead of 32 streams in lock step.  Same state machine (uni16), but inside a
+ * prefix-coded column the next 96 stream bits stay in a register window (the chain of a step is
+ * table lookup -> shift -> next lookup, no load), and the window is reloaded from global memory
+ * (L1 hits: the lines ahead are prefetched once per block) at every column selector.
+ * Walks blocks [b0, b0 + nb) from bit position P0 and leaves the same records and column offsets
+ * as the batch walk; nscan[0] = the blocks walked so far (b0 + those of this launch).
+ */
+constexpr int W1_THREADS = 256;
+constexpr uint32_t W1_PBYTES = 4u << ACM_UNI_KBITS; /* bytes per page of the widened table */
+
+struct SmemWalk1 {
+	/* uni16 widened to 32-bit entries: bits to advance | byte offset of the next page << 8 -- the
+	 * lookup's result needs one shift and one mask, each off the other's path */
+	uint32_t uni32[ACM_UNI_PAGES * ACM_UNI_PSIZE];
+	uint16_t off[COLS + 8];
+};
+
+__global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, SplitArgs g, uint32_t b0, uint32_t nb, uint32_t P0)
+{
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	SmemWalk1 &sm = *reinterpret_cast<SmemWalk1 *>(smem_raw);
+	const int tid = threadIdx.x, lane = tid & 31;
+	for (int i = tid; i < ACM_UNI_PAGES * ACM_UNI_PSIZE; i += W1_THREADS) {
+		const uint32_t e = a.tables->uni16[i];
+		sm.uni32[i] = (e & 0xFFu) | (((e >> 8) * W1_PBYTES) << 8);
+	}
+	__syncthreads();
+	if (tid >= 32)
+		return;
+	const DevStream d = a.streams[0];
+	const Gen2Stream gs = g.gs[0];
+	const uint32_t *const words = reinterpret_cast<const uint32_t *>(a.blob + d.base_off);
+	const uint32_t limit = d.file_end + 8u;
+	/* the last word index a 4-word window may start at; positions beyond it only occur in blocks
+	 * that are walked again with the reference's verdicts */
+	const uint32_t room_w = a.blob_room > d.base_off ? (uint32_t)((a.blob_room - d.base_off) / 4u) : 0u;
+	const uint32_t last_i = room_w > 4u ? room_w - 4u : 0u;
+	const unsigned char *uni = reinterpret_cast<const unsigned char *>(sm.uni32);
+	constexpr uint32_t S_K0 = (uint32_t)ACM_UNI_K0 * W1_PBYTES, S_HALT = (uint32_t)ACM_UNI_HALT * W1_PBYTES,
+			   S_SKIP6 = (uint32_t)ACM_UNI_SKIP6 * W1_PBYTES;
+	constexpr uint32_t M_SEL = 0x1FFFu << 2, M_K = ((1u << ACM_UNI_KBITS) - 1u) << 2;
+	uint32_t P = P0, b = b0;
+	for (; b < b0 + nb; b++) {
+		int status = SCAN_EOF;
+		uint32_t ncols = 0, pend = P, val = 0;
+		if (lane == 0 && P + 20u <= limit) {
+			/* the block's lines, once: the loads below are L1 hits */
+			for (uint32_t k = 0; k < 12u; k++) {
+				const uint32_t wi = (P >> 5) + 32u * k;
+				if (wi < room_w)
+					asm volatile("prefetch.global.L1 [%0];" ::"l"(words + wi));
+			}
+			bool clean = true;
+			{
+				const uint32_t i = min(P >> 5, last_i);
+				val = (fsr(__ldg(words + i), __ldg(words + i + 1), P) >> 4) & 0xFFFFu; /* pwr(4) val(16): decode.c:588-589 */
+			}
+			/* R = position - 2: the 32 bits at R, masked, are the byte offset of a 4-byte table entry */
+			uint32_t R = P + 18u;
+			for (uint32_t c = 0; c < (uint32_t)COLS; c++) {
+				const uint32_t i = min(R >> 5, last_i);
+				const uint32_t *wp = words + i;
+				const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+				uint32_t lo = fsr(w0, w1, R);
+				uint32_t e = *reinterpret_cast<const uint32_t *>(uni + (lo & M_SEL));
+				sm.off[c] = (uint16_t)(R + 2u - P);
+				uint32_t adv = e & 0xFFu, pg = e >> 8;
+				R += adv;
+				if (pg == 0u)
+					continue; /* a fixed-size column, walked in one step */
+				if (pg >= S_K0 && pg < S_HALT) {
+					/* inside a prefix-coded column: <= 80 payload bits, all in the window */
+					uint32_t mid = fsr(w1, w2, R - adv), hi = fsr(w2, w3, R - adv);
+					do {
+						lo = fsr(lo, mid, adv);
+						mid = fsr(mid, hi, adv);
+						hi >>= adv;
+						e = *reinterpret_cast<const uint32_t *>(uni + (pg | (lo & M_K)));
+						adv = e & 0xFFu;
+						pg = e >> 8;
+						R += adv;
+					} while (pg != 0u);
+				} else if (pg == S_SKIP6) {
+					R += 6u; /* 16-bit linear column: 261 bits */
+				} else {
+					clean = false; /* bad selector (f_bad, decode.c:190-194) */
+					break;
+				}
+			}
+			if (clean && R + 2u <= limit) {
+				status = SCAN_OK; /* 128 columns, every read inside the stream */
+				ncols = COLS;
+				pend = R + 2u;
+			} else {
+				/* bad selector, or the stream ended inside the block: the reference's verdicts */
+				BitReader br;
+				br.init(words, d.file_end);
+				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS, sm.off, P, a.tables->kind, a.tables->k8);
+				status = sc.status;
+				ncols = sc.ncols;
+				pend = sc.end;
+				val = (uint32_t)sc.val;
+			}
+		}
+		status = __shfl_sync(0xFFFFFFFFu, status, 0);
+		pend = __shfl_sync(0xFFFFFFFFu, pend, 0);
+		__syncwarp();
+		{
+			const uint2 v = *reinterpret_cast<const uint2 *>(&sm.off[4 * lane]);
+			reinterpret_cast<uint2 *>(g.coff16 + (gs.rec_base + b) * (uint64_t)COLS)[lane] = v;
+		}
+		if (lane == 0) {
+			uint4 *rp = reinterpret_cast<uint4 *>(g.rec + gs.rec_base + b);
+			rp[0] = make_uint4(P, pend, val, (uint32_t)status);
+			rp[1] = make_uint4(ncols, 0u, b, g.epoch);
+		}
+		__syncwarp();
+		if (status != SCAN_OK) {
+			b++;
+			break; /* the stream ends with this block */
+		}
+		P = pend;
+	}
+	if (lane == 0)
+		g.nscan[0] = b;
 }
 
 /* ================================================================== unpack */
@@ -223,35 +382,51 @@ constexpr int UB = 16;              /* blocks per tile */
 constexpr int U_THREADS = 256;
 constexpr int U_COLS = UB * COLS;   /* 2048 columns per tile */
 constexpr int U_PER = U_COLS / U_THREADS;
-/* work classes, in the order the tile's columns are processed */
-enum { B_ZERO = 0, B_LIN = 1, B_WIDE = 2, B_T0 = 3, B_K0 = 6, B_NONE = 14, NBUCKET = 15 };
+/* work classes in the order they are processed: the longest first.  Prefix-coded columns by payload
+ * length (lanes of a warp then run about the same number of table steps), linear columns by
+ * their width (the field positions are compile-time constants), radix-coded ones by code. */
+enum {
+	C_K7 = 0, C_K0 = 7,   /* prefix codes, eight length classes, longest = 0 */
+	C_WIDE = 8,           /* linear, 8 .. 16 bits: int16 side array */
+	C_T2 = 9, C_T0 = 11,  /* t37, t27, t15 */
+	C_L7 = 12, C_L3 = 16, /* linear, 7 .. 3 bits */
+	NCLS = 17, C_NONE = 31
+};
+constexpr int U_LIST = U_COLS + 32 * NCLS; /* every class padded to whole warps */
 
 struct SmemUnpack {
 	uint64_t k8w[ACM_K8_SIZE];
 	uint16_t t[ACM_T_SIZE];
 	uint8_t kind[32];
-	uint32_t pos[U_COLS];        /* P of the column's selector */
-	uint16_t list[U_COLS];       /* the tile's columns, sorted by class: column | class << 11 */
-	uint8_t sel[U_COLS];
-	uint32_t cnt[NBUCKET + 1], base[NBUCKET + 1];
+	uint32_t pos[U_COLS];        /* P of the column's payload */
+	uint16_t list[U_LIST];       /* the tile's columns, sorted by class: column | aux << 11; 0xFFFF = nothing */
+	uint8_t chunk_cls[U_LIST / 32];
+	uint32_t cnt[NCLS + 1], base[NCLS + 1];
+	uint32_t next_chunk;
 	uint32_t wmask[UB][4];
 	const uint32_t *bbase[UB];   /* per block of the tile: stream base */
-	uint32_t bP[UB], bfe[UB], bstream[UB], bno[UB], bcheck[UB], bok[UB];
+	uint32_t bP[UB], bend[UB], bfe[UB], bstream[UB], bno[UB], bcheck[UB], bflags[UB];
 };
+enum { BF_OK = 1, BF_NEAR = 2 }; /* block decodes; block (and the unpackers' read-ahead) reaches the end of its file */
 
-/* word i of a stream, with the reference's end-of-file rule (bits at and past file_end read as
- * zero, decode.c:57-61); never touches memory past the word that holds the file's last bit */
+/* word i of a stream.  near = the block reaches the end of its file: bits at and past file_end read
+ * as zero (decode.c:57-61), and memory past the word that holds the file's last bit is not touched */
+__device__ __forceinline__ uint32_t ldw(const uint32_t *w, uint32_t i, uint32_t fe, bool near)
+{
+	if (!near)
+		return __ldg(w + i);
+	const uint32_t fe_word = fe >> 5, fe_tail = fe & 31u;
+	if (i < fe_word)
+		return __ldg(w + i);
+	if (i == fe_word && fe_tail)
+		return __ldg(w + i) & ((1u << fe_tail) - 1u);
+	return 0u;
+}
 struct StreamWords {
 	const uint32_t *w;
-	uint32_t fe_word, fe_tail;
-	__device__ __forceinline__ uint32_t word(uint32_t i) const
-	{
-		if (i < fe_word)
-			return __ldg(w + i);
-		if (i == fe_word && fe_tail)
-			return __ldg(w + i) & ((1u << fe_tail) - 1u);
-		return 0u;
-	}
+	uint32_t fe;
+	bool near;
+	__device__ __forceinline__ uint32_t word(uint32_t i) const { return ldw(w, i, fe, near); }
 };
 
 /* eight 4-bit two's complement values -> eight signed bytes, times 2^QS */
@@ -265,10 +440,38 @@ __device__ __forceinline__ void nib_to_bytes(uint32_t a, uint32_t &b0, uint32_t 
 	b1 = (n1 << QS) | ((n1 & 0x08080808u) * FILL);
 }
 
+/* f_linear (decode.c:196-206) for a column of IND-bit codes, IND + QS <= 8: W = the 128 stream bits
+ * from the column's payload on; the sixteen (code - 2^(IND-1)) << QS as signed bytes.  Every field
+ * position is a constant. */
+template <int IND>
+__device__ __forceinline__ uint4 lin_narrow(const uint32_t (&W)[4])
+{
+	constexpr uint32_t MASK = (1u << IND) - 1u, MIDQ = (1u << (IND - 1)) << QS;
+	constexpr uint32_t SB = MIDQ * 0x01010101u;
+	constexpr uint32_t FILLM = ((0xFFu << (IND + QS)) & 0xFFu) >> (IND - 1 + QS);
+	uint32_t q[4];
+#pragma unroll
+	for (int j = 0; j < 4; j++) {
+		uint32_t acc = 0u;
+#pragma unroll
+		for (int r = 0; r < 4; r++) {
+			const int bit = (4 * j + r) * IND, k = bit >> 5, sft = bit & 31;
+			uint32_t v = sft + IND <= 32 ? W[k] >> sft : __funnelshift_r(W[k], W[k + 1 < 4 ? k + 1 : 3], sft);
+			if (sft + IND != 32)
+				v &= MASK;
+			acc += v << (8 * r + QS);
+		}
+		/* code ^ mid = the index in IND-bit two's complement; fill the bits above its sign */
+		const uint32_t y = acc ^ SB;
+		q[j] = y | ((y & SB) * FILLM);
+	}
+	return make_uint4(q[0], q[1], q[2], q[3]);
+}
+
 __global__ void __launch_bounds__(U_THREADS) acm_unpack_kernel(KernelArgs a, SplitArgs g)
 {
 	__shared__ SmemUnpack sm;
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const int tid = threadIdx.x, lane = tid & 31;
 	for (int i = tid; i < ACM_K8_SIZE; i += U_THREADS)
 		sm.k8w[i] = a.tables->k8w[i];
 	for (int i = tid; i < ACM_T_SIZE; i += U_THREADS)
@@ -282,18 +485,22 @@ __global__ void __launch_bounds__(U_THREADS) acm_unpack_kernel(KernelArgs a, Spl
 		/* ---- the tile's blocks */
 		if (tid < UB) {
 			const uint64_t gb = g0 + tid;
-			uint32_t check = 0, ok = 0;
+			uint32_t check = 0, flags = 0;
 			if (gb < g.n_blocks) {
 				const uint4 r0 = __ldcg(reinterpret_cast<const uint4 *>(g.rec + gb));
 				const uint4 r1 = __ldcg(reinterpret_cast<const uint4 *>(g.rec + gb) + 1);
 				if (r1.w == g.epoch) { /* walked in this run */
 					const int status = (int)r0.w;
 					const DevStream d = a.streams[r1.y];
-					ok = status == SCAN_OK;
+					flags = status == SCAN_OK ? BF_OK : 0u;
 					/* column ncols is included when its payload ran past the limit: a radix code
 					 * that still fits may be out of range first (decode.c:412/:438/:464) */
-					check = ok ? (uint32_t)COLS : r1.x + (status == -7 ? 1u : 0u);
+					check = flags ? (uint32_t)COLS : r1.x + (status == -7 ? 1u : 0u);
+					/* the unpackers read up to 160 bits past a column's selector */
+					if (!flags || r0.y + 224u > d.file_end)
+						flags |= BF_NEAR;
 					sm.bP[tid] = r0.x;
+					sm.bend[tid] = r0.y - r0.x;
 					sm.bfe[tid] = d.file_end;
 					sm.bstream[tid] = r1.y;
 					sm.bno[tid] = r1.z;
@@ -301,51 +508,62 @@ __global__ void __launch_bounds__(U_THREADS) acm_unpack_kernel(KernelArgs a, Spl
 				}
 			}
 			sm.bcheck[tid] = check;
-			sm.bok[tid] = ok;
+			sm.bflags[tid] = flags;
 		}
-		if (tid < NBUCKET + 1)
+		if (tid < NCLS + 1)
 			sm.cnt[tid] = 0u;
 		if (tid < UB * 4)
 			(&sm.wmask[0][0])[tid] = 0u;
+		if (tid == 0)
+			sm.next_chunk = 0u;
 		__syncthreads();
 
-		/* ---- classify: where the column's selector sits, what it says, the class's running count */
-		uint32_t mine[U_PER]; /* class << 16 | rank */
+		/* ---- classify: where the column's payload sits, its class, the class's running count.  A warp
+		 * looks at 32 consecutive columns of one block. */
+		uint32_t mine[U_PER]; /* class << 24 | aux << 16 | rank */
 #pragma unroll
 		for (int k = 0; k < U_PER; k++) {
 			const uint32_t cid = (uint32_t)tid + (uint32_t)k * U_THREADS;
 			const uint32_t bi = cid >> 7, col = cid & 127u;
-			uint32_t cls = B_NONE;
-			if (col < sm.bcheck[bi]) {
-				const uint32_t off = g.coff16[(g0 + bi) * (uint64_t)COLS + col];
+			const uint32_t ncheck = sm.bcheck[bi], flags = sm.bflags[bi];
+			const uint16_t *coff = g.coff16 + (g0 + bi) * (uint64_t)COLS;
+			const uint32_t off = col < ncheck ? coff[col] : 0xFFFFu;
+			/* the next column's offset: the neighbour lane has it */
+			uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, off, 1);
+			if (lane == 31)
+				nxt = col + 1u < ncheck ? coff[col + 1u] : sm.bend[bi];
+			uint32_t cls = C_NONE, aux = 0u;
+			if (col < ncheck) {
 				const uint32_t Pc = sm.bP[bi] + off;
-				StreamWords sw;
-				sw.w = sm.bbase[bi];
-				sw.fe_word = sm.bfe[bi] >> 5;
-				sw.fe_tail = sm.bfe[bi] & 31u;
+				const bool near = (flags & BF_NEAR) != 0u;
+				const uint32_t *w = sm.bbase[bi];
 				const uint32_t iw = Pc >> 5;
-				const uint32_t w0 = sw.word(iw), w1 = (Pc & 31u) > 27u ? sw.word(iw + 1) : 0u;
+				const uint32_t w0 = ldw(w, iw, sm.bfe[bi], near), w1 = ldw(w, iw + 1u, sm.bfe[bi], near);
 				const uint32_t ind = fsr(w0, w1, Pc) & 31u;
 				const uint32_t kind = sm.kind[ind];
 				const uint32_t c = kind & 7u, sub = kind >> 3;
-				sm.pos[cid] = Pc;
-				sm.sel[cid] = (uint8_t)ind;
+				sm.pos[cid] = Pc + 5u;
 				if (c == ACM_CLS_T) {
-					cls = B_T0 + sub;
-				} else if (sm.bok[bi]) {
+					cls = C_T0 - sub;
+					aux = flags & BF_OK;
+				} else if (flags & BF_OK) {
 					if (c == ACM_CLS_ZERO) {
-						cls = B_ZERO;
+						/* f_zero decode.c:181-188 */
+						*reinterpret_cast<uint4 *>(g.inter + (g0 + bi) * (uint64_t)BLEN + (col & 31u) * 64u + (col >> 5) * 16u) =
+							make_uint4(0u, 0u, 0u, 0u);
 					} else if (c == ACM_CLS_LINEAR) {
-						cls = ind <= 8u - QS ? B_LIN : B_WIDE;
+						if (ind + QS <= 8u) {
+							cls = C_L3 - (ind - 3u);
+						} else {
+							cls = C_WIDE;
+							aux = ind - 8u;
+						}
 					} else if (c == ACM_CLS_K) {
-						/* by payload length: lanes of a warp then run about the same number of steps */
-						const uint32_t nxt = col + 1u < (uint32_t)COLS
-									     ? g.coff16[(g0 + bi) * (uint64_t)COLS + col + 1u]
-									     : 0xFFFFu;
-						uint32_t len = nxt - off - 5u; /* 8 .. 80 bits; the last column: unknown, long */
+						uint32_t len = nxt - off - 5u; /* 8 .. 80 bits */
 						len = len > 80u ? 80u : len;
-						cls = B_K0 + (len > 16u ? (len - 9u) >> 3 : 0u); /* 0 .. 8 -> eight classes */
-						cls = cls > B_K0 + 7u ? B_K0 + 7u : cls;
+						const uint32_t lc = len > 16u ? (len - 9u) >> 3 : 0u; /* 0 .. 8 */
+						cls = C_K0 - (lc > 7u ? 7u : lc);
+						aux = sub;
 					}
 				}
 			}
@@ -353,116 +571,125 @@ __global__ void __launch_bounds__(U_THREADS) acm_unpack_kernel(KernelArgs a, Spl
 			const unsigned peers = __match_any_sync(0xFFFFFFFFu, cls);
 			uint32_t base = 0;
 			const int leader = __ffs((int)peers) - 1;
-			if (lane == leader)
+			if (lane == leader && cls != C_NONE)
 				base = atomicAdd(&sm.cnt[cls], (uint32_t)__popc(peers));
 			base = __shfl_sync(0xFFFFFFFFu, base, leader);
-			mine[k] = (cls << 16) | (base + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+			mine[k] = (cls << 24) | (aux << 16) | (base + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
 		}
 		__syncthreads();
 		if (tid == 0) {
 			uint32_t acc = 0;
-			for (int b = 0; b < NBUCKET; b++) {
-				sm.base[b] = acc;
-				acc += b == B_NONE ? 0u : sm.cnt[b];
+			for (int c = 0; c < NCLS; c++) {
+				sm.base[c] = acc;
+				acc += (sm.cnt[c] + 31u) & ~31u;
 			}
-			sm.base[NBUCKET] = acc;
+			sm.base[NCLS] = acc;
 		}
 		__syncthreads();
 #pragma unroll
 		for (int k = 0; k < U_PER; k++) {
 			const uint32_t cid = (uint32_t)tid + (uint32_t)k * U_THREADS;
-			const uint32_t cls = mine[k] >> 16, rank = mine[k] & 0xFFFFu;
-			if (cls != B_NONE)
-				sm.list[sm.base[cls] + rank] = (uint16_t)(cid | (cls << 11));
+			const uint32_t cls = mine[k] >> 24, aux = (mine[k] >> 16) & 31u, rank = mine[k] & 0xFFFFu;
+			if (cls != C_NONE)
+				sm.list[sm.base[cls] + rank] = (uint16_t)(cid | (aux << 11));
+		}
+		if (tid < NCLS) {
+			/* the holes at the end of every class, and the class of every chunk of 32 entries */
+			const uint32_t b0 = sm.base[tid], n = sm.cnt[tid], b1 = sm.base[tid + 1];
+			for (uint32_t i = b0 + n; i < b1; i++)
+				sm.list[i] = 0xFFFFu;
+			for (uint32_t ch = b0 >> 5; ch < b1 >> 5; ch++)
+				sm.chunk_cls[ch] = (uint8_t)tid;
 		}
 		__syncthreads();
 
-		/* ---- unpack, class by class, 32 columns per warp and turn */
-		const uint32_t n_items = sm.base[NBUCKET];
-		for (uint32_t it0 = 32u * (uint32_t)warp; it0 < n_items; it0 += 32u * (U_THREADS / 32)) {
-			const uint32_t it = it0 + (uint32_t)lane;
-			const bool have = it < n_items;
-			const uint32_t ent = have ? sm.list[it] : 0u;
-			const uint32_t cid = ent & 2047u, cls = have ? ent >> 11 : (uint32_t)B_NONE;
+		/* ---- unpack: a warp takes the next 32 columns of the sorted list; they are of one class */
+		const uint32_t nchunks = sm.base[NCLS] >> 5;
+		for (;;) {
+			uint32_t ch = 0;
+			if (lane == 0)
+				ch = atomicAdd(&sm.next_chunk, 1u);
+			ch = __shfl_sync(0xFFFFFFFFu, ch, 0);
+			if (ch >= nchunks)
+				break;
+			const uint32_t cls = sm.chunk_cls[ch];
+			const uint32_t ent = sm.list[32u * ch + (uint32_t)lane];
+			const bool have = ent != 0xFFFFu;
+			const uint32_t cid = have ? ent & 2047u : 0u, aux = ent >> 11;
 			const uint32_t bi = cid >> 7, col = cid & 127u;
-			const uint32_t PP = sm.pos[cid] + 5u; /* payload */
+			const uint32_t PP = sm.pos[cid];
 			const uint64_t gb = g0 + bi;
-			StreamWords sw;
-			sw.w = sm.bbase[bi];
-			sw.fe_word = sm.bfe[bi] >> 5;
-			sw.fe_tail = sm.bfe[bi] & 31u;
+			const uint32_t *w = sm.bbase[bi];
+			const uint32_t fe = sm.bfe[bi];
+			const bool near = (sm.bflags[bi] & BF_NEAR) != 0u;
+			const uint32_t iw = PP >> 5;
 			uint4 *const dst = reinterpret_cast<uint4 *>(g.inter + gb * (uint64_t)BLEN + (col & 31u) * 64u + (col >> 5) * 16u);
-			uint32_t a0 = 0u, a1 = 0u;
-			bool nib = false;
-			const bool isk = cls >= B_K0 && cls < B_NONE, ist = cls >= B_T0 && cls < B_K0;
-			if (__any_sync(0xFFFFFFFFu, isk)) {
-				if (isk) {
-					const uint32_t iw = PP >> 5;
-					uint32_t w0, w1, w2, w3;
-					if (iw + 4u < sw.fe_word) {
-						w0 = __ldg(sw.w + iw); w1 = __ldg(sw.w + iw + 1); w2 = __ldg(sw.w + iw + 2); w3 = __ldg(sw.w + iw + 3);
-					} else {
-						w0 = sw.word(iw); w1 = sw.word(iw + 1); w2 = sw.word(iw + 2); w3 = sw.word(iw + 3);
-					}
+			if (cls <= C_K0) {
+				if (have) {
+					const uint32_t w0 = ldw(w, iw, fe, near), w1 = ldw(w, iw + 1u, fe, near), w2 = ldw(w, iw + 2u, fe, near),
+						       w3 = ldw(w, iw + 3u, fe, near);
 					const uint32_t lo = fsr(w0, w1, PP), mid = fsr(w1, w2, PP), hi = fsr(w2, w3, PP);
-					fast2::unpack_k(lo, mid, hi, sm.kind[sm.sel[cid]] >> 3, sm.k8w, a0, a1);
-					nib = true;
+					uint32_t a0, a1;
+					fast2::unpack_k(lo, mid, hi, aux, sm.k8w, a0, a1);
+					uint4 v;
+					nib_to_bytes(a0, v.x, v.y);
+					nib_to_bytes(a1, v.z, v.w);
+					*dst = v;
 				}
-				__syncwarp();
-			}
-			if (__any_sync(0xFFFFFFFFu, ist)) {
-				if (ist) {
-					const uint32_t iw = PP >> 5;
-					const uint32_t w0 = sw.word(iw), w1 = sw.word(iw + 1), w2 = sw.word(iw + 2);
+			} else if (cls >= C_T2 && cls <= C_T0) {
+				if (have) {
+					const uint32_t w0 = ldw(w, iw, fe, near), w1 = ldw(w, iw + 1u, fe, near), w2 = ldw(w, iw + 2u, fe, near);
 					const uint32_t lo = fsr(w0, w1, PP), mid = fsr(w1, w2, PP);
-					const int bad = fast2::unpack_t(lo, mid, PP, sm.bfe[bi] + 8u, cls - B_T0, sm.t, a0, a1);
+					uint32_t a0, a1;
+					const int bad = fast2::unpack_t(lo, mid, PP, fe + 8u, (uint32_t)C_T0 - cls, sm.t, a0, a1);
 					if (bad)
 						atomicMin(g.first_bad + sm.bstream[bi], sm.bno[bi]);
-					nib = sm.bok[bi] != 0u;
-				}
-				__syncwarp();
-			}
-			if (nib) {
-				uint4 v;
-				nib_to_bytes(a0, v.x, v.y);
-				nib_to_bytes(a1, v.z, v.w);
-				*dst = v;
-			}
-			if (cls == B_ZERO)
-				*dst = make_uint4(0u, 0u, 0u, 0u); /* f_zero decode.c:181-188 */
-			const bool isl = cls == B_LIN || cls == B_WIDE;
-			if (__any_sync(0xFFFFFFFFu, isl)) {
-				if (isl) {
-					/* f_linear decode.c:196-206: code - 2^(ind-1) */
-					uint32_t v[ROWS];
-					fast2::unpack_linear(sw, PP, (uint32_t)sm.sel[cid], 1, v);
-					if (cls == B_LIN) {
-						uint32_t q[4];
-#pragma unroll
-						for (int j = 0; j < 4; j++) {
-							const uint32_t p01 = __byte_perm(v[4 * j] << QS, v[4 * j + 1] << QS, 0x0040);
-							const uint32_t p23 = __byte_perm(v[4 * j + 2] << QS, v[4 * j + 3] << QS, 0x0040);
-							q[j] = __byte_perm(p01, p23, 0x5410);
-						}
-						*dst = make_uint4(q[0], q[1], q[2], q[3]);
-					} else {
-						uint32_t q[8];
-#pragma unroll
-						for (int j = 0; j < 8; j++)
-							q[j] = __byte_perm(v[2 * j], v[2 * j + 1], 0x5410);
-						uint4 *wd = reinterpret_cast<uint4 *>(g.wide + (gb * COLS + col) * (uint64_t)ROWS);
-						wd[0] = make_uint4(q[0], q[1], q[2], q[3]);
-						wd[1] = make_uint4(q[4], q[5], q[6], q[7]);
-						atomicOr(&sm.wmask[bi][col >> 5], 1u << (col & 31u));
+					if (aux & 1u) { /* the block decodes */
+						uint4 v;
+						nib_to_bytes(a0, v.x, v.y);
+						nib_to_bytes(a1, v.z, v.w);
+						*dst = v;
 					}
 				}
-				__syncwarp();
+			} else if (cls >= C_L7) {
+				if (have) {
+					const uint32_t w0 = ldw(w, iw, fe, near), w1 = ldw(w, iw + 1u, fe, near), w2 = ldw(w, iw + 2u, fe, near),
+						       w3 = ldw(w, iw + 3u, fe, near), w4 = ldw(w, iw + 4u, fe, near);
+					const uint32_t W[4] = { fsr(w0, w1, PP), fsr(w1, w2, PP), fsr(w2, w3, PP), fsr(w3, w4, PP) };
+					uint4 v;
+					switch (cls) { /* uniform */
+					case C_L3: v = lin_narrow<3>(W); break;
+					case C_L3 - 1: v = lin_narrow<4>(W); break;
+					case C_L3 - 2: v = lin_narrow<5>(W); break;
+					case C_L3 - 3: v = lin_narrow<6>(W); break;
+					default: v = lin_narrow<8 - QS>(W); break;
+					}
+					*dst = v;
+				}
+			} else { /* C_WIDE */
+				if (have) {
+					/* f_linear decode.c:196-206: code - 2^(ind-1), as int16 */
+					StreamWords sw;
+					sw.w = w;
+					sw.fe = fe;
+					sw.near = near;
+					uint32_t v[ROWS];
+					fast2::unpack_linear(sw, PP, aux + 8u, 1, v);
+					uint32_t q[8];
+#pragma unroll
+					for (int j = 0; j < 8; j++)
+						q[j] = __byte_perm(v[2 * j], v[2 * j + 1], 0x5410);
+					uint4 *wd = reinterpret_cast<uint4 *>(g.wide + (gb * COLS + col) * (uint64_t)ROWS);
+					wd[0] = make_uint4(q[0], q[1], q[2], q[3]);
+					wd[1] = make_uint4(q[4], q[5], q[6], q[7]);
+					atomicOr(&sm.wmask[bi][col >> 5], 1u << (col & 31u));
+				}
 			}
 		}
 		__syncthreads();
 		if (tid < UB * 4) {
 			const uint64_t gb = g0 + (tid >> 2);
-			if (gb < g.n_blocks && sm.bok[tid >> 2])
+			if (gb < g.n_blocks && (sm.bflags[tid >> 2] & BF_OK))
 				g.wmask[gb * 4u + (tid & 3)] = sm.wmask[tid >> 2][tid & 3];
 		}
 	}
@@ -859,10 +1086,8 @@ size_t split_bytes_per_block()
 	return sizeof(BlockRec) + 8 + 2 * split::COLS + split::BLEN + 2 * split::BLEN + 16;
 }
 
-cudaError_t launch_split(const KernelArgs &a, const SplitArgs &g, int sms, cudaStream_t st)
+static cudaError_t split_configure()
 {
-	if (a.count == 0)
-		return cudaSuccess;
 	static bool configured[64] = {};
 	int dev = 0;
 	cudaError_t e = cudaGetDevice(&dev);
@@ -871,6 +1096,9 @@ cudaError_t launch_split(const KernelArgs &a, const SplitArgs &g, int sms, cudaS
 	if (!configured[dev & 63]) {
 		e = cudaFuncSetAttribute(split::acm_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
 					 (int)sizeof(walk::SmemWalk));
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute(split::acm_walk1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+						 (int)sizeof(split::SmemWalk1));
 		if (e == cudaSuccess)
 			e = cudaFuncSetAttribute(split::acm_lift_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 						 (int)split::LIFT_SMEM);
@@ -881,28 +1109,75 @@ cudaError_t launch_split(const KernelArgs &a, const SplitArgs &g, int sms, cudaS
 			return e;
 		configured[dev & 63] = true;
 	}
+	return cudaSuccess;
+}
+
+/* unpack of the records [u0, u0 + n) of g's arrays */
+static void launch_unpack(const KernelArgs &a, const SplitArgs &g, uint64_t u0, uint64_t n, int sms, cudaStream_t st)
+{
+	SplitArgs gu = g;
+	gu.rec += u0;
+	gu.coff16 += u0 * split::COLS;
+	gu.inter += u0 * split::BLEN;
+	gu.wide += u0 * split::BLEN;
+	gu.wmask += u0 * 4u;
+	gu.n_blocks = n;
+	const uint64_t tiles = (n + split::UB - 1) / split::UB;
+	const uint32_t ugrid = (uint32_t)(tiles < (uint64_t)sms * 5u ? tiles : (uint64_t)sms * 5u);
+	if (ugrid)
+		split::acm_unpack_kernel<<<ugrid, split::U_THREADS, 0, st>>>(a, gu);
+}
+
+static void launch_lift(const KernelArgs &a, const SplitArgs &g, int sms, cudaStream_t st)
+{
+	if (!g.n_items)
+		return;
+	const uint32_t want = (g.n_items + split::L_WARPS - 1) / split::L_WARPS;
+	const uint32_t lgrid = want < 2u * (uint32_t)sms ? want : 2u * (uint32_t)sms;
+	if (a.fmt.checksums)
+		split::acm_lift_kernel<true><<<lgrid, split::L_THREADS, split::LIFT_SMEM, st>>>(a, g);
+	else
+		split::acm_lift_kernel<false><<<lgrid, split::L_THREADS, split::LIFT_SMEM, st>>>(a, g);
+}
+
+/*
+ * One stream (a.count == 1, g.gs[0].rec_base == 0): walk blocks [b0, b0 + nb) from bit position P0,
+ * unpack them (which also finds out-of-range radix codes: g.first_bad) and, if lift is set,
+ * transform them: g.items / g.n_items = the lift work items of exactly these blocks,
+ * g.item_counter zeroed by the caller.  The block before b0 is unpacked again (its index bytes
+ * rebuild the transform history).
+ */
+cudaError_t launch_split_range(const KernelArgs &a, const SplitArgs &g, uint32_t b0, uint32_t nb, uint32_t P0,
+			       int lift, int sms, cudaStream_t st)
+{
+	cudaError_t e = split_configure();
+	if (e != cudaSuccess)
+		return e;
+	split::acm_walk1_kernel<<<1, split::W1_THREADS, sizeof(split::SmemWalk1), st>>>(a, g, b0, nb, P0);
+	const uint32_t u0 = b0 ? b0 - 1u : 0u;
+	launch_unpack(a, g, u0, (uint64_t)b0 + nb - u0, sms, st);
+	if (lift)
+		launch_lift(a, g, sms, st);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_split(const KernelArgs &a, const SplitArgs &g, int sms, cudaStream_t st)
+{
+	if (a.count == 0)
+		return cudaSuccess;
+	cudaError_t e = split_configure();
+	if (e != cudaSuccess)
+		return e;
 	/* walk: one stream per lane; few streams are spread thin (the walk is latency bound: a warp
-	 * that has its sub-partition to itself steps almost twice as fast), many fill 8 warps per SM */
+	 * that has its sub-partition to itself steps faster), many fill 8 warps per SM */
 	const uint32_t warps = (a.count + 31u) / 32u;
 	uint32_t nw = (warps + (uint32_t)sms - 1u) / (uint32_t)sms;
 	nw = nw < 1u ? 1u : nw > (uint32_t)walk::SW ? (uint32_t)walk::SW : nw;
 	uint32_t ctas = (warps + nw - 1u) / nw;
 	ctas = ctas > (uint32_t)sms ? (uint32_t)sms : ctas;
 	split::acm_walk_kernel<<<ctas, 32 * nw, sizeof(walk::SmemWalk), st>>>(a, g);
-	/* unpack: tiles of 16 blocks */
-	const uint64_t tiles = (g.n_blocks + split::UB - 1) / split::UB;
-	const uint32_t ugrid = (uint32_t)(tiles < (uint64_t)sms * 16u ? tiles : (uint64_t)sms * 16u);
-	if (ugrid)
-		split::acm_unpack_kernel<<<ugrid, split::U_THREADS, 0, st>>>(a, g);
-	/* lift: persistent CTAs, two per SM */
-	if (g.n_items) {
-		const uint32_t want = (g.n_items + split::L_WARPS - 1) / split::L_WARPS;
-		const uint32_t lgrid = want < 2u * (uint32_t)sms ? want : 2u * (uint32_t)sms;
-		if (a.fmt.checksums)
-			split::acm_lift_kernel<true><<<lgrid, split::L_THREADS, split::LIFT_SMEM, st>>>(a, g);
-		else
-			split::acm_lift_kernel<false><<<lgrid, split::L_THREADS, split::LIFT_SMEM, st>>>(a, g);
-	}
+	launch_unpack(a, g, 0, g.n_blocks, sms, st);
+	launch_lift(a, g, sms, st);
 	return launch_gen2_finish(a, g, st);
 }
 

@@ -35,6 +35,7 @@
  * with ACM_ERR_OTHER.
  */
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -95,6 +96,16 @@ struct GpuState {
 	uint32_t c_block0 = 0, c_attempted = 0, c_nok = 0, c_words = 0, c_endP = 0;
 	int c_status = 0;            /* verdict of attempt c_block0 + c_nok when c_nok < c_attempted */
 
+	/* split path (acm_split.cu; level 7, 16 rows, 16-bit formats): one lane walks the stream, the
+	 * blocks of a chunk are unpacked and transformed in parallel.  Per-block intermediates for the
+	 * whole stream: the records double as the block index (bit position of every walked block). */
+	bool split = false;
+	SplitArgs sp{};
+	uint8_t *d_split = nullptr;
+	Gen2Item *d_items = nullptr;
+	int sm_count = 0;
+	std::vector<BlockRec> recs;  /* host copy of the last chunk's records */
+
 	std::vector<SavedState> index;  /* sorted by block; [0] is block 0 */
 	uint32_t next_block = 0;        /* block acm_read decodes next when !block_ready */
 	uint32_t cur_block = 0;         /* block the current block_pos refers to */
@@ -131,6 +142,7 @@ void gpu_free(GpuState *g)
 	cudaFree(g->d_tables);
 	cudaFree(g->scratch.buf);
 	cudaFree(g->d_pcm);
+	cudaFree(g->d_split);
 	if (g->stream)
 		cudaStreamDestroy(g->stream);
 	delete g;
@@ -164,6 +176,57 @@ int gpu_setup(GpuState *g)
 	CUS(cudaMalloc(&g->scratch.buf, g->scratch.stride * 4));
 	g->pcm_cap = (size_t)g->chunk_blocks * blen * 4 + 64;
 	CUS(cudaMalloc(&g->d_pcm, g->pcm_cap));
+	CUS(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device));
+	g->split = split_shape(g->hdr.level, g->hdr.rows) && g->n_attempt_total > 0 &&
+		   (uint64_t)g->n_attempt_total * split_bytes_per_block() < ((uint64_t)8 << 30);
+	if (g->split) {
+		/* one allocation: stream table, state, work items (runs of SP_RUN blocks), per-block arrays */
+		static std::atomic<uint32_t> epoch_counter{0x40000000u};
+		constexpr uint32_t SP_RUN = 8;
+		const uint64_t nb = (uint64_t)g->n_attempt_total + 1;
+		const size_t n_items = (size_t)((nb + SP_RUN - 1) / SP_RUN);
+		size_t total = 0;
+		auto carve = [&total](size_t bytes) {
+			const size_t at = total;
+			total += (bytes + 255u) & ~(size_t)255u;
+			return at;
+		};
+		const size_t o_gs = carve(sizeof(Gen2Stream)), o_state = carve(64), o_items = carve(n_items * sizeof(Gen2Item));
+		const size_t o_rec = carve(nb * sizeof(BlockRec)), o_cks = carve(nb * 8), o_coff = carve(nb * 256);
+		const size_t o_wmask = carve(nb * 16), o_inter = carve(nb * 2048), o_wide = carve(nb * 4096);
+		CUS(cudaMalloc(&g->d_split, total));
+		uint8_t *base = g->d_split;
+		Gen2Stream gs;
+		memset(&gs, 0, sizeof(gs));
+		gs.max_blocks = g->n_attempt_total;
+		std::vector<Gen2Item> items(n_items);
+		for (size_t i = 0; i < n_items; i++) {
+			items[i].stream = 0;
+			items[i].b0 = (uint32_t)(i * SP_RUN);
+			items[i].nb = SP_RUN;
+			items[i].warm = 0;
+		}
+		CUS(cudaMemcpyAsync(base + o_gs, &gs, sizeof(gs), cudaMemcpyHostToDevice, g->stream));
+		CUS(cudaMemcpyAsync(base + o_items, items.data(), n_items * sizeof(Gen2Item), cudaMemcpyHostToDevice, g->stream));
+		CUS(cudaMemsetAsync(base + o_state, 0, 4, g->stream));        /* nscan */
+		CUS(cudaMemsetAsync(base + o_state + 4, 0xFF, 4, g->stream)); /* first_bad */
+		CUS(cudaMemsetAsync(base + o_rec, 0, nb * sizeof(BlockRec), g->stream));
+		CUS(cudaStreamSynchronize(g->stream)); /* `items` goes out of scope */
+		memset(&g->sp, 0, sizeof(g->sp));
+		g->sp.gs = reinterpret_cast<const Gen2Stream *>(base + o_gs);
+		g->sp.nscan = reinterpret_cast<uint32_t *>(base + o_state);
+		g->sp.first_bad = g->sp.nscan + 1;
+		g->sp.item_counter = g->sp.nscan + 2;
+		g->d_items = reinterpret_cast<Gen2Item *>(base + o_items);
+		g->sp.rec = reinterpret_cast<BlockRec *>(base + o_rec);
+		g->sp.cks_blk = reinterpret_cast<unsigned long long *>(base + o_cks);
+		g->sp.coff16 = reinterpret_cast<uint16_t *>(base + o_coff);
+		g->sp.wmask = reinterpret_cast<uint32_t *>(base + o_wmask);
+		g->sp.inter = base + o_inter;
+		g->sp.wide = reinterpret_cast<uint16_t *>(base + o_wide);
+		g->sp.n_blocks = g->n_attempt_total;
+		g->sp.epoch = epoch_counter.fetch_add(1);
+	}
 	CUS(cudaStreamSynchronize(g->stream)); /* `tab` is on this stack frame */
 	return ACM_OK;
 }
@@ -235,7 +298,9 @@ int upload(GpuState *g)
  * Decode the chunk that starts at index entry `si` (blocks [b0, b0 + nb)) in format key
  * `fmt` into the host cache.  On full success the end state becomes a new index entry.
  */
-int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, int sgned)
+int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevStream d, int be, int sgned, bool lift);
+
+int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, int sgned, bool lift = true)
 {
 	const SavedState &s0 = g->index[si];
 	const uint32_t blen = acm->block_len, b0 = s0.block;
@@ -287,6 +352,10 @@ int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, in
 		uint64_t cap = (uint64_t)nb * blen;
 		d.words_limit = (uint32_t)(left < cap ? left : cap);
 	}
+	if (g->split && wordlen == 2)
+		return decode_chunk_split(acm, g, si, nb, d, be, sgned, lift);
+	if (!lift)
+		return ACM_OK; /* only the split path can skip ahead */
 	CUS(cudaMemcpyAsync(g->d_desc, &d, sizeof(d), cudaMemcpyHostToDevice, g->stream));
 	if (d.resume)
 		CUS(cudaMemcpyAsync(g->d_hist, s0.hist.data(), s0.hist.size() * 4, cudaMemcpyHostToDevice, g->stream));
@@ -340,6 +409,93 @@ int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, in
 }
 
 /*
+ * The same for a stream on the split path: one lane walks blocks [b0, b0 + nb) (acm_walk1_kernel),
+ * the blocks are unpacked in parallel and -- unless lift is false: a seek skipping ahead, which only
+ * needs to know that the blocks decode -- transformed in parallel, PCM into the host cache.
+ */
+int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevStream d, int be, int sgned, bool lift)
+{
+	const uint32_t blen = acm->block_len, b0 = g->index[si].block, P0 = g->index[si].P;
+	KernelArgs a;
+	SplitArgs sp = g->sp;
+	uint32_t state[2] = { 0, 0xFFFFFFFFu };
+	constexpr uint32_t SP_RUN = 8;
+
+	d.bit0 = g->base.bit0;
+	d.n_attempt = g->n_attempt_total;
+	d.words_limit = g->words_limit;
+	d.resume = 0;
+	CUS(cudaMemcpyAsync(g->d_desc, &d, sizeof(d), cudaMemcpyHostToDevice, g->stream));
+	CUS(cudaMemsetAsync(sp.item_counter, 0, 4, g->stream));
+	memset(&a, 0, sizeof(a));
+	a.blob = g->d_blob;
+	a.blob_room = g->blob_room;
+	/* the lift kernel writes block b at word b * block_len of the stream's PCM: block b0 = the start of
+	 * the chunk buffer */
+	a.out = g->d_pcm - (size_t)b0 * blen * 2u;
+	a.streams = g->d_desc;
+	a.count = 1;
+	a.status = g->d_status;
+	a.words = g->d_words;
+	a.cks = g->d_cks;
+	a.tables = g->d_tables;
+	a.counter = g->d_counter;
+	a.errflag = g->d_counter + 2;
+	a.fmt.wordlen = 2;
+	a.fmt.be = be ? 1 : 0;
+	a.fmt.bias = sgned ? 0u : 0x8000u;
+	a.fmt.checksums = 0;
+	sp.items = g->d_items + b0 / SP_RUN; /* chunks start at multiples of chunk_blocks, a multiple of SP_RUN */
+	sp.n_items = (nb + SP_RUN - 1) / SP_RUN;
+	CUS(launch_split_range(a, sp, b0, nb, P0, lift ? 1 : 0, g->sm_count, g->stream));
+	g->recs.resize(nb);
+	CUS(cudaMemcpyAsync(g->recs.data(), sp.rec + b0, (size_t)nb * sizeof(BlockRec), cudaMemcpyDeviceToHost, g->stream));
+	CUS(cudaMemcpyAsync(state, sp.nscan, 8, cudaMemcpyDeviceToHost, g->stream));
+	CUS(cudaStreamSynchronize(g->stream));
+	/* what the reference's read loop would see: blocks decode up to the first one whose walk fails, or
+	 * that holds an out-of-range radix code */
+	const uint32_t walked = state[0] > b0 ? state[0] - b0 : 0u;
+	uint32_t nok = 0;
+	int status = 0;
+	while (nok < nb && nok < walked && g->recs[nok].status == SCAN_OK)
+		nok++;
+	if (nok < nb && nok < walked)
+		status = g->recs[nok].status == SCAN_EOF ? 0 : g->recs[nok].status;
+	if (state[1] < b0 + nok || (state[1] == b0 + nok && nok < nb)) {
+		nok = state[1] > b0 ? state[1] - b0 : 0u;
+		status = ACM_ERR_CORRUPT;
+	}
+	uint32_t words = 0;
+	{
+		const uint64_t done = (uint64_t)b0 * blen, left = g->words_limit > done ? g->words_limit - done : 0;
+		const uint64_t cap = (uint64_t)nok * blen;
+		words = (uint32_t)(left < cap ? left : cap);
+	}
+	if (lift) {
+		g->pcm.resize((size_t)words * 2 + 16);
+		if (words)
+			CUS(cudaMemcpy(g->pcm.data(), g->d_pcm, (size_t)words * 2, cudaMemcpyDeviceToHost));
+		g->c_valid = true;
+		g->c_fmt = fmt_key(be, 2, sgned);
+		g->c_block0 = b0;
+		g->c_attempted = nb;
+		g->c_nok = nok;
+		g->c_words = words;
+		g->c_endP = nok ? g->recs[nok - 1].end : P0;
+		g->c_status = status;
+		if (g->c_endP > g->consumed_P)
+			g->consumed_P = g->c_endP;
+	}
+	if (nok == nb && b0 + nb < g->n_attempt_total && si + 1 == g->index.size()) {
+		SavedState n;
+		n.block = b0 + nb;
+		n.P = g->recs[nb - 1].end;
+		g->index.push_back(std::move(n));
+	}
+	return ACM_OK;
+}
+
+/*
  * Make block b available in the cache (in the given format).  Returns 1 if the block
  * decoded, 0 for a clean end of stream at that block (decode.c:842-843), <0 for the
  * error the reference's decode_block would return.
@@ -347,6 +503,13 @@ int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, in
 int ensure_block(ACMStream *acm, GpuState *g, uint32_t b, int be, int wordlen, int sgned)
 {
 	const int key = fmt_key(be, wordlen, sgned);
+	if (g->split && wordlen != 2) {
+		/* 24 / 32-bit words are the generic kernel's: its index entries carry the transform history,
+		 * the split path's do not -- start the index over */
+		g->split = false;
+		g->index.resize(1);
+		g->c_valid = false;
+	}
 	for (;;) {
 		if (g->c_valid && g->c_fmt == key && b >= g->c_block0 && b < g->c_block0 + g->c_attempted) {
 			if (b < g->c_block0 + g->c_nok)
@@ -570,6 +733,17 @@ extern "C" int acm_seek_pcm(ACMStream *acm, unsigned pcm_pos)
 		g->next_block = 0;
 		g->cur_block = 0;
 		g->drained = false; /* util.c:230-234: the reader starts over */
+	}
+	if (g->split && word_pos > acm->stream_pos && acm->block_len % acm->info.channels == 0) {
+		/* split path: the walk alone (plus the unpack, which finds out-of-range codes) extends the
+		 * index up to the chunk that holds the target; nothing is transformed or copied on the way */
+		const uint32_t tb = word_pos / acm->block_len;
+		while (g->index.back().block + g->chunk_blocks <= tb &&
+		       g->index.back().block + g->chunk_blocks < g->n_attempt_total) {
+			const size_t before = g->index.size();
+			if (decode_chunk(acm, g, before - 1, 0, 2, 1, false) < 0 || g->index.size() == before)
+				break; /* a block on the way does not decode: the read loop below reports it */
+		}
 	}
 	while (acm->stream_pos < word_pos) {
 		int step = 2048, res;

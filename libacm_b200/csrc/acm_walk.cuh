@@ -140,6 +140,15 @@ struct Ring {
 	 * nothing to store writes the ring's spare rows, a lane that wants nothing loads `safe`. */
 	__device__ __forceinline__ void topup(uint32_t P)
 	{
+		/* last period's loads go into the ring; nothing touches them before (a register copy right
+		 * after the loads would wait out the memory latency in every period) */
+		if (__any_sync(0xFFFFFFFFu, hold_n > 0u && hold_c0 + hold_n > full16)) {
+			/* some lane is at the end of its file (once per stream) */
+#pragma unroll
+			for (int k = 0; k < NHOLD; k++)
+				if ((uint32_t)k < hold_n)
+					hold[k] = trim(hold_c0 + k, hold[k]);
+		}
 #pragma unroll
 		for (int k = 0; k < NHOLD; k++) {
 			const uint32_t c = hold_c0 + k;
@@ -161,14 +170,7 @@ struct Ring {
 		n = base && n > 0 ? n : 0;
 #pragma unroll
 		for (int k = 0; k < NHOLD; k++)
-			hold[k] = ldg_keep_v4(k < n ? base + (size_t)(f0 + k) * 16u : safe, pol);
-		if (__any_sync(0xFFFFFFFFu, n > 0 && f0 + (uint32_t)n > full16)) {
-			/* some lane is at the end of its file (once per stream) */
-#pragma unroll
-			for (int k = 0; k < NHOLD; k++)
-				if (k < n)
-					hold[k] = trim(f0 + k, hold[k]);
-		}
+			hold[k] = ldg_keep_v4(k < n && f0 + (uint32_t)k < room16 ? base + (size_t)(f0 + k) * 16u : safe, pol);
 		prefetch_l2(base && f0 + 64u < room16 ? base + (size_t)(f0 + 64u) * 16u : safe);
 		hold_c0 = f0;
 		hold_n = (uint32_t)n;

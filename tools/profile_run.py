@@ -35,6 +35,12 @@ for _ in range(args.runs):
     plan.run(d_blob, d_out, cs)
     torch.cuda.synchronize()
     print("ms", plan.last_ms(), "Msamples/s", s["total_values"].sum() / plan.last_ms() / 1e3)
+if os.environ.get("WALK_PROF"):
+    import ctypes as C
+    buf = (C.c_uint64 * 64)()
+    api.lib().acm_gpu_plan_debug_counters.argtypes = [C.c_void_p, C.c_void_p]
+    api.lib().acm_gpu_plan_debug_counters(plan._h, buf)
+    print("walk warp 0: cycles retire %d topup %d header %d steps %d looptail %d periods %d outer %d" % tuple(buf[40:47]))
 if os.environ.get("F2_PROF"):
     import ctypes as C
     buf = (C.c_uint64 * 64)()
