@@ -916,6 +916,7 @@ extern "C" void acm_gpu_release_workspace(void)
 {
 	int cur = 0;
 	cudaGetDevice(&cur);
+	acm_stream_release_pool();
 	for (int d = 0; d < MAX_DEV; d++) {
 		std::lock_guard<std::mutex> lock(g_ws_mutex[d]);
 		Workspace &w = g_ws[d];

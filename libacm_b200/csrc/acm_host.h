@@ -17,6 +17,10 @@ void acm_read_plan(uint32_t total, uint32_t blen, uint32_t channels, uint32_t *w
 		   uint32_t *n_attempt);
 
 void acm_set_error(const char *fmt, ...);
+#ifdef __cplusplus
+/* acm_stream.cu keeps the buffers of closed streams for the next open; this frees them */
+void acm_stream_release_pool();
+#endif
 
 #ifdef __cplusplus
 struct acm_gpu_stream;

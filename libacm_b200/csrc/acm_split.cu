@@ -260,8 +260,12 @@ constexpr int W1_THREADS = 256;
 constexpr uint32_t W1_PBYTES = 4u << ACM_UNI_KBITS; /* bytes per page of the widened table */
 
 struct SmemWalk1 {
-	/* uni16 widened to 32-bit entries: bits to advance | byte offset of the next page << 8 -- the
-	 * lookup's result needs one shift and one mask, each off the other's path */
+	/* uni16 widened to 32-bit entries: bits to advance (byte 0) | byte offset of the next page (a
+	 * multiple of 1024).  The entry is used as it is: as a funnel-shift count (the low five bits
+	 * count; no step advances 32 bits or more where the window is shifted), as the next table
+	 * address (one LOP3 selects the page bits from the entry and the index bits from the window),
+	 * as the loop condition (>= 1024: another page), and its byte 0 is added to the position by a
+	 * dot-product instruction */
 	uint32_t uni32[ACM_UNI_PAGES * ACM_UNI_PSIZE];
 	uint16_t off[COLS + 8];
 };
@@ -273,7 +277,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, 
 	const int tid = threadIdx.x, lane = tid & 31;
 	for (int i = tid; i < ACM_UNI_PAGES * ACM_UNI_PSIZE; i += W1_THREADS) {
 		const uint32_t e = a.tables->uni16[i];
-		sm.uni32[i] = (e & 0xFFu) | (((e >> 8) * W1_PBYTES) << 8);
+		sm.uni32[i] = (e & 0xFFu) | ((e >> 8) * W1_PBYTES);
 	}
 	__syncthreads();
 	if (tid >= 32)
@@ -311,27 +315,26 @@ __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, 
 			for (uint32_t c = 0; c < (uint32_t)COLS; c++) {
 				const uint32_t i = min(R >> 5, last_i);
 				const uint32_t *wp = words + i;
-				const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+				const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
 				uint32_t lo = fsr(w0, w1, R);
 				uint32_t e = *reinterpret_cast<const uint32_t *>(uni + (lo & M_SEL));
 				sm.off[c] = (uint16_t)(R + 2u - P);
-				uint32_t adv = e & 0xFFu, pg = e >> 8;
-				R += adv;
-				if (pg == 0u)
+				const uint32_t R0 = R;
+				R = __dp4a(e, 1u, R); /* += byte 0 */
+				if (e < W1_PBYTES)
 					continue; /* a fixed-size column, walked in one step */
-				if (pg >= S_K0 && pg < S_HALT) {
+				if (e >= S_K0 && e < S_HALT) {
 					/* inside a prefix-coded column: <= 80 payload bits, all in the window */
-					uint32_t mid = fsr(w1, w2, R - adv), hi = fsr(w2, w3, R - adv);
+					const uint32_t w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+					uint32_t mid = fsr(w1, w2, R0), hi = fsr(w2, w3, R0);
 					do {
-						lo = fsr(lo, mid, adv);
-						mid = fsr(mid, hi, adv);
-						hi >>= adv;
-						e = *reinterpret_cast<const uint32_t *>(uni + (pg | (lo & M_K)));
-						adv = e & 0xFFu;
-						pg = e >> 8;
-						R += adv;
-					} while (pg != 0u);
-				} else if (pg == S_SKIP6) {
+						lo = fsr(lo, mid, e);
+						mid = fsr(mid, hi, e);
+						hi = fsr(hi, 0u, e);
+						e = *reinterpret_cast<const uint32_t *>(uni + ((e & ~(W1_PBYTES - 1u)) | (lo & M_K)));
+						R = __dp4a(e, 1u, R);
+					} while (e >= W1_PBYTES);
+				} else if ((e & ~(W1_PBYTES - 1u)) == S_SKIP6) {
 					R += 6u; /* 16-bit linear column: 261 bits */
 				} else {
 					clean = false; /* bad selector (f_bad, decode.c:190-194) */

@@ -39,7 +39,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -104,7 +106,19 @@ struct GpuState {
 	uint8_t *d_split = nullptr;
 	Gen2Item *d_items = nullptr;
 	int sm_count = 0;
-	std::vector<BlockRec> recs;  /* host copy of the last chunk's records */
+	/* two chunk slots (device PCM, pinned host PCM / records / walk state): while acm_read serves one
+	 * chunk, the next one is walked, decoded and copied behind it (look-ahead) */
+	uint8_t *d_chunk[2] = { nullptr, nullptr };
+	uint8_t *h_chunk[2] = { nullptr, nullptr };
+	BlockRec *h_recs[2] = { nullptr, nullptr };
+	uint32_t *h_state[2] = { nullptr, nullptr };
+	int cur_slot = 0;
+	struct Ahead {
+		bool active = false;
+		uint32_t b0 = 0, nb = 0, P0 = 0;
+		int key = 0, slot = 0;
+	} ahead;
+	const uint8_t *pcm_ptr = nullptr; /* the cached chunk's PCM: pcm.data(), or a pinned chunk slot */
 
 	std::vector<SavedState> index;  /* sorted by block; [0] is block 0 */
 	uint32_t next_block = 0;        /* block acm_read decodes next when !block_ready */
@@ -126,23 +140,151 @@ inline int fmt_key(int be, int wordlen, int sgned) { return (be ? 1 : 0) | (word
 		}                                                                   \
 	} while (0)
 
+
+/*
+ * Device and pinned-host buffers of closed streams are kept for the next open (cudaMalloc,
+ * cudaHostAlloc and cudaFree are milliseconds each and synchronise the device: a stream's open and
+ * close would cost more than decoding it).  Bounded; acm_gpu_release_workspace() empties it.
+ */
+struct PoolBuf {
+	void *p;
+	size_t cap;
+	int dev;
+	bool pinned;
+};
+std::mutex g_pool_mu;
+std::vector<PoolBuf> g_pool_free;
+std::unordered_map<void *, PoolBuf> g_pool_live;
+size_t g_pool_bytes = 0;
+constexpr size_t POOL_MAX_BYTES = (size_t)1 << 30;
+
+cudaError_t pool_alloc(void **out, size_t size, bool pinned, int dev)
+{
+	const size_t want = (size + 255u) & ~(size_t)255u;
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		size_t best = g_pool_free.size();
+		for (size_t i = 0; i < g_pool_free.size(); i++) {
+			const PoolBuf &b = g_pool_free[i];
+			if (b.dev == dev && b.pinned == pinned && b.cap >= want && b.cap <= 4 * want + ((size_t)1 << 16) &&
+			    (best == g_pool_free.size() || b.cap < g_pool_free[best].cap))
+				best = i;
+		}
+		if (best != g_pool_free.size()) {
+			const PoolBuf b = g_pool_free[best];
+			g_pool_free.erase(g_pool_free.begin() + (long)best);
+			g_pool_bytes -= b.cap;
+			g_pool_live[b.p] = b;
+			*out = b.p;
+			return cudaSuccess;
+		}
+	}
+	void *p = nullptr;
+	const cudaError_t e = pinned ? cudaHostAlloc(&p, want, cudaHostAllocDefault) : cudaMalloc(&p, want);
+	if (e != cudaSuccess)
+		return e;
+	std::lock_guard<std::mutex> lk(g_pool_mu);
+	g_pool_live[p] = PoolBuf{ p, want, dev, pinned };
+	*out = p;
+	return cudaSuccess;
+}
+
+void pool_free(void *p)
+{
+	if (!p)
+		return;
+	PoolBuf b;
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		auto it = g_pool_live.find(p);
+		if (it == g_pool_live.end())
+			return;
+		b = it->second;
+		g_pool_live.erase(it);
+		if (g_pool_bytes + b.cap <= POOL_MAX_BYTES && g_pool_free.size() < 256) {
+			g_pool_free.push_back(b);
+			g_pool_bytes += b.cap;
+			return;
+		}
+	}
+	if (b.pinned)
+		cudaFreeHost(b.p);
+	else
+		cudaFree(b.p);
+}
+
+} // namespace
+
+/* empties the pool (acm_gpu_release_workspace) */
+void acm_stream_release_pool()
+{
+	std::vector<PoolBuf> take;
+	{
+		std::lock_guard<std::mutex> lk(g_pool_mu);
+		take.swap(g_pool_free);
+		g_pool_bytes = 0;
+	}
+	for (const PoolBuf &b : take) {
+		if (b.pinned)
+			cudaFreeHost(b.p);
+		else
+			cudaFree(b.p);
+	}
+}
+
+namespace {
+
+/* the code tables on a device: built and uploaded once per process and device */
+const acm_tables *device_tables(int dev)
+{
+	static std::mutex mu;
+	static acm_tables *d_tab[64] = {};
+	static acm_tables host;
+	static bool built = false;
+	std::lock_guard<std::mutex> lk(mu);
+	if (dev < 0 || dev >= 64)
+		return nullptr;
+	if (!d_tab[dev]) {
+		if (!built) {
+			acm_tables_build(&host);
+			built = true;
+		}
+		acm_tables *p = nullptr;
+		if (cudaMalloc(&p, sizeof(acm_tables)) != cudaSuccess)
+			return nullptr;
+		if (cudaMemcpy(p, &host, sizeof(host), cudaMemcpyHostToDevice) != cudaSuccess) {
+			cudaFree(p);
+			return nullptr;
+		}
+		d_tab[dev] = p;
+	}
+	return d_tab[dev];
+}
+
 void gpu_free(GpuState *g)
 {
 	if (!g)
 		return;
 	cudaSetDevice(g->device);
-	cudaFree(g->d_blob);
-	cudaFree(g->d_desc);
-	cudaFree(g->d_status);
-	cudaFree(g->d_words);
-	cudaFree(g->d_cks);
-	cudaFree(g->d_counter);
-	cudaFree(g->d_endpos);
-	cudaFree(g->d_hist);
-	cudaFree(g->d_tables);
-	cudaFree(g->scratch.buf);
-	cudaFree(g->d_pcm);
-	cudaFree(g->d_split);
+	if (g->stream)
+		cudaStreamSynchronize(g->stream); /* a look-ahead may still be writing the buffers that go back to the pool */
+	pool_free(g->d_blob);
+	pool_free(g->d_desc);
+	pool_free(g->d_status);
+	pool_free(g->d_words);
+	pool_free(g->d_cks);
+	pool_free(g->d_counter);
+	pool_free(g->d_endpos);
+	pool_free(g->d_hist);
+	pool_free(g->scratch.buf);
+	pool_free(g->d_pcm);
+	pool_free(g->d_split);
+	for (int k = 0; k < 2; k++) {
+		pool_free(g->d_chunk[k]);
+		pool_free(g->h_chunk[k]);
+		pool_free(g->h_recs[k]);
+		pool_free(g->h_state[k]);
+	}
 	if (g->stream)
 		cudaStreamDestroy(g->stream);
 	delete g;
@@ -150,7 +292,6 @@ void gpu_free(GpuState *g)
 
 int gpu_setup(GpuState *g)
 {
-	acm_tables tab;
 	const uint32_t blen = g->hdr.rows << g->hdr.level;
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -160,22 +301,24 @@ int gpu_setup(GpuState *g)
 	CUS(cudaGetDevice(&g->device));
 	CUS(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
 	g->blob_room = 0;
-	CUS(cudaMalloc(&g->d_desc, sizeof(DevStream)));
-	CUS(cudaMalloc(&g->d_status, 16));
-	CUS(cudaMalloc(&g->d_words, 16));
-	CUS(cudaMalloc(&g->d_cks, 16));
-	CUS(cudaMalloc(&g->d_counter, 64));
-	CUS(cudaMalloc(&g->d_endpos, 16));
-	CUS(cudaMalloc(&g->d_hist, (size_t)2 * g->cols * 4 + 16));
-	acm_tables_build(&tab);
-	CUS(cudaMalloc(&g->d_tables, sizeof(acm_tables)));
-	CUS(cudaMemcpyAsync(g->d_tables, &tab, sizeof(tab), cudaMemcpyHostToDevice, g->stream));
+	CUS(pool_alloc((void **)&g->d_desc, sizeof(DevStream), false, g->device));
+	CUS(pool_alloc((void **)&g->d_status, 16, false, g->device));
+	CUS(pool_alloc((void **)&g->d_words, 16, false, g->device));
+	CUS(pool_alloc((void **)&g->d_cks, 16, false, g->device));
+	CUS(pool_alloc((void **)&g->d_counter, 64, false, g->device));
+	CUS(pool_alloc((void **)&g->d_endpos, 16, false, g->device));
+	CUS(pool_alloc((void **)&g->d_hist, (size_t)2 * g->cols * 4 + 16, false, g->device));
+	g->d_tables = const_cast<acm_tables *>(device_tables(g->device));
+	if (!g->d_tables) {
+		acm_set_error("code tables: device allocation failed");
+		return ACM_ERR_OTHER;
+	}
 	g->scratch.stride = generic_scratch_words(blen, g->cols);
 	g->scratch.max_blen = blen;
 	g->scratch.max_cols = g->cols;
-	CUS(cudaMalloc(&g->scratch.buf, g->scratch.stride * 4));
+	CUS(pool_alloc((void **)&g->scratch.buf, g->scratch.stride * 4, false, g->device));
 	g->pcm_cap = (size_t)g->chunk_blocks * blen * 4 + 64;
-	CUS(cudaMalloc(&g->d_pcm, g->pcm_cap));
+	CUS(pool_alloc((void **)&g->d_pcm, g->pcm_cap, false, g->device));
 	CUS(cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, g->device));
 	g->split = split_shape(g->hdr.level, g->hdr.rows) && g->n_attempt_total > 0 &&
 		   (uint64_t)g->n_attempt_total * split_bytes_per_block() < ((uint64_t)8 << 30);
@@ -194,7 +337,7 @@ int gpu_setup(GpuState *g)
 		const size_t o_gs = carve(sizeof(Gen2Stream)), o_state = carve(64), o_items = carve(n_items * sizeof(Gen2Item));
 		const size_t o_rec = carve(nb * sizeof(BlockRec)), o_cks = carve(nb * 8), o_coff = carve(nb * 256);
 		const size_t o_wmask = carve(nb * 16), o_inter = carve(nb * 2048), o_wide = carve(nb * 4096);
-		CUS(cudaMalloc(&g->d_split, total));
+		CUS(pool_alloc((void **)&g->d_split, total, false, g->device));
 		uint8_t *base = g->d_split;
 		Gen2Stream gs;
 		memset(&gs, 0, sizeof(gs));
@@ -226,8 +369,14 @@ int gpu_setup(GpuState *g)
 		g->sp.wide = reinterpret_cast<uint16_t *>(base + o_wide);
 		g->sp.n_blocks = g->n_attempt_total;
 		g->sp.epoch = epoch_counter.fetch_add(1);
+		for (int k = 0; k < 2; k++) {
+			const size_t cb = (size_t)g->chunk_blocks * blen * 2 + 64;
+			CUS(pool_alloc((void **)&g->d_chunk[k], cb, false, g->device));
+			CUS(pool_alloc((void **)&g->h_chunk[k], cb, true, g->device));
+			CUS(pool_alloc((void **)&g->h_recs[k], (size_t)g->chunk_blocks * sizeof(BlockRec), true, g->device));
+			CUS(pool_alloc((void **)&g->h_state[k], 16, true, g->device));
+		}
 	}
-	CUS(cudaStreamSynchronize(g->stream)); /* `tab` is on this stack frame */
 	return ACM_OK;
 }
 
@@ -276,12 +425,12 @@ int upload(GpuState *g)
 			cap = g->len_hint + 64;
 		cap = (cap + 255u) & ~(size_t)255u;
 		uint8_t *nb = nullptr;
-		CUS(cudaMalloc(&nb, cap));
+		CUS(pool_alloc((void **)&nb, cap, false, g->device));
 		CUS(cudaMemsetAsync(nb, 0, cap, g->stream));
 		if (g->uploaded)
 			CUS(cudaMemcpyAsync(nb, g->d_blob, g->uploaded, cudaMemcpyDeviceToDevice, g->stream));
 		CUS(cudaStreamSynchronize(g->stream));
-		cudaFree(g->d_blob);
+		pool_free(g->d_blob);
 		g->d_blob = nb;
 		g->blob_cap = cap;
 	}
@@ -300,18 +449,16 @@ int upload(GpuState *g)
  */
 int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevStream d, int be, int sgned, bool lift);
 
-int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, int sgned, bool lift = true)
+/* what every chunk decode starts with: pull and upload what the chunk can consume at most, and the
+ * stream descriptor with the end of the data as it is known by then */
+int chunk_prologue(ACMStream *acm, GpuState *g, size_t si, uint32_t *nb_out, DevStream *d_out)
 {
 	const SavedState &s0 = g->index[si];
-	const uint32_t blen = acm->block_len, b0 = s0.block;
+	const uint32_t b0 = s0.block;
 	uint32_t nb = g->n_attempt_total - b0;
 	if (nb > g->chunk_blocks)
 		nb = g->chunk_blocks;
 	DevStream d = g->base;
-	KernelArgs a;
-	uint32_t endpos[2] = { 0, 0 }, words = 0;
-	int32_t status = 0;
-
 	CUS(cudaSetDevice(g->device));
 	{
 		/* everything this chunk can consume at most, or the end of the source */
@@ -338,6 +485,25 @@ int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, in
 		 * chunk can reach */
 		d.file_end = g->base.bit0 + (uint32_t)data_len * 8u;
 		g->base.file_end = d.file_end;
+	}
+	*nb_out = nb;
+	*d_out = d;
+	return ACM_OK;
+}
+
+int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, int sgned, bool lift = true)
+{
+	const SavedState &s0 = g->index[si];
+	const uint32_t blen = acm->block_len, b0 = s0.block;
+	uint32_t nb = 0;
+	DevStream d;
+	KernelArgs a;
+	uint32_t endpos[2] = { 0, 0 }, words = 0;
+	int32_t status = 0;
+	{
+		const int perr = chunk_prologue(acm, g, si, &nb, &d);
+		if (perr < 0)
+			return perr;
 	}
 	d.bit0 = s0.P;
 	d.out_off = 0;
@@ -387,6 +553,7 @@ int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, in
 	g->pcm.resize((size_t)words * wordlen + 16);
 	if (words)
 		CUS(cudaMemcpy(g->pcm.data(), g->d_pcm, (size_t)words * wordlen, cudaMemcpyDeviceToHost));
+	g->pcm_ptr = g->pcm.data();
 	g->c_valid = true;
 	g->c_fmt = fmt_key(be, wordlen, sgned);
 	g->c_block0 = b0;
@@ -411,14 +578,16 @@ int decode_chunk(ACMStream *acm, GpuState *g, size_t si, int be, int wordlen, in
 /*
  * The same for a stream on the split path: one lane walks blocks [b0, b0 + nb) (acm_walk1_kernel),
  * the blocks are unpacked in parallel and -- unless lift is false: a seek skipping ahead, which only
- * needs to know that the blocks decode -- transformed in parallel, PCM into the host cache.
+ * needs to know that the blocks decode -- transformed in parallel, PCM into a pinned chunk slot.
+ * split_launch queues all of it on the stream; split_finish, after the stream has been waited for,
+ * turns the records into what the reference's read loop would see.
  */
-int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevStream d, int be, int sgned, bool lift)
+int split_launch(ACMStream *acm, GpuState *g, uint32_t b0, uint32_t nb, uint32_t P0, DevStream d, int be, int sgned,
+		 bool lift, int slot)
 {
-	const uint32_t blen = acm->block_len, b0 = g->index[si].block, P0 = g->index[si].P;
+	const uint32_t blen = acm->block_len;
 	KernelArgs a;
 	SplitArgs sp = g->sp;
-	uint32_t state[2] = { 0, 0xFFFFFFFFu };
 	constexpr uint32_t SP_RUN = 8;
 
 	d.bit0 = g->base.bit0;
@@ -432,7 +601,7 @@ int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevS
 	a.blob_room = g->blob_room;
 	/* the lift kernel writes block b at word b * block_len of the stream's PCM: block b0 = the start of
 	 * the chunk buffer */
-	a.out = g->d_pcm - (size_t)b0 * blen * 2u;
+	a.out = g->d_chunk[slot] - (size_t)b0 * blen * 2u;
 	a.streams = g->d_desc;
 	a.count = 1;
 	a.status = g->d_status;
@@ -448,50 +617,102 @@ int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevS
 	sp.items = g->d_items + b0 / SP_RUN; /* chunks start at multiples of chunk_blocks, a multiple of SP_RUN */
 	sp.n_items = (nb + SP_RUN - 1) / SP_RUN;
 	CUS(launch_split_range(a, sp, b0, nb, P0, lift ? 1 : 0, g->sm_count, g->stream));
-	g->recs.resize(nb);
-	CUS(cudaMemcpyAsync(g->recs.data(), sp.rec + b0, (size_t)nb * sizeof(BlockRec), cudaMemcpyDeviceToHost, g->stream));
-	CUS(cudaMemcpyAsync(state, sp.nscan, 8, cudaMemcpyDeviceToHost, g->stream));
-	CUS(cudaStreamSynchronize(g->stream));
-	/* what the reference's read loop would see: blocks decode up to the first one whose walk fails, or
-	 * that holds an out-of-range radix code */
-	const uint32_t walked = state[0] > b0 ? state[0] - b0 : 0u;
+	CUS(cudaMemcpyAsync(g->h_recs[slot], sp.rec + b0, (size_t)nb * sizeof(BlockRec), cudaMemcpyDeviceToHost, g->stream));
+	CUS(cudaMemcpyAsync(g->h_state[slot], sp.nscan, 8, cudaMemcpyDeviceToHost, g->stream));
+	if (lift) {
+		const uint64_t done = (uint64_t)b0 * blen, left = g->words_limit > done ? g->words_limit - done : 0;
+		const uint64_t cap = (uint64_t)nb * blen, words = left < cap ? left : cap;
+		if (words)
+			CUS(cudaMemcpyAsync(g->h_chunk[slot], g->d_chunk[slot], (size_t)words * 2, cudaMemcpyDeviceToHost, g->stream));
+	}
+	return ACM_OK;
+}
+
+void split_finish(ACMStream *acm, GpuState *g, uint32_t b0, uint32_t nb, uint32_t P0, int key, bool lift, int slot)
+{
+	const uint32_t blen = acm->block_len;
+	const BlockRec *recs = g->h_recs[slot];
+	const uint32_t nscan = g->h_state[slot][0], first_bad = g->h_state[slot][1];
+	/* blocks decode up to the first one whose walk fails, or that holds an out-of-range radix code */
+	const uint32_t walked = nscan > b0 ? nscan - b0 : 0u;
 	uint32_t nok = 0;
 	int status = 0;
-	while (nok < nb && nok < walked && g->recs[nok].status == SCAN_OK)
+	while (nok < nb && nok < walked && recs[nok].status == SCAN_OK)
 		nok++;
 	if (nok < nb && nok < walked)
-		status = g->recs[nok].status == SCAN_EOF ? 0 : g->recs[nok].status;
-	if (state[1] < b0 + nok || (state[1] == b0 + nok && nok < nb)) {
-		nok = state[1] > b0 ? state[1] - b0 : 0u;
+		status = recs[nok].status == SCAN_EOF ? 0 : recs[nok].status;
+	if (first_bad < b0 + nok || (first_bad == b0 + nok && nok < nb)) {
+		nok = first_bad > b0 ? first_bad - b0 : 0u;
 		status = ACM_ERR_CORRUPT;
 	}
-	uint32_t words = 0;
-	{
+	if (lift) {
 		const uint64_t done = (uint64_t)b0 * blen, left = g->words_limit > done ? g->words_limit - done : 0;
 		const uint64_t cap = (uint64_t)nok * blen;
-		words = (uint32_t)(left < cap ? left : cap);
-	}
-	if (lift) {
-		g->pcm.resize((size_t)words * 2 + 16);
-		if (words)
-			CUS(cudaMemcpy(g->pcm.data(), g->d_pcm, (size_t)words * 2, cudaMemcpyDeviceToHost));
+		g->pcm_ptr = g->h_chunk[slot];
+		g->cur_slot = slot;
 		g->c_valid = true;
-		g->c_fmt = fmt_key(be, 2, sgned);
+		g->c_fmt = key;
 		g->c_block0 = b0;
 		g->c_attempted = nb;
 		g->c_nok = nok;
-		g->c_words = words;
-		g->c_endP = nok ? g->recs[nok - 1].end : P0;
+		g->c_words = (uint32_t)(left < cap ? left : cap);
+		g->c_endP = nok ? recs[nok - 1].end : P0;
 		g->c_status = status;
 		if (g->c_endP > g->consumed_P)
 			g->consumed_P = g->c_endP;
 	}
-	if (nok == nb && b0 + nb < g->n_attempt_total && si + 1 == g->index.size()) {
+	if (nok == nb && b0 + nb < g->n_attempt_total && g->index.back().block == b0) {
 		SavedState n;
 		n.block = b0 + nb;
-		n.P = g->recs[nb - 1].end;
+		n.P = recs[nb - 1].end;
 		g->index.push_back(std::move(n));
 	}
+}
+
+int chunk_prologue(ACMStream *acm, GpuState *g, size_t si, uint32_t *nb_out, DevStream *d_out);
+
+/* queue the chunk after the cached one, if it is known to exist and nothing is under way */
+void split_look_ahead(ACMStream *acm, GpuState *g, int be, int sgned)
+{
+	if (!g->split || !g->c_valid || g->c_nok != g->c_attempted || g->ahead.active)
+		return;
+	const uint32_t nextb = g->c_block0 + g->c_attempted;
+	if (nextb >= g->n_attempt_total)
+		return;
+	size_t si = g->index.size();
+	while (si-- > 0)
+		if (g->index[si].block <= nextb)
+			break;
+	if (si == (size_t)-1 || g->index[si].block != nextb)
+		return;
+	uint32_t nb = 0;
+	DevStream d;
+	if (chunk_prologue(acm, g, si, &nb, &d) < 0)
+		return;
+	const int slot = 1 - g->cur_slot;
+	if (split_launch(acm, g, nextb, nb, g->index[si].P, d, be, sgned, true, slot) < 0)
+		return;
+	g->ahead.active = true;
+	g->ahead.b0 = nextb;
+	g->ahead.nb = nb;
+	g->ahead.P0 = g->index[si].P;
+	g->ahead.key = fmt_key(be, 2, sgned);
+	g->ahead.slot = slot;
+}
+
+int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevStream d, int be, int sgned, bool lift)
+{
+	const uint32_t b0 = g->index[si].block, P0 = g->index[si].P;
+	/* a chunk slot that a look-ahead may still be filling is not reused before the stream is idle */
+	const int slot = g->ahead.active ? 1 - g->ahead.slot : g->cur_slot;
+	int err = split_launch(acm, g, b0, nb, P0, d, be, sgned, lift, slot);
+	if (err < 0)
+		return err;
+	CUS(cudaStreamSynchronize(g->stream));
+	g->ahead.active = false; /* whatever was under way has landed too; it is not what was asked for */
+	split_finish(acm, g, b0, nb, P0, fmt_key(be, 2, sgned), lift, slot);
+	if (lift)
+		split_look_ahead(acm, g, be, sgned);
 	return ACM_OK;
 }
 
@@ -511,6 +732,16 @@ int ensure_block(ACMStream *acm, GpuState *g, uint32_t b, int be, int wordlen, i
 		g->c_valid = false;
 	}
 	for (;;) {
+		if (g->split && g->ahead.active && g->ahead.key == key && b >= g->ahead.b0 && b < g->ahead.b0 + g->ahead.nb &&
+		    !(g->c_valid && g->c_fmt == key && b >= g->c_block0 && b < g->c_block0 + g->c_attempted)) {
+			/* the chunk that was queued behind the previous one */
+			if (cudaStreamSynchronize(g->stream) != cudaSuccess)
+				return ACM_ERR_OTHER;
+			g->ahead.active = false;
+			split_finish(acm, g, g->ahead.b0, g->ahead.nb, g->ahead.P0, key, true, g->ahead.slot);
+			split_look_ahead(acm, g, be, sgned);
+			continue;
+		}
 		if (g->c_valid && g->c_fmt == key && b >= g->c_block0 && b < g->c_block0 + g->c_attempted) {
 			if (b < g->c_block0 + g->c_nok)
 				return 1;
@@ -678,7 +909,7 @@ extern "C" int acm_read(ACMStream *acm, void *dst, unsigned numbytes, int bigend
 		size_t off = ((size_t)(g->cur_block - g->c_block0) * acm->block_len + acm->block_pos) * (size_t)wordlen;
 		if (off + (size_t)gotbytes > (size_t)g->c_words * wordlen)
 			return ACM_ERR_OTHER; /* cannot happen: the block decoded and holds these words */
-		memcpy(dst, g->pcm.data() + off, (size_t)gotbytes);
+		memcpy(dst, g->pcm_ptr + off, (size_t)gotbytes);
 	}
 	/* decode.c:868-873 */
 	acm->stream_pos += (unsigned)numwords;
