@@ -34,6 +34,7 @@
  * Intermediates (block records, column offsets, index bytes: 2.3 KB per block + the side array)
  * live in an arena that a plan sizes for one GROUP of streams and reuses from group to group.
  */
+#include <cstdio>
 #include "acm_walk.cuh"
 #include "acm_kernels.cuh"
 
@@ -249,98 +250,266 @@ __global__ void __launch_bounds__(WALK_THREADS_MAX, 1) acm_walk_kernel(KernelArg
 /*
  * The walk of ONE stream, for the streaming API (acm_stream.cu): what bounds acm_read on a single
  * stream is the latency of this serial walk, so here it is a scalar routine on one lane, with
- * branches, instead of 32 streams in lock step.  Same state machine (uni16), but inside a
- * prefix-coded column the next 96 stream bits stay in a register window (the chain of a step is
- * table lookup -> shift -> next lookup, no load), and the window is reloaded from global memory
- * (L1 hits: the lines ahead are prefetched once per block) at every column selector.
+ * branches, instead of 32 streams in lock step.  Same state machine (uni16).  The CTA's other
+ * seven warps keep a shared-memory ring of the stream's bytes filled ahead of the walker (with the
+ * reference's end-of-file rule applied: bits past the file read as zero, decode.c:57-61), so every
+ * load on the walker's chain is a shared-memory load of known latency:
+ *   column start:  ring address (2 ALU) -> the 128 stream bits from the position on (4 LDS, together)
+ *                  -> funnel shift -> mask -> table LDS -> position += advance
+ *   inside a prefix-coded column the next 96 bits stay in a register window:
+ *                  table LDS -> funnel shift -> mask -> table LDS
  * Walks blocks [b0, b0 + nb) from bit position P0 and leaves the same records and column offsets
  * as the batch walk; nscan[0] = the blocks walked so far (b0 + those of this launch).
  */
 constexpr int W1_THREADS = 256;
+constexpr int W1_STAGERS = W1_THREADS - 32;
 constexpr uint32_t W1_PBYTES = 4u << ACM_UNI_KBITS; /* bytes per page of the widened table */
+constexpr uint32_t W1_RING = 4096;                  /* ring words (16 KB) */
+constexpr uint32_t W1_UNI_BYTES = 4u * ACM_UNI_PAGES * ACM_UNI_PSIZE;
+/* words a block can span at most (header, 128 selectors, 128 columns of 16 x 16 bits) + the window's read-ahead */
+constexpr uint32_t W1_BLOCK_WORDS = (20u + 128u * (5u + 256u) + 31u) / 32u + 8u;
+static_assert(W1_BLOCK_WORDS * 2u < W1_RING, "the ring holds more than a block");
 
-struct SmemWalk1 {
-	/* uni16 widened to 32-bit entries: bits to advance (byte 0) | byte offset of the next page (a
-	 * multiple of 1024).  The entry is used as it is: as a funnel-shift count (the low five bits
-	 * count; no step advances 32 bits or more where the window is shifted), as the next table
-	 * address (one LOP3 selects the page bits from the entry and the index bits from the window),
-	 * as the loop condition (>= 1024: another page), and its byte 0 is added to the position by a
-	 * dot-product instruction */
-	uint32_t uni32[ACM_UNI_PAGES * ACM_UNI_PSIZE];
-	uint16_t off[COLS + 8];
+/*
+ * Shared memory of the one-stream walker, by ABSOLUTE shared-window address (the dynamic
+ * allocation starts somewhere in the first kilobytes; everything sits above 32 K):
+ *   [32 K, 187 K)        uni32: uni16 widened to 32-bit entries, bits to advance (byte 0) | ABSOLUTE
+ *                        address of the next page (a multiple of 1024) | W1_DONE when the next step is
+ *                        at a selector again (the page is then the selector page: a lookup issued
+ *                        before that is known reads a valid address) | W1_BAD on the page a bad
+ *                        selector leads to
+ *   [192 K, 208 K)       ring: word i of the stream at word i % W1_RING
+ *   [208 K, 208 K + 16)  the ring's first four words again, so that the four words from any index
+ *                        on are consecutive
+ *   then the block's column offsets and the control words of the two sides.
+ * Aligned like this, "ring base | masked position" and "table base | masked window" are one LOP3
+ * each, and a prefix-code step's next address is (entry & ~1023) | (window & 1020): no add on
+ * the walker's chain.  The entry is used as it is as a funnel-shift count (the low five bits
+ * count; no step advances 32 bits or more where the window is shifted), and its byte 0 is added
+ * to the position by a dot-product instruction.
+ */
+constexpr uint32_t W1_A_UNI = 32768u;
+constexpr uint32_t W1_A_RING = 196608u;
+constexpr uint32_t W1_DONE = 0x100u, W1_BAD = 0x200u; /* entry flags (pages are 1024-byte aligned: bits 8, 9 are free) */
+static_assert(W1_A_UNI + W1_UNI_BYTES <= W1_A_RING, "the table ends below the ring");
+constexpr uint32_t W1_A_TAIL = W1_A_RING + 4u * W1_RING;
+constexpr uint32_t W1_A_OFF = W1_A_TAIL + 16u;               /* u16 off[COLS + 8] */
+constexpr uint32_t W1_A_CTL = W1_A_OFF + 2u * (COLS + 8);    /* wpos, fill, quit, s_target, s_quit */
+constexpr uint32_t W1_A_END = W1_A_CTL + 32u;
+constexpr size_t W1_SMEM = W1_A_END; /* the allocation starts above address 0: this much always reaches W1_A_END */
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
+{
+	asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v)
+{
+	asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v)
+{
+	asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+/* the four ring words from the one that holds bit R on */
+struct Win4 {
+	uint32_t w0, w1, w2, w3;
 };
+__device__ __forceinline__ Win4 ring4(uint32_t R)
+{
+	/* (R >> 3) & 0x3FFC: SHF + LOP3; the ring's base is the loads' immediate offset */
+	const uint32_t a0 = (R >> 3) & ((W1_RING - 1u) << 2);
+	Win4 w;
+	/* a0 + 4 k stays inside [0, 16 K + 12): the tail copy sits right behind the ring */
+	asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w.w0) : "r"(a0), "n"(W1_A_RING));
+	asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w.w1) : "r"(a0), "n"(W1_A_RING + 4u));
+	asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w.w2) : "r"(a0), "n"(W1_A_RING + 8u));
+	asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(w.w3) : "r"(a0), "n"(W1_A_RING + 12u));
+	return w;
+}
 
 __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, SplitArgs g, uint32_t b0, uint32_t nb, uint32_t P0)
 {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	SmemWalk1 &sm = *reinterpret_cast<SmemWalk1 *>(smem_raw);
 	const int tid = threadIdx.x, lane = tid & 31;
+	const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw);
+	/* the layout is by absolute address: the allocation must start at or below the table (it does:
+	 * the window's first kilobyte is the system's) and reach W1_A_END */
+	if (sbase > W1_A_UNI) {
+		if (tid == 0)
+			atomicExch(a.errflag, 1u);
+		return;
+	}
 	for (int i = tid; i < ACM_UNI_PAGES * ACM_UNI_PSIZE; i += W1_THREADS) {
 		const uint32_t e = a.tables->uni16[i];
-		sm.uni32[i] = (e & 0xFFu) | ((e >> 8) * W1_PBYTES);
+		const uint32_t page = e >> 8;
+		uint32_t w = (e & 0xFFu) | (page ? W1_A_UNI + page * W1_PBYTES : W1_A_UNI | W1_DONE);
+		if ((uint32_t)i / ACM_UNI_PSIZE == (uint32_t)ACM_UNI_BAD)
+			w = W1_A_UNI | W1_DONE | W1_BAD; /* where a bad selector leads: 0 bits, done, flagged */
+		asm volatile("st.shared.u32 [%0], %1;" ::"r"(W1_A_UNI + 4u * (uint32_t)i), "r"(w) : "memory");
 	}
-	__syncthreads();
-	if (tid >= 32)
-		return;
 	const DevStream d = a.streams[0];
 	const Gen2Stream gs = g.gs[0];
-	const uint32_t *const words = reinterpret_cast<const uint32_t *>(a.blob + d.base_off);
+	/* a launch that continues where the previous one stopped (P0 = 0, b0 > 0) finds its start in
+	 * the previous block's record */
+	if (b0 && !P0)
+		P0 = __ldcg(&g.rec[gs.rec_base + b0 - 1u].end);
+	constexpr uint32_t A_WPOS = W1_A_CTL, A_FILL = W1_A_CTL + 4u, A_QUIT = W1_A_CTL + 8u, A_TARGET = W1_A_CTL + 12u,
+			   A_SQUIT = W1_A_CTL + 16u;
+	if (tid == 0) {
+		sts32_volatile(A_WPOS, P0 >> 5);
+		sts32_volatile(A_FILL, (P0 >> 5) & ~3u);
+		sts32_volatile(A_QUIT, 0u);
+	}
+	__syncthreads();
+
+	if (tid >= 32) {
+		/* ---- stagers: 16-byte chunks of the stream into the ring, up to a ring's length ahead */
+		const int st = tid - 32;
+		const uint8_t *base = a.blob + d.base_off;
+		const uint32_t room16 = a.blob_room > d.base_off ? (uint32_t)((a.blob_room - d.base_off) >> 4) : 0u;
+		const uint32_t fe_byte = d.file_end >> 3;
+		const uint32_t full16 = fe_byte >> 4 < room16 ? fe_byte >> 4 : room16;
+		uint32_t fill = (P0 >> 5) & ~3u;
+		for (;;) {
+			if (st == 0) {
+				sts32_volatile(A_TARGET, (lds32_volatile(A_WPOS) & ~3u) + W1_RING);
+				sts32_volatile(A_SQUIT, lds32_volatile(A_QUIT));
+			}
+			asm volatile("bar.sync 1, %0;" ::"n"(W1_STAGERS) : "memory");
+			const uint32_t target = lds32_volatile(A_TARGET);
+			if (lds32_volatile(A_SQUIT))
+				break;
+			uint32_t n = (target - fill) >> 2;
+			n = n < (uint32_t)W1_STAGERS ? n : (uint32_t)W1_STAGERS;
+			if ((uint32_t)st < n) {
+				const uint32_t c = (fill >> 2) + (uint32_t)st;
+				uint4 v = make_uint4(0u, 0u, 0u, 0u);
+				if (c < full16) {
+					v = __ldg(reinterpret_cast<const uint4 *>(base) + c);
+				} else if (c < room16 && c * 16u < fe_byte) {
+					/* the chunk that holds the end of the file: 1 .. 15 of its bytes exist */
+					v = __ldg(reinterpret_cast<const uint4 *>(base) + c);
+					const uint32_t nbytes = fe_byte - c * 16u;
+					uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const uint32_t m = nbytes > 4u * k ? nbytes - 4u * k : 0u;
+						w[k] = m >= 4u ? w[k] : m ? w[k] & ((1u << (8u * m)) - 1u) : 0u;
+					}
+					v = make_uint4(w[0], w[1], w[2], w[3]);
+				}
+				const uint32_t at = (c << 4) & (4u * W1_RING - 1u);
+				sts128(W1_A_RING + at, v);
+				if (at == 0u)
+					sts128(W1_A_TAIL, v);
+			}
+			asm volatile("bar.sync 1, %0;" ::"n"(W1_STAGERS) : "memory");
+			fill += 4u * n;
+			if (st == 0) {
+				__threadfence_block();
+				sts32_volatile(A_FILL, fill);
+			}
+			if (n == 0u)
+				__nanosleep(400);
+		}
+		return;
+	}
+
+	/* ---- the walker: lane 0 walks, the warp writes the block's column offsets */
 	const uint32_t limit = d.file_end + 8u;
-	/* the last word index a 4-word window may start at; positions beyond it only occur in blocks
-	 * that are walked again with the reference's verdicts */
-	const uint32_t room_w = a.blob_room > d.base_off ? (uint32_t)((a.blob_room - d.base_off) / 4u) : 0u;
-	const uint32_t last_i = room_w > 4u ? room_w - 4u : 0u;
-	const unsigned char *uni = reinterpret_cast<const unsigned char *>(sm.uni32);
-	constexpr uint32_t S_K0 = (uint32_t)ACM_UNI_K0 * W1_PBYTES, S_HALT = (uint32_t)ACM_UNI_HALT * W1_PBYTES,
-			   S_SKIP6 = (uint32_t)ACM_UNI_SKIP6 * W1_PBYTES;
 	constexpr uint32_t M_SEL = 0x1FFFu << 2, M_K = ((1u << ACM_UNI_KBITS) - 1u) << 2;
 	uint32_t P = P0, b = b0;
+#ifdef W1_DEBUG
+	unsigned long long t0c = clock64(), t0n, waitc = 0;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0n));
+#endif
 	for (; b < b0 + nb; b++) {
 		int status = SCAN_EOF;
 		uint32_t ncols = 0, pend = P, val = 0;
 		if (lane == 0 && P + 20u <= limit) {
-			/* the block's lines, once: the loads below are L1 hits */
-			for (uint32_t k = 0; k < 12u; k++) {
-				const uint32_t wi = (P >> 5) + 32u * k;
-				if (wi < room_w)
-					asm volatile("prefetch.global.L1 [%0];" ::"l"(words + wi));
-			}
+			/* the whole block is in the ring before its walk starts */
+			sts32_volatile(A_WPOS, P >> 5);
+#ifdef W1_DEBUG
+			unsigned long long tw = clock64();
+#endif
+			while ((int32_t)(lds32_volatile(A_FILL) - ((P >> 5) + W1_BLOCK_WORDS)) < 0)
+				;
+#ifdef W1_DEBUG
+			waitc += clock64() - tw;
+#endif
+			__threadfence_block();
 			bool clean = true;
-			{
-				const uint32_t i = min(P >> 5, last_i);
-				val = (fsr(__ldg(words + i), __ldg(words + i + 1), P) >> 4) & 0xFFFFu; /* pwr(4) val(16): decode.c:588-589 */
-			}
+			Win4 w = ring4(P);
+			val = (fsr(w.w0, w.w1, P) >> 4) & 0xFFFFu; /* pwr(4) val(16): decode.c:588-589 */
 			/* R = position - 2: the 32 bits at R, masked, are the byte offset of a 4-byte table entry */
 			uint32_t R = P + 18u;
+			w = ring4(R);
+			uint32_t flags = 0u;
+#pragma unroll 4
 			for (uint32_t c = 0; c < (uint32_t)COLS; c++) {
-				const uint32_t i = min(R >> 5, last_i);
-				const uint32_t *wp = words + i;
-				const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
-				uint32_t lo = fsr(w0, w1, R);
-				uint32_t e = *reinterpret_cast<const uint32_t *>(uni + (lo & M_SEL));
-				sm.off[c] = (uint16_t)(R + 2u - P);
-				const uint32_t R0 = R;
+				uint32_t lo = fsr(w.w0, w.w1, R);
+				uint32_t e;
+				asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(e) : "r"(lo & M_SEL), "n"(W1_A_UNI));
+				uint32_t mid = fsr(w.w1, w.w2, R), hi = fsr(w.w2, w.w3, R);
+				sts16(W1_A_OFF + 2u * c, R + 2u - P);
 				R = __dp4a(e, 1u, R); /* += byte 0 */
-				if (e < W1_PBYTES)
-					continue; /* a fixed-size column, walked in one step */
-				if (e >= S_K0 && e < S_HALT) {
-					/* inside a prefix-coded column: <= 80 payload bits, all in the window */
-					const uint32_t w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
-					uint32_t mid = fsr(w1, w2, R0), hi = fsr(w2, w3, R0);
-					do {
-						lo = fsr(lo, mid, e);
-						mid = fsr(mid, hi, e);
-						hi = fsr(hi, 0u, e);
-						e = *reinterpret_cast<const uint32_t *>(uni + ((e & ~(W1_PBYTES - 1u)) | (lo & M_K)));
-						R = __dp4a(e, 1u, R);
-					} while (e >= W1_PBYTES);
-				} else if ((e & ~(W1_PBYTES - 1u)) == S_SKIP6) {
-					R += 6u; /* 16-bit linear column: 261 bits */
-				} else {
-					clean = false; /* bad selector (f_bad, decode.c:190-194) */
-					break;
+				/* the next column's window, as if this one were of fixed size (it is, more often than not):
+				 * on its way before the branch below is resolved */
+				w = ring4(R);
+				if (!(e & W1_DONE)) {
+					/* inside a prefix-coded column (<= 80 payload bits, all in the window), or on the way to
+					 * the SKIP6 / BAD page.  Every lookup is issued BEFORE the branch on the entry before it
+					 * resolves (a finished column's entry points at the selector page: the one lookup too
+					 * many reads a valid address and is dropped), so the branch waits in the shadow of the
+					 * load instead of on the chain: table LDS -> funnel shift -> mask -> table LDS */
+#define W1_SHIFT_LOOKUP(ec, out)                                                                                       \
+	do {                                                                                                            \
+		lo = fsr(lo, mid, ec);                                                                                  \
+		mid = fsr(mid, hi, ec);                                                                                 \
+		hi = fsr(hi, 0u, ec);                                                                                   \
+		uint32_t page_, at_;                                                                                    \
+		asm volatile("and.b32 %0, %1, %2;" : "=r"(page_) : "r"(ec), "n"(~(W1_PBYTES - 1u)));                    \
+		asm volatile("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(at_) : "r"(lo), "n"(M_K), "r"(page_));          \
+		out = lds32(at_);                                                                                       \
+	} while (0)
+					uint32_t ea, eb, spec; /* ea / eb alternate: no register copy between a load and the branch behind it */
+					W1_SHIFT_LOOKUP(e, ea);
+					for (;;) {
+						W1_SHIFT_LOOKUP(ea, eb);
+						R = __dp4a(ea, 1u, R);
+						if (ea & W1_DONE) {
+							flags |= ea;
+							spec = eb;
+							break;
+						}
+						W1_SHIFT_LOOKUP(eb, ea);
+						R = __dp4a(eb, 1u, R);
+						if (eb & W1_DONE) {
+							flags |= eb;
+							spec = ea;
+							break;
+						}
+					}
+					w = ring4(R);
+					/* the lookup too many is "used" (selector-page entries never carry W1_BAD), and only here,
+					 * when it has long landed: the compiler would otherwise sink it below the branch */
+					flags |= spec & W1_BAD;
 				}
 			}
+			clean = !(flags & W1_BAD);
 			if (clean && R + 2u <= limit) {
 				status = SCAN_OK; /* 128 columns, every read inside the stream */
 				ncols = COLS;
@@ -348,8 +517,9 @@ __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, 
 			} else {
 				/* bad selector, or the stream ended inside the block: the reference's verdicts */
 				BitReader br;
-				br.init(words, d.file_end);
-				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS, sm.off, P, a.tables->kind, a.tables->k8);
+				br.init(reinterpret_cast<const uint32_t *>(a.blob + d.base_off), d.file_end);
+				uint16_t *off = reinterpret_cast<uint16_t *>(smem_raw + (W1_A_OFF - sbase));
+				const ScanResult sc = scan_block(br, P, limit, (uint32_t)COLS, (uint32_t)ROWS, off, P, a.tables->kind, a.tables->k8);
 				status = sc.status;
 				ncols = sc.ncols;
 				pend = sc.end;
@@ -360,7 +530,8 @@ __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, 
 		pend = __shfl_sync(0xFFFFFFFFu, pend, 0);
 		__syncwarp();
 		{
-			const uint2 v = *reinterpret_cast<const uint2 *>(&sm.off[4 * lane]);
+			uint2 v;
+			asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(W1_A_OFF + 8u * (uint32_t)lane) : "memory");
 			reinterpret_cast<uint2 *>(g.coff16 + (gs.rec_base + b) * (uint64_t)COLS)[lane] = v;
 		}
 		if (lane == 0) {
@@ -375,8 +546,15 @@ __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, 
 		}
 		P = pend;
 	}
-	if (lane == 0)
+	if (lane == 0) {
 		g.nscan[0] = b;
+		sts32_volatile(A_QUIT, 1u);
+#ifdef W1_DEBUG
+		unsigned long long t1n;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1n));
+		printf("walk1: %u blocks, %llu cycles (%llu waiting for the ring), %llu ns\n", b - b0, clock64() - t0c, waitc, t1n - t0n);
+#endif
+	}
 }
 
 /* ================================================================== unpack */
@@ -1101,7 +1279,7 @@ static cudaError_t split_configure()
 					 (int)sizeof(walk::SmemWalk));
 		if (e == cudaSuccess)
 			e = cudaFuncSetAttribute(split::acm_walk1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-						 (int)sizeof(split::SmemWalk1));
+						 (int)split::W1_SMEM);
 		if (e == cudaSuccess)
 			e = cudaFuncSetAttribute(split::acm_lift_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 						 (int)split::LIFT_SMEM);
@@ -1156,7 +1334,7 @@ cudaError_t launch_split_range(const KernelArgs &a, const SplitArgs &g, uint32_t
 	cudaError_t e = split_configure();
 	if (e != cudaSuccess)
 		return e;
-	split::acm_walk1_kernel<<<1, split::W1_THREADS, sizeof(split::SmemWalk1), st>>>(a, g, b0, nb, P0);
+	split::acm_walk1_kernel<<<1, split::W1_THREADS, split::W1_SMEM, st>>>(a, g, b0, nb, P0);
 	const uint32_t u0 = b0 ? b0 - 1u : 0u;
 	launch_unpack(a, g, u0, (uint64_t)b0 + nb - u0, sms, st);
 	if (lift)
