@@ -519,6 +519,19 @@ def run_ours(args):
             cpu = {"value": round(r, 2), "unit": "Msamples/s", "cores": threads_cpu, "kind": kind,
                    "sample": f"first {n_sample} streams of the workload ({wds} words, {dt:.2f} s wall), "
                              f"in-memory images, one decode each"}
+        streaming = None
+        if world == 1 and not args.no_streaming:
+            # BASELINE configs[0] / configs[4]: ONE stream through the libacm.h drop-in surface, beside the
+            # reference on one host core (same C harness on both sides; tools/stream_time.py)
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import stream_time
+                streaming = stream_time.run(reps=3, seek=True)
+                streaming["what"] = ("config 1: open + acm_read_loop(8 KiB requests) + close of one 60 s stereo 22 050 Hz "
+                                     "stream; config 5: first forward acm_seek_pcm to the middle of a 5 min stereo 44 100 Hz "
+                                     "stream + one read; best of 3; reference = unmodified libacm on one host core")
+            except Exception as e:  # the bench line must not depend on it
+                streaming = {"error": repr(e)}
         line = {
             "metric": "batched decode PCM Msamples/s", "value": round(value, 1), "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
@@ -555,6 +568,7 @@ def run_ours(args):
             "gpu_launches": n_launches * args.steps,
             "clocks": clocks,
             "config4": config4,
+            "streaming": streaming,
         }
         print(json.dumps(line), flush=True)
     plan.close()
@@ -583,6 +597,7 @@ def main():
     ap.add_argument("--no-acmtool", action="store_true", help="reference arm: skip the acmtool / xargs variant")
     ap.add_argument("--acmtool-streams", type=int, default=N_STREAMS)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true", help="skip the single-stream libacm.h timing block")
     ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
                     help="config2 = BASELINE configs[1] (the headline); config4 = configs[3] shape per GPU")
     args = ap.parse_args()

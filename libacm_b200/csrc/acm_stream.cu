@@ -113,6 +113,7 @@ struct GpuState {
 	BlockRec *h_recs[2] = { nullptr, nullptr };
 	uint32_t *h_state[2] = { nullptr, nullptr };
 	int cur_slot = 0;
+	cudaEvent_t slot_done[2] = { nullptr, nullptr }; /* recorded behind a chunk's last copy */
 	struct Ahead {
 		bool active = false;
 		uint32_t b0 = 0, nb = 0, P0 = 0;
@@ -285,6 +286,9 @@ void gpu_free(GpuState *g)
 		pool_free(g->h_recs[k]);
 		pool_free(g->h_state[k]);
 	}
+	for (int k = 0; k < 2; k++)
+		if (g->slot_done[k])
+			cudaEventDestroy(g->slot_done[k]);
 	if (g->stream)
 		cudaStreamDestroy(g->stream);
 	delete g;
@@ -375,6 +379,7 @@ int gpu_setup(GpuState *g)
 			CUS(pool_alloc((void **)&g->h_chunk[k], cb, true, g->device));
 			CUS(pool_alloc((void **)&g->h_recs[k], (size_t)g->chunk_blocks * sizeof(BlockRec), true, g->device));
 			CUS(pool_alloc((void **)&g->h_state[k], 16, true, g->device));
+			CUS(cudaEventCreateWithFlags(&g->slot_done[k], cudaEventDisableTiming));
 		}
 	}
 	return ACM_OK;
@@ -625,6 +630,7 @@ int split_launch(ACMStream *acm, GpuState *g, uint32_t b0, uint32_t nb, uint32_t
 		if (words)
 			CUS(cudaMemcpyAsync(g->h_chunk[slot], g->d_chunk[slot], (size_t)words * 2, cudaMemcpyDeviceToHost, g->stream));
 	}
+	CUS(cudaEventRecord(g->slot_done[slot], g->stream));
 	return ACM_OK;
 }
 
@@ -713,6 +719,82 @@ int decode_chunk_split(ACMStream *acm, GpuState *g, size_t si, uint32_t nb, DevS
 	split_finish(acm, g, b0, nb, P0, fmt_key(be, 2, sgned), lift, slot);
 	if (lift)
 		split_look_ahead(acm, g, be, sgned);
+	return ACM_OK;
+}
+
+/*
+ * A seek skipping ahead on the split path: walk (and unpack, which finds out-of-range radix codes)
+ * whole chunks until the index reaches the chunk that holds block tb; nothing is transformed or
+ * copied.  Two chunks are in flight: chunk k + 1 is queued -- its walk takes its start position from
+ * chunk k's last record on the device -- before the host waits for chunk k, so the walker, the one
+ * serial resource, never waits for the host.
+ */
+int split_skip_ahead(ACMStream *acm, GpuState *g, uint32_t tb)
+{
+	struct Pend {
+		bool on = false;
+		uint32_t b0 = 0, nb = 0;
+		int slot = 0;
+	} pend;
+	const unsigned long long colbits = 5ull + 16ull * g->hdr.rows;
+	const unsigned long long blkbytes = (20ull + (unsigned long long)g->cols * colbits + 7ull) / 8ull;
+	CUS(cudaSetDevice(g->device));
+	if (g->ahead.active) {
+		CUS(cudaStreamSynchronize(g->stream)); /* a look-ahead of the read path: dropped */
+		g->ahead.active = false;
+	}
+	uint32_t nextb = g->index.back().block;
+	/* where the next chunk can start at most (bytes from the start of the image) */
+	unsigned long long at_upper = g->base.base_off + (g->index.back().P >> 3);
+	for (;;) {
+		const bool more = nextb + g->chunk_blocks <= tb && nextb + g->chunk_blocks < g->n_attempt_total;
+		int slot = 0;
+		if (more) {
+			DevStream d = g->base;
+			at_upper += (unsigned long long)g->chunk_blocks * blkbytes;
+			unsigned long long want = at_upper + 64ull;
+			if (want > ((unsigned long long)1 << 40))
+				want = (unsigned long long)1 << 40;
+			int perr = pull(acm, g, (size_t)want);
+			if (perr < 0)
+				return perr;
+			perr = upload(g);
+			if (perr < 0)
+				return perr;
+			const uint32_t hdr = g->hdr.header_len;
+			const unsigned long long data_len = g->file.size() > hdr ? g->file.size() - hdr : 0;
+			if (data_len * 8ull + 256ull + (1ull << 20) >= 0xFFFFFFFFull) {
+				acm_set_error("stream image of 512 MiB or more: not supported by the device decoder");
+				return ACM_ERR_OTHER;
+			}
+			d.file_end = g->base.bit0 + (uint32_t)data_len * 8u;
+			g->base.file_end = d.file_end;
+			slot = pend.on ? 1 - pend.slot : 1 - g->cur_slot;
+			/* P0 = 0: continue from the previous chunk's last record (on the device) */
+			const int err = split_launch(acm, g, nextb, g->chunk_blocks, pend.on ? 0u : g->index.back().P, d, 0, 1, false, slot);
+			if (err < 0)
+				return err;
+		}
+		if (pend.on) {
+			CUS(cudaEventSynchronize(g->slot_done[pend.slot]));
+			const size_t before = g->index.size();
+			split_finish(acm, g, pend.b0, pend.nb, 0u, fmt_key(0, 2, 1), false, pend.slot);
+			if (g->index.size() == before) {
+				/* a block on the way does not decode: the read loop reports it */
+				if (more)
+					CUS(cudaStreamSynchronize(g->stream));
+				return ACM_OK;
+			}
+			at_upper = g->base.base_off + (g->index.back().P >> 3) + (more ? (unsigned long long)g->chunk_blocks * blkbytes : 0ull);
+		}
+		if (!more)
+			break;
+		pend.on = true;
+		pend.b0 = nextb;
+		pend.nb = g->chunk_blocks;
+		pend.slot = slot;
+		nextb += g->chunk_blocks;
+	}
 	return ACM_OK;
 }
 
@@ -968,13 +1050,9 @@ extern "C" int acm_seek_pcm(ACMStream *acm, unsigned pcm_pos)
 	if (g->split && word_pos > acm->stream_pos && acm->block_len % acm->info.channels == 0) {
 		/* split path: the walk alone (plus the unpack, which finds out-of-range codes) extends the
 		 * index up to the chunk that holds the target; nothing is transformed or copied on the way */
-		const uint32_t tb = word_pos / acm->block_len;
-		while (g->index.back().block + g->chunk_blocks <= tb &&
-		       g->index.back().block + g->chunk_blocks < g->n_attempt_total) {
-			const size_t before = g->index.size();
-			if (decode_chunk(acm, g, before - 1, 0, 2, 1, false) < 0 || g->index.size() == before)
-				break; /* a block on the way does not decode: the read loop below reports it */
-		}
+		/* whatever goes wrong on the way is reported by the read loop below, as in the reference
+		 * (util.c:243-251: the loop breaks, the position reached is returned) */
+		(void)split_skip_ahead(acm, g, word_pos / acm->block_len);
 	}
 	while (acm->stream_pos < word_pos) {
 		int step = 2048, res;

@@ -227,3 +227,21 @@ def test_config5_full_size_long_stream(libs, level, rows):
             break
     assert a.getters()["pcm_tell"] == b.getters()["pcm_tell"] == pcm_total
     a.close(), b.close()
+
+
+def test_single_stream_at_least_as_fast_as_one_cpu_core(libs):
+    """BASELINE configs[0] / configs[4] through the libacm.h surface, timed (tools/stream_time.py): the
+    drop-in must not be slower than what it replaces -- open + acm_read_loop(8 KiB requests) + close
+    of the 60 s stereo stream at >= the reference's single-core rate, and a first forward
+    acm_seek_pcm to the middle of the 5-minute stereo stream no slower than the reference's
+    (which decodes the whole prefix, util.c:243-251).  Best of several runs on both sides."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import stream_time
+    r = stream_time.run(reps=5, seek=True)
+    g, c = r["gpu"], r["reference"]
+    print(r)
+    assert g["seek_pos"] == c["seek_pos"]
+    assert g["read_loop_msamples_s"] >= c["read_loop_msamples_s"], r
+    assert g["seek_middle_ms"] <= c["seek_middle_ms"], r
