@@ -55,6 +55,18 @@ def corpus_params(n_streams, rank, workload="config2"):
     """Generator parameters of the synthetic workload (one record per stream)."""
     from libacm_b200 import gen
     rng = np.random.default_rng(1234 + rank)
+    if workload == "config3":
+        # BASELINE configs[2]: filler-stress streams (random per-column fill types: every f_k / f_t / f_linear
+        # path), levels 4-10, rows 4-32, plain and WAVC headers, mono and stereo, 1-10 s at 22050 Hz
+        tv = rng.integers(22050, 220500 + 1, size=n_streams)
+        lv = rng.integers(4, 11, size=n_streams)
+        rw = rng.choice(np.array([4, 8, 16, 32]), size=n_streams)
+        chs = rng.integers(1, 3, size=n_streams)
+        wv = rng.integers(0, 2, size=n_streams)
+        return [gen.params(level=int(lv[i]), rows=int(rw[i]), channels=int(chs[i]), rate=22050,
+                           total_values=int(tv[i]) * int(chs[i]), wavc=int(wv[i]), dist=gen.DIST_STRESS,
+                           seed=(rank << 32) + 17 * i + 1)
+                for i in range(n_streams)]
     if workload == "config4":
         # BASELINE configs[3] shape: mixed-length stereo streams, log-uniform 0.05-5 s at 22050 Hz
         tv = config4_lengths(n_streams, rank)
@@ -538,6 +550,9 @@ def run_ours(args):
             "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": WORKLOAD if args.workload == "config2" else
+                       "filler-stress corpus (BASELINE configs[2]): random per-column fill types, levels 4-10, rows 4-32, "
+                       "plain and WAVC headers, mono and stereo, 1-10 s at 22050 Hz, via acm_gpu_decode_batch"
+                       if args.workload == "config3" else
                        "mixed-length synthetic stereo 22050 Hz streams (level 7, 16 rows, log-uniform 0.05-5 s), "
                        "sharded by stream (BASELINE configs[3] shape)",
                        "streams_per_gpu": args.streams,
@@ -598,8 +613,9 @@ def main():
     ap.add_argument("--acmtool-streams", type=int, default=N_STREAMS)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-streaming", action="store_true", help="skip the single-stream libacm.h timing block")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
-                    help="config2 = BASELINE configs[1] (the headline); config4 = configs[3] shape per GPU")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"],
+                    help="config2 = BASELINE configs[1] (the headline); config3 = configs[2] (filler-stress corpus, levels 4-10: the "
+                         "general path); config4 = configs[3] shape per GPU")
     args = ap.parse_args()
     from libacm_b200 import build
     rank, _, _ = dist_env()

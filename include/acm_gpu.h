@@ -123,6 +123,10 @@ int acm_gpu_plan_fetch(acm_gpu_plan *plan, acm_gpu_stream *streams, void *cuda_s
 int acm_gpu_plan_launches(const acm_gpu_plan *plan);
 /* streams routed to the (fast, generic) kernels */
 void acm_gpu_plan_split(const acm_gpu_plan *plan, uint64_t *n_fast, uint64_t *n_generic);
+/* the same by decode route: out4 = { the fused level-7 / 16-row kernel, the split path (opts.kernel = 2),
+ * the general throughput path (any rows, level <= 10: scan -> unpack -> tile lift), the block-at-a-time
+ * backstop (level 11..15) } */
+void acm_gpu_plan_routes(const acm_gpu_plan *plan, uint64_t *out4);
 /* average device time of the kernels of the last run on that plan, ms (CUDA events on cuda_stream) */
 float acm_gpu_plan_last_ms(acm_gpu_plan *plan);
 void acm_gpu_plan_destroy(acm_gpu_plan *plan);

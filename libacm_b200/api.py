@@ -73,6 +73,8 @@ def lib():
         L.acm_gpu_plan_launches.restype = C.c_int
         L.acm_gpu_plan_split.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.acm_gpu_plan_split.restype = None
+        L.acm_gpu_plan_routes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.acm_gpu_plan_routes.restype = None
         L.acm_gpu_plan_last_ms.argtypes = [C.c_void_p]
         L.acm_gpu_plan_last_ms.restype = C.c_float
         L.acm_gpu_plan_destroy.argtypes = [C.c_void_p]
@@ -176,6 +178,12 @@ class Plan:
         a, b = C.c_uint64(0), C.c_uint64(0)
         lib().acm_gpu_plan_split(self._h, C.byref(a), C.byref(b))
         return a.value, b.value
+
+    def routes(self):
+        """(fused level-7 kernel, split path, general throughput path, backstop) stream counts"""
+        out = (C.c_uint64 * 4)()
+        lib().acm_gpu_plan_routes(self._h, out)
+        return tuple(int(v) for v in out)
 
     def last_ms(self) -> float:
         return lib().acm_gpu_plan_last_ms(self._h)

@@ -181,6 +181,8 @@ struct Segment {
 	int walk_bound;                   /* fast kernel: the longest stream's walk bounds the launch (more scan CTAs) */
 	uint64_t item_first, n_items;     /* general path: this segment's decode work items */
 	uint64_t g2_first;                /* ... and its slice of the per-stream arrays */
+	uint64_t tile_first, n_tiles;     /* level <= 10: lift tiles */
+	uint32_t n_deep;                  /* generic streams of level > 10 */
 	uint64_t split_first, n_split;    /* split path (acm_split.cu): slice of d_streams, */
 	uint64_t sp_item_first, sp_n_items; /* lift work items, */
 	uint64_t sp_first;                /* slice of the per-stream arrays, */
@@ -201,10 +203,12 @@ struct acm_gpu_plan {
 	uint32_t *d_words;
 	unsigned long long *d_cks;
 	acm_tables *d_tables;
-	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue, [4g+2] finished scan warps, [4g+3] heartbeat; [4*nseg] error flag */
+	uint32_t *d_counters; /* per segment g: [4g] fast queue, [4g+1] generic queue, [4g+2] finished scan warps, [4g+3] heartbeat; [4*nseg] error flag;
+			       * [4*nseg+4+4g ..] general path: unpack queue, tile queue, scan queue */
 	GenericScratch scratch;
 	Gen2Args g2;         /* general path: block records, column offsets, work items (device pointers) */
 	size_t g2_state_bytes; /* nscan + first_bad: reset before every run */
+	size_t g2_cks_bytes;   /* per-block checksum slots: zeroed before a run with checksums (tiles add to them) */
 	SplitArgs sp;        /* split path: the same for its streams, plus the intermediates between its kernels */
 	size_t sp_state_bytes;
 	uint64_t n_split;
@@ -263,6 +267,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	std::vector<DevStream> all;
 	std::vector<Gen2Stream> g2_streams; /* parallel to the generic streams, in `all` order */
 	std::vector<Gen2Item> g2_items;
+	std::vector<Gen2Item> g3_tiles;     /* lift work items of the level <= 10 streams */
+	uint64_t g3_words = 0;              /* words of the int16 intermediate */
 	std::vector<Gen2Stream> sp_streams; /* the same for the split path's streams */
 	std::vector<Gen2Item> sp_items;
 	uint64_t g2_blocks = 0, g2_coffs = 0, sp_blocks = 0;
@@ -292,6 +298,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	memset(&p->scratch, 0, sizeof(p->scratch));
 	memset(&p->g2, 0, sizeof(p->g2));
 	p->g2_state_bytes = 0;
+	p->g2_cks_bytes = 0;
 	memset(&p->sp, 0, sizeof(p->sp));
 	p->sp_state_bytes = 0;
 	p->n_split = 0;
@@ -385,6 +392,25 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 				gen.push_back(d);
 				max_blen = std::max(max_blen, blen);
 				max_cols = std::max(max_cols, 1u << g.level);
+			}
+		}
+		/* A small group of level-7 / 16-row streams inside a batch that is mostly other shapes: the
+		 * fused kernel's launch would last as long as the walk of its longest stream (37 us per block)
+		 * whatever the group's size, while the general path walks them alongside its own streams for
+		 * free -- they go with the majority. */
+		if (opts->kernel == 0 && !fast.empty() && !gen.empty()) {
+			uint64_t wf = 0, wg = 0;
+			for (const DevStream &d : fast)
+				wf += (uint64_t)d.n_attempt * (d.rows << d.level);
+			for (const DevStream &d : gen)
+				wg += (uint64_t)d.n_attempt * (d.rows << d.level);
+			if (wf * 4u < wg) {
+				for (const DevStream &d : fast) {
+					gen.push_back(d);
+					max_blen = std::max(max_blen, d.rows << d.level);
+					max_cols = std::max(max_cols, 1u << d.level);
+				}
+				fast.clear();
 			}
 		}
 		if (sg.blob_lo > sg.blob_hi)
@@ -481,6 +507,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		 * history (the look-back is 2*cols-2 words) */
 		sg.item_first = g2_items.size();
 		sg.g2_first = g2_streams.size();
+		sg.tile_first = g3_tiles.size();
+		sg.n_deep = 0;
 		for (size_t k = 0; k < gen.size(); k++) {
 			const DevStream &d = gen[k];
 			Gen2Stream gs;
@@ -491,6 +519,22 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			gs.max_blocks = (uint32_t)gen2_max_blocks(d.n_attempt, d.file_end > d.bit0 ? d.file_end - d.bit0 : 0, d.level);
 			g2_blocks += gs.max_blocks;
 			g2_coffs += (uint64_t)gs.max_blocks * cols;
+			if (d.level <= GEN3_MAX_LEVEL) {
+				/* unpack -> int16 intermediate -> tile lift; tiles cover what the read loop can deliver */
+				const uint64_t wcap = std::min<uint64_t>((uint64_t)gs.max_blocks * blen, d.words_limit);
+				gs.word_base = g3_words;
+				g3_words += ((uint64_t)gs.max_blocks * blen + 7u) & ~(uint64_t)7u;
+				for (uint64_t t0 = 0; t0 < wcap; t0 += GEN3_TILE_WORDS) {
+					Gen2Item it;
+					it.stream = (uint32_t)k;
+					it.b0 = (uint32_t)(t0 / GEN3_TILE_WORDS);
+					it.nb = 1;
+					it.warm = 0;
+					g3_tiles.push_back(it);
+				}
+			} else {
+				sg.n_deep++;
+			}
 			g2_streams.push_back(gs);
 			const uint32_t look = 2u * cols - 2u;
 			const uint32_t warm_full = look ? (look + blen - 1u) / blen : 0u;
@@ -504,6 +548,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			}
 		}
 		sg.n_items = g2_items.size() - sg.item_first;
+		sg.n_tiles = g3_tiles.size() - sg.tile_first;
 		p->n_fast += sg.n_fast;
 		p->n_generic += sg.n_gen;
 		max_fast = std::max(max_fast, sg.n_fast);
@@ -556,7 +601,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		const size_t o_streams = carve((p->n_dev + 1) * sizeof(DevStream));
 		const size_t o_results = carve((n + 1) * 16); /* status (4) | words (4) | checksums (8) */
 		const size_t o_tables = carve(sizeof(acm_tables));
-		const size_t o_counters = carve((4 * p->seg.size() + 4) * sizeof(uint32_t));
+		const size_t o_counters = carve((8 * p->seg.size() + 4) * sizeof(uint32_t));
 		const size_t o_prof = carve(64 * sizeof(unsigned long long));
 		const size_t o_ctl = carve(ctl_bytes);
 		const size_t o_hist = carve(hist_words * 4 + 16);
@@ -573,6 +618,12 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		const size_t o_g2rec = carve((g2_blocks + 1) * sizeof(BlockRec));
 		const size_t o_g2cks = carve((g2_blocks + 1) * 8);
 		const size_t o_g2coff = carve((g2_coffs + 4) * 4);
+		const size_t o_g3tiles = carve((g3_tiles.size() + 1) * sizeof(Gen2Item));
+		const size_t o_g3inter = carve(g3_words ? (g3_words + 8) * 2 : 0);
+		if (g3_words >> 35) {
+			acm_set_error("general path: %llu words of intermediate", (unsigned long long)g3_words);
+			goto fail;
+		}
 		/* split path: per-stream tables and state, work items, and per block: record, checksum,
 		 * column offsets, index bytes, wide mask, side array */
 		const size_t n_sp = sp_streams.size();
@@ -628,6 +679,11 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		p->g2.rec = reinterpret_cast<BlockRec *>(base + o_g2rec);
 		p->g2.cks_blk = reinterpret_cast<unsigned long long *>(base + o_g2cks);
 		p->g2.coff = reinterpret_cast<uint32_t *>(base + o_g2coff);
+		p->g2.tiles = reinterpret_cast<const Gen2Item *>(base + o_g3tiles);
+		p->g2.inter16 = reinterpret_cast<int16_t *>(base + o_g3inter);
+		p->g2_cks_bytes = (g2_blocks + 1) * 8;
+		if (!g3_tiles.empty())
+			CU(cudaMemcpy(base + o_g3tiles, g3_tiles.data(), g3_tiles.size() * sizeof(Gen2Item), cudaMemcpyHostToDevice));
 		p->sp.gs = reinterpret_cast<const Gen2Stream *>(base + o_sps);
 		p->sp.items = reinterpret_cast<const Gen2Item *>(base + o_spitems);
 		p->sp.nscan = reinterpret_cast<uint32_t *>(base + o_spstate);
@@ -739,6 +795,10 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 		g2.items += sg.item_first;
 		g2.n_items = (uint32_t)sg.n_items;
 		g2.item_counter = p->d_counters + 4 * g + 1;
+		g2.tiles += sg.tile_first;
+		g2.n_tiles = (uint32_t)sg.n_tiles;
+		g2.n_deep = sg.n_deep;
+		g2.g3_counters = p->d_counters + 4 * p->seg.size() + 4 + 4 * g;
 		CU(launch_gen2(a, g2, sc, sg.gen_ctas, st));
 	}
 	return ACM_OK;
@@ -755,12 +815,14 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 		return ACM_ERR_OTHER;
 	}
 	CU(cudaSetDevice(p->device));
-	CU(cudaMemsetAsync(p->d_counters, 0, (4 * p->seg.size() + 4) * sizeof(uint32_t), st));
+	CU(cudaMemsetAsync(p->d_counters, 0, (8 * p->seg.size() + 4) * sizeof(uint32_t), st));
 	if (p->d_ctl)
 		CU(cudaMemsetAsync(p->d_ctl, 0, p->ctl_bytes, st));
 	if (p->n_generic) {
 		CU(cudaMemsetAsync(p->g2.nscan, 0, p->g2_state_bytes / 2, st));
 		CU(cudaMemsetAsync(p->g2.first_bad, 0xFF, p->g2_state_bytes / 2, st));
+		if (p->fmt.checksums)
+			CU(cudaMemsetAsync(p->g2.cks_blk, 0, p->g2_cks_bytes, st));
 	}
 	if (p->n_split) {
 		CU(cudaMemsetAsync(p->sp.nscan, 0, p->sp_state_bytes / 2, st));
@@ -820,6 +882,17 @@ extern "C" int acm_gpu_plan_launches(const acm_gpu_plan *p)
 		k += (sg.n_fast ? 1 : 0) + (sg.n_gen ? 2 + (sg.n_items ? 1 : 0) : 0) /* general path: scan, blocks, finish */
 		     + (sg.n_split ? 3 + (sg.sp_n_items ? 1 : 0) : 0);                /* split path: walk, unpack, lift, finish */
 	return k;
+}
+
+extern "C" void acm_gpu_plan_routes(const acm_gpu_plan *p, uint64_t *out4)
+{
+	uint64_t deep = 0;
+	for (const Segment &sg : p->seg)
+		deep += sg.n_deep;
+	out4[0] = p->n_fast;
+	out4[1] = p->n_split;
+	out4[2] = p->n_generic - deep;
+	out4[3] = deep;
 }
 
 extern "C" void acm_gpu_plan_split(const acm_gpu_plan *p, uint64_t *n_fast, uint64_t *n_generic)
@@ -973,12 +1046,14 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 		CUR(cudaEventCreateWithFlags(&ev_k[g], cudaEventDisableTiming));
 	}
 	/* the cursors are zeroed before anything else is queued: the copy-in stream waits for it */
-	CUR(cudaMemsetAsync(plan->d_counters, 0, (4 * ns + 4) * sizeof(uint32_t), w.s_in));
+	CUR(cudaMemsetAsync(plan->d_counters, 0, (8 * ns + 4) * sizeof(uint32_t), w.s_in));
 	if (plan->d_ctl)
 		CUR(cudaMemsetAsync(plan->d_ctl, 0, plan->ctl_bytes, w.s_in));
 	if (plan->n_generic) {
 		CUR(cudaMemsetAsync(plan->g2.nscan, 0, plan->g2_state_bytes / 2, w.s_in));
 		CUR(cudaMemsetAsync(plan->g2.first_bad, 0xFF, plan->g2_state_bytes / 2, w.s_in));
+		if (plan->fmt.checksums)
+			CUR(cudaMemsetAsync(plan->g2.cks_blk, 0, plan->g2_cks_bytes, w.s_in));
 	}
 	if (plan->n_split) {
 		CUR(cudaMemsetAsync(plan->sp.nscan, 0, plan->sp_state_bytes / 2, w.s_in));

@@ -2,7 +2,7 @@
  * acm_gen2.cu -- the GENERAL decode path: any level (cols = 1 << level), any row count, any
  * output format, as three kernels around a table of block records:
  *
- *   scan      acm_scan_kernel: one warp per stream, its first lane walks the stream block by
+ *   scan      acm_scan_kernel: one LANE per stream, which walks the stream block by
  *             block (the walk is serial: where column c+1 starts is only known once column c has
  *             been walked) and leaves, per block, a BlockRec (bit position, val,
  *             verdict) and the position of every column selector.  This is fill_block's control
@@ -22,7 +22,29 @@
  *
  * The level-7 / 16-row shape has its own fused kernel (acm_fast2.cu); everything else, and the
  * 24/32-bit formats, come here.
+ *
+ * Streams of level <= 10 (cols <= 1024: every shape the reference's own files have) take the
+ * THROUGHPUT form of the decode stage, two kernels instead of acm_blocks_kernel:
+ *
+ *   unpack    acm_unpack_any_kernel: with the column positions known every COLUMN of every block
+ *             is an independent unit of work; a CTA takes a run of blocks and spreads their columns
+ *             over its threads (a 16-column block does not leave 7/8 of a CTA idle).  A column
+ *             leaves as int16 quantiser indices (decode.c:174-177 without the midbuf multiply) in
+ *             stream order: word m of the stream at inter16[word_base + m].
+ *   lift      acm_lift_tile_kernel: juggle_block (decode.c:528-577) in flat form does not know
+ *             about blocks at all: the stream is ONE sequence of words run through `level` 3-tap
+ *             stages of delay C = cols/2 ... 1 (row parity = (m / C) & 1 and the "+1" of
+ *             decode.c:561-564 = "m % (cols/2) == 0 in the first stage" hold for stream positions,
+ *             because a block is a whole number of row pairs of every stage).  So the unit of work
+ *             is a TILE of 4096 consecutive words of a stream, whatever its rows and cols, plus the
+ *             2 * cols words before it that its history depends on: int16
+ *             index x the block's multiplier (decode.c:591-600) into shared memory, the stages
+ *             ping-pong between two shared buffers four words per thread (128-bit accesses), the
+ *             last stage's words leave through output_values' shift / format (decode.c:617-677) as
+ *             coalesced stores.  Tiles of one stream are independent: a long stream is transformed
+ *             by many CTAs at once.
  */
+#include "acm_walk.cuh"
 #include "acm_kernels.cuh"
 
 namespace acm {
@@ -30,6 +52,7 @@ namespace acm {
 namespace {
 
 constexpr int G2_THREADS = 128;   /* decode CTA */
+constexpr uint32_t G3_MAXLEVEL = GEN3_MAX_LEVEL; /* cols <= 1024: halo 2048 words */
 constexpr int G2_SCAN_WARPS = 4;  /* scan CTA: one stream per warp */
 
 struct TablesSmem {
@@ -50,39 +73,174 @@ __device__ __forceinline__ void load_tables(TablesSmem &s, const acm_tables *g, 
 
 /* ------------------------------------------------------------------ scan */
 
+/*
+ * All lanes of a warp step their streams together: a step is "read the 32 bits at the lane's
+ * position and act on the lane's state" -- block header, column selector, or one table step inside
+ * a prefix-coded column (up to 7 rows per 8 bits, k8) -- so a warp's 32 walks cost what the slowest
+ * lane's does, not their sum (one stream per lane with scan_block's loops, lanes diverging, was
+ * measured at 265 us per block and lane).  No end-of-file checks on the way: bits past the end read
+ * as zero (BitReader), and a block whose walk ends at or before the limit cannot have read past it;
+ * the rare other block -- and one with a bad selector -- is walked again by scan_block, which has
+ * the reference's verdicts (decode.c:108-135, :190-194).  Lanes take streams from a queue.
+ */
+struct SmemScan {
+	TablesSmem tab;
+	uint32_t ring[walk::RW + 1 + 4][walk::RROW]; /* acm_walk.cuh: [word][warp][lane] */
+};
+constexpr int G2_SCAN_PERIOD = 16; /* steps between two top-ups of the rings */
+
 __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs a, Gen2Args g)
 {
-	__shared__ TablesSmem tab;
-	load_tables(tab, a.tables, threadIdx.x, 32 * G2_SCAN_WARPS);
+	extern __shared__ __align__(128) unsigned char scan_smem[];
+	SmemScan &sm = *reinterpret_cast<SmemScan *>(scan_smem);
+	TablesSmem &tab = sm.tab;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	load_tables(tab, a.tables, tid, 32 * G2_SCAN_WARPS);
+	for (int i = tid; i < (walk::RW + 5) * walk::RROW; i += 32 * G2_SCAN_WARPS)
+		(&sm.ring[0][0])[i] = 0u;
 	__syncthreads();
-	const uint32_t si = blockIdx.x * G2_SCAN_WARPS + (threadIdx.x >> 5);
-	if (si >= a.count || (threadIdx.x & 31) != 0)
-		return;
-	const DevStream d = a.streams[si];
-	const Gen2Stream gs = g.gs[si];
-	const uint32_t cols = 1u << d.level, limit = d.file_end + 8u;
+	/* the lane's stream bits come from its shared-memory ring, topped up for all lanes together with
+	 * 16-byte loads well ahead of the position (acm_walk.cuh): a warp-wide load straight from global
+	 * memory waits for the slowest of 32 unrelated cache lines at every step */
+	walk::Ring ring;
+	const uint32_t lane4 = 4u * (uint32_t)(warp * 32 + lane);
+	ring.rw = &sm.ring[0][warp * 32 + lane];
+	ring.pol = walk::l2_keep_policy();
+	ring.safe = a.blob;
+	ring.hold_c0 = 0u;
+	ring.idle();
+	enum { M_NONE = 0, M_HDR = 1, M_SEL = 2, M_K = 3 };
+	int mode = M_NONE;
+	bool exhausted = false;
+	uint32_t si = 0, cols = 0, rows = 0, limit = 0, nmax = 0, P = 0, Pblk = 0, b = 0, c = 0, rem = 0, ktab = 0, val = 0;
+	uint32_t t15_bits = 0, t27_bits = 0, t37_bits = 0;
+	uint64_t rec_base = 0, coff_base = 0;
+	uint32_t *cp = g.coff;
 	BitReader br;
-	br.init((const uint32_t *)(a.blob + d.base_off), d.file_end);
-	uint32_t P = d.bit0, b = 0;
-	const uint32_t nmax = d.n_attempt < gs.max_blocks ? d.n_attempt : gs.max_blocks;
-	for (; b < nmax; b++) {
-		uint32_t *coff = g.coff + gs.coff_base + (size_t)b * cols;
-		const ScanResult sc = scan_block(br, P, limit, cols, d.rows, coff, 0u, tab.kind, tab.k8);
-		BlockRec r;
-		r.P = P;
-		r.end = sc.end;
-		r.val = sc.val;
-		r.status = sc.status;
-		r.ncols = sc.ncols;
-		r.pad0 = r.pad1 = r.pad2 = 0u;
-		g.rec[gs.rec_base + b] = r;
-		if (sc.status != SCAN_OK) {
-			b++;
-			break; /* the stream ends with this block */
+	br.init(nullptr, 0);
+	for (;;) {
+		if (mode == M_NONE && !exhausted) {
+			const uint32_t idx = atomicAdd(g.g3_counters + 2, 1u);
+			if (idx < a.count) {
+				const DevStream d = a.streams[idx];
+				const Gen2Stream gs = g.gs[idx];
+				si = idx;
+				cols = 1u << d.level;
+				rows = d.rows;
+				t15_bits = ((rows + 2u) / 3u) * 5u; /* f_t15 / f_t27: 3 rows per code, f_t37: 2 (decode.c:405-476) */
+				t27_bits = ((rows + 2u) / 3u) * 7u;
+				t37_bits = ((rows + 1u) / 2u) * 7u;
+				limit = d.file_end + 8u;
+				nmax = d.n_attempt < gs.max_blocks ? d.n_attempt : gs.max_blocks;
+				rec_base = gs.rec_base;
+				coff_base = gs.coff_base;
+				cp = g.coff + coff_base;
+				br.init((const uint32_t *)(a.blob + d.base_off), d.file_end);
+				P = d.bit0;
+				b = 0;
+				ring.start(a.blob + d.base_off, a.blob_room > d.base_off ? a.blob_room - d.base_off : 0, d.file_end, P);
+				mode = M_HDR;
+			} else {
+				exhausted = true;
+			}
 		}
-		P = sc.end;
+		if (!__any_sync(0xFFFFFFFFu, mode != M_NONE))
+			break;
+#pragma unroll 4
+		for (int step = 0; step < G2_SCAN_PERIOD; step++) {
+			/* a lane whose bits have not landed yet does nothing this step */
+			const bool have = mode != M_NONE && P <= ring.ready_p;
+			const uint32_t *rp = walk::ring_word(&sm.ring[0][0], lane4, P << 5);
+			const uint32_t w = walk::fsr(rp[0], rp[walk::RROW], P);
+			/* ---- the common step, at a selector or inside a prefix-coded column: ONE straight-line
+			 * instruction stream for both states (two table loads side by side, selects, a predicated
+			 * store) -- with one warp per sub-partition every branch costs as much as four dependent
+			 * ALU instructions, and lanes in different states would take turns */
+			const bool hdr = have && mode == M_HDR;
+			const bool act = have && mode >= M_SEL;
+			const bool in_k = mode == M_K;
+			const uint32_t ind = w & 31u, kind = tab.kind[ind], cls = kind & 7u, sub = kind >> 3;
+			const uint32_t e = reinterpret_cast<const uint32_t *>(tab.k8)[2u * (ktab + (w & 255u))];
+			{
+				/* column c's selector position (fill_block's "ind = get_bits(5)", decode.c:496); the
+				 * offsets of a stream's blocks are one array: a running pointer */
+				asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
+					     ::"l"(cp), "r"(P), "r"((uint32_t)(act && !in_k)) : "memory");
+			}
+			/* selector: f_zero 5 bits, f_linear 5 + rows * ind (decode.c:196-206), radix codes whole */
+			uint32_t tb = t15_bits;
+			tb = sub == 1u ? t27_bits : tb;
+			tb = sub == 2u ? t37_bits : tb;
+			const uint32_t adv_sel = 5u + (cls == ACM_CLS_LINEAR ? rows * ind : 0u) + (cls == ACM_CLS_T ? tb : 0u);
+			/* prefix codes: whole symbols of the next 8 bits, up to the rows that remain */
+			const uint32_t k = umin32(e & 15u, rem);
+			const uint32_t adv_k = (e >> (4u * k)) & 15u;
+			const bool enter_k = !in_k && cls == ACM_CLS_K;
+			const uint32_t nrem = in_k ? rem - k : rows;
+			const bool col_done = in_k ? nrem == 0u : !enter_k;
+			const bool bad = act && !in_k && cls == ACM_CLS_BAD;
+			P += act ? (in_k ? adv_k : adv_sel) : 0u;
+			c += (act && col_done) ? 1u : 0u;
+			cp += (act && col_done) ? 1 : 0;
+			mode = act ? ((enter_k || (in_k && nrem != 0u)) ? M_K : M_SEL) : mode;
+			ktab = (act && enter_k) ? sub * 256u : ktab;
+			rem = act ? nrem : rem;
+			const bool endblk = act && mode == M_SEL && c == cols;
+			/* ---- the rare step: block header, end of a block, bad selector */
+			if (hdr || endblk || bad) {
+				bool rewalk = bad;
+				if (hdr) {
+					if (b >= nmax) {
+						g.nscan[si] = b;
+						mode = M_NONE;
+					} else if (P + 20u > limit) {
+						/* pwr / val cannot be read: GET_BITS_EXPECT_EOF, decode.c:588-589 */
+						BlockRec r;
+						r.P = P; r.end = P; r.val = 0; r.status = SCAN_EOF; r.ncols = 0; r.pad0 = r.pad1 = r.pad2 = 0u;
+						g.rec[rec_base + b] = r;
+						g.nscan[si] = b + 1u;
+						mode = M_NONE;
+					} else {
+						val = (w >> 4) & 0xFFFFu;
+						Pblk = P;
+						P += 20u;
+						c = 0;
+						mode = M_SEL;
+					}
+				} else if (!bad) {
+					if (P <= limit) {
+						BlockRec r;
+						r.P = Pblk; r.end = P; r.val = (int32_t)val; r.status = SCAN_OK; r.ncols = cols; r.pad0 = r.pad1 = r.pad2 = 0u;
+						g.rec[rec_base + b] = r;
+						b++;
+						mode = M_HDR;
+					} else {
+						rewalk = true;
+					}
+				}
+				if (rewalk) {
+					/* the stream's last block: the reference's verdict */
+					const ScanResult sc = scan_block(br, Pblk, limit, cols, rows, g.coff + coff_base + (size_t)b * cols, 0u, tab.kind, tab.k8);
+					BlockRec r;
+					r.P = Pblk; r.end = sc.end; r.val = sc.val; r.status = sc.status; r.ncols = sc.ncols; r.pad0 = r.pad1 = r.pad2 = 0u;
+					g.rec[rec_base + b] = r;
+					if (sc.status == SCAN_OK) {
+						/* cannot happen (the walk above found the block's end past the limit, or a bad selector) */
+						b++;
+						P = sc.end;
+						cp = g.coff + coff_base + (size_t)b * cols;
+						mode = M_HDR;
+					} else {
+						g.nscan[si] = b + 1u;
+						mode = M_NONE;
+					}
+				}
+				if (mode == M_NONE)
+					ring.idle();
+			}
+		}
+		ring.topup(P);
 	}
-	g.nscan[si] = b;
 }
 
 /* ------------------------------------------------------------------ decode */
@@ -106,11 +264,14 @@ __global__ void __launch_bounds__(G2_THREADS) acm_blocks_kernel(KernelArgs a, Ge
 			s_item = atomicAdd(g.item_counter, 1u);
 		__syncthreads();
 		const uint32_t it = s_item;
+		__syncthreads(); /* everyone has read it before the next one is written */
 		if (it >= g.n_items)
 			break;
 		const Gen2Item item = g.items[it];
 		const uint32_t si = item.stream;
 		const DevStream d = a.streams[si];
+		if (d.level <= G3_MAXLEVEL)
+			continue; /* the unpack + tile-lift kernels' (uniform: decided from the item) */
 		const Gen2Stream gs = g.gs[si];
 		const uint32_t level = d.level, cols = 1u << level, rows = d.rows;
 		const uint32_t blen = rows * cols, limit = d.file_end + 8u;
@@ -198,6 +359,225 @@ __global__ void __launch_bounds__(G2_THREADS) acm_blocks_kernel(KernelArgs a, Ge
 	}
 }
 
+/* ------------------------------------------------------------------ level <= 10: unpack + tile lift */
+
+constexpr int G3_THREADS = 256;
+constexpr uint32_t G3_TILE = GEN3_TILE_WORDS; /* output words per lift work item */
+constexpr uint32_t G3_BUF = G3_TILE + 2048;
+constexpr size_t G3_LIFT_SMEM = 2 * (size_t)G3_BUF * 4;
+
+__global__ void __launch_bounds__(G3_THREADS) acm_unpack_any_kernel(KernelArgs a, Gen2Args g)
+{
+	int16_t *const inter16 = g.inter16;
+	__shared__ TablesSmem tab;
+	__shared__ uint32_t s_item;
+	const int tid = threadIdx.x;
+	load_tables(tab, a.tables, tid, G3_THREADS);
+	__syncthreads();
+	for (;;) {
+		if (tid == 0)
+			s_item = atomicAdd(g.g3_counters, 1u);
+		__syncthreads();
+		const uint32_t it = s_item;
+		__syncthreads();
+		if (it >= g.n_items)
+			break;
+		const Gen2Item item = g.items[it];
+		const uint32_t si = item.stream;
+		const DevStream d = a.streams[si];
+		if (d.level > G3_MAXLEVEL)
+			continue; /* acm_blocks_kernel's */
+		const Gen2Stream gs = g.gs[si];
+		const uint32_t level = d.level, cols = 1u << level, rows = d.rows;
+		const uint32_t blen = rows * cols, limit = d.file_end + 8u;
+		const uint32_t nscan = g.nscan[si];
+		const uint32_t bend = item.b0 + item.nb < nscan ? item.b0 + item.nb : nscan;
+		if (item.b0 >= bend)
+			continue;
+		BitReader br;
+		br.init((const uint32_t *)(a.blob + d.base_off), d.file_end);
+		int16_t *dst0 = inter16 + gs.word_base;
+		const uint32_t ncol_run = (bend - item.b0) << level;
+		for (uint32_t idx = tid; idx < ncol_run; idx += G3_THREADS) {
+			const uint32_t b = item.b0 + (idx >> level), c = idx & (cols - 1u);
+			const BlockRec *rp = g.rec + gs.rec_base + b;
+			const int status = __ldg(&rp->status);
+			/* column ncols is included when its payload ran past the limit: a radix code that still
+			 * fits may be out of range first (decode.c:412/:438/:464) */
+			const uint32_t ncheck = __ldg(&rp->ncols) + (status == -7 ? 1u : 0u);
+			if (c >= ncheck)
+				continue;
+			const uint32_t Pc = __ldg(g.coff + gs.coff_base + (size_t)b * cols + c);
+			const uint32_t ind = br.peek(Pc) & 31u;
+			const int r = decode_column(br, Pc + 5u, limit, ind, tab.kind[ind], rows, 1, dst0 + (size_t)b * blen + c, cols,
+						    tab.k8, tab.t);
+			if (r < 0)
+				atomicMin(g.first_bad + si, b);
+		}
+	}
+}
+
+/* four consecutive outputs of a stage with C < 4 from the eight inputs v[0..7] = words j-4 .. j+3
+ * (j = 4 * q: row parity and the "+1" follow from the word's position alone) */
+template <int C>
+__device__ __forceinline__ uint4 lift_small(const uint32_t (&v)[8], bool first_stage)
+{
+	uint32_t o[4];
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const uint32_t s = v[4 + k] + v[4 + k - 2 * C];
+		uint32_t r = ((k / C) & 1) ? 2u * v[4 + k - C] - s : 2u * v[4 + k - C] + s;
+		if (first_stage && (k % C) == 0)
+			r += 1u; /* decode.c:561-564 */
+		o[k] = r;
+	}
+	return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+__global__ void __launch_bounds__(G3_THREADS) acm_lift_tile_kernel(KernelArgs a, Gen2Args g)
+{
+	const int16_t *const inter16 = g.inter16;
+	const Gen2Item *const tiles = g.tiles;
+	const uint32_t n_tiles = g.n_tiles;
+	uint32_t *const tile_counter = g.g3_counters + 1;
+	extern __shared__ __align__(16) uint32_t g3_smem[];
+	__shared__ uint32_t s_item;
+	uint32_t *bufA = g3_smem, *bufB = g3_smem + G3_BUF;
+	const int tid = threadIdx.x;
+	for (;;) {
+		if (tid == 0)
+			s_item = atomicAdd(tile_counter, 1u);
+		__syncthreads();
+		const uint32_t it = s_item;
+		__syncthreads();
+		if (it >= n_tiles)
+			break;
+		const Gen2Item item = tiles[it];
+		const uint32_t si = item.stream;
+		const DevStream d = a.streams[si];
+		const Gen2Stream gs = g.gs[si];
+		const uint32_t level = d.level, cols = 1u << level, blen = d.rows << level;
+		/* words that are delivered: blocks up to the first one that fails (scan verdict or an
+		 * out-of-range radix code), clipped to what the read loop delivers */
+		const uint32_t ns = g.nscan[si], fb = g.first_bad[si];
+		uint32_t nok = 0;
+		if (ns) {
+			const int last = __ldg(&g.rec[gs.rec_base + ns - 1].status);
+			nok = last == SCAN_OK ? ns : ns - 1u;
+		}
+		nok = fb < nok ? fb : nok;
+		const uint64_t w64 = (uint64_t)nok * blen;
+		const uint32_t wend = w64 < d.words_limit ? (uint32_t)w64 : d.words_limit;
+		const uint32_t t0 = item.b0 * G3_TILE; /* first output word of the tile */
+		if (t0 >= wend)
+			continue;
+		const uint32_t t1 = t0 + G3_TILE < wend ? t0 + G3_TILE : wend;
+		const uint32_t halo = level ? (2u * cols < t0 ? 2u * cols : t0) : 0u; /* a multiple of 4 (t0 is one of 4096) */
+		const uint32_t m0 = t0 - halo;                 /* stream word at buffer position 0 */
+		const uint32_t n = (t1 - m0 + 3u) & ~3u;       /* buffer words in use */
+		const int16_t *src = inter16 + gs.word_base;
+		const uint64_t cap = (uint64_t)gs.max_blocks * blen; /* words the intermediate holds */
+
+		/* ---- load: index x the block's multiplier (midbuf, decode.c:591-600) */
+		for (uint32_t j = 4u * tid; j < n; j += 4u * G3_THREADS) {
+			const uint32_t m = m0 + j;
+			uint32_t b = m / blen;
+			uint32_t bnext = (b + 1u) * blen; /* first word of the next block */
+			uint32_t val = b < ns ? (uint32_t)__ldg(&g.rec[gs.rec_base + b].val) : 0u;
+			uint32_t x[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t mk = m + (uint32_t)k;
+				if (mk >= bnext) {
+					b++;
+					bnext += blen;
+					val = b < ns ? (uint32_t)__ldg(&g.rec[gs.rec_base + b].val) : 0u;
+				}
+				const int16_t idx = (uint64_t)mk < cap ? src[mk] : (int16_t)0;
+				x[k] = (uint32_t)((int32_t)idx * (int32_t)val);
+			}
+			*reinterpret_cast<uint4 *>(bufA + j) = make_uint4(x[0], x[1], x[2], x[3]);
+		}
+		__syncthreads();
+
+		/* ---- the stages: positions before the buffer read as zero -- exact for a tile at the start of
+		 * its stream (decode.c:812: zero history), and only reaches the halo's own words otherwise */
+		uint32_t *cur = bufA, *nxt = bufB;
+		for (uint32_t l = 1; l <= level; l++) {
+			const uint32_t C = cols >> l;
+			if (C >= 4u) {
+				const uint32_t sh = level - l; /* log2 C */
+				for (uint32_t j = 4u * tid; j < n; j += 4u * G3_THREADS) {
+					const uint4 x0 = *reinterpret_cast<const uint4 *>(cur + j);
+					const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+					const uint4 x1 = j >= C ? *reinterpret_cast<const uint4 *>(cur + j - C) : z;
+					const uint4 x2 = j >= 2u * C ? *reinterpret_cast<const uint4 *>(cur + j - 2u * C) : z;
+					const uint32_t m = m0 + j;
+					const bool odd = (m >> sh) & 1u;
+					uint4 o;
+					if (odd) {
+						o.x = 2u * x1.x - (x0.x + x2.x); o.y = 2u * x1.y - (x0.y + x2.y);
+						o.z = 2u * x1.z - (x0.z + x2.z); o.w = 2u * x1.w - (x0.w + x2.w);
+					} else {
+						o.x = 2u * x1.x + (x0.x + x2.x); o.y = 2u * x1.y + (x0.y + x2.y);
+						o.z = 2u * x1.z + (x0.z + x2.z); o.w = 2u * x1.w + (x0.w + x2.w);
+					}
+					if (l == 1u && (m & (C - 1u)) == 0u)
+						o.x += 1u; /* decode.c:561-564 */
+					*reinterpret_cast<uint4 *>(nxt + j) = o;
+				}
+			} else {
+				for (uint32_t j = 4u * tid; j < n; j += 4u * G3_THREADS) {
+					const uint4 x0 = *reinterpret_cast<const uint4 *>(cur + j);
+					const uint4 xp = j >= 4u ? *reinterpret_cast<const uint4 *>(cur + j - 4u) : make_uint4(0u, 0u, 0u, 0u);
+					const uint32_t v[8] = { xp.x, xp.y, xp.z, xp.w, x0.x, x0.y, x0.z, x0.w };
+					*reinterpret_cast<uint4 *>(nxt + j) = C == 2u ? lift_small<2>(v, l == 1u) : lift_small<1>(v, l == 1u);
+				}
+			}
+			__syncthreads();
+			uint32_t *t = cur; cur = nxt; nxt = t;
+		}
+
+		/* ---- output (decode.c:617-677), words [t0, t1) */
+		uint8_t *out = a.out + d.out_off;
+		unsigned long long cks = 0ull;
+		for (uint32_t j = halo + 4u * tid; j < t1 - m0; j += 4u * G3_THREADS) {
+			const uint4 q = *reinterpret_cast<const uint4 *>(cur + j);
+			const uint32_t m = m0 + j;
+			const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+			if (a.fmt.wordlen == 2 && m + 4u <= t1 && !a.fmt.checksums) {
+				uint32_t u[4];
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					u[k] = ((uint32_t)((int32_t)w[k] >> level) + a.fmt.bias) & 0xFFFFu;
+					if (a.fmt.be)
+						u[k] = ((u[k] >> 8) | (u[k] << 8)) & 0xFFFFu;
+				}
+				/* out_off is 16-byte aligned and m a multiple of 4: an 8-byte aligned store */
+				*reinterpret_cast<uint2 *>(out + (size_t)m * 2u) = make_uint2(u[0] | (u[1] << 16), u[2] | (u[3] << 16));
+			} else {
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+					if (m + (uint32_t)k < t1) {
+						const uint32_t u = emit_word(out + (size_t)(m + k) * a.fmt.wordlen, (int32_t)w[k] >> level, a.fmt);
+						if (a.fmt.checksums)
+							cks += (unsigned long long)(m + (uint32_t)k + 1u) * (unsigned long long)(u + 1ull);
+					}
+				}
+			}
+		}
+		if (a.fmt.checksums) {
+			/* the finalise kernel adds up the blocks that were delivered: a tile's sum goes to its first
+			 * block's slot (every block it touches is delivered, or none of its words were emitted) */
+			for (int o = 16; o; o >>= 1)
+				cks += __shfl_xor_sync(0xFFFFFFFFu, cks, o);
+			if ((tid & 31) == 0 && cks)
+				atomicAdd(&g.cks_blk[gs.rec_base + t0 / blen], cks);
+		}
+		__syncthreads(); /* the buffers are free */
+	}
+}
+
 /* ------------------------------------------------------------------ finalise */
 
 __global__ void __launch_bounds__(G2_THREADS) acm_finish_kernel(KernelArgs a, Gen2Args g)
@@ -274,9 +654,38 @@ cudaError_t launch_gen2(const KernelArgs &a, const Gen2Args &g, const GenericScr
 {
 	if (a.count == 0)
 		return cudaSuccess;
-	const unsigned scan_grid = (a.count + G2_SCAN_WARPS - 1) / G2_SCAN_WARPS;
-	acm_scan_kernel<<<scan_grid, 32 * G2_SCAN_WARPS, 0, st>>>(a, g);
-	if (g.n_items)
+	/* scan: one stream per LANE (a lane walks its stream on its own: the code is the scalar walk, the
+	 * warp diverges, but 32 streams are in flight per warp instead of one) */
+	static bool configured[64] = {};
+	int dev = 0, sms = 0;
+	cudaError_t e = cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		return e;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	if (sms < 1)
+		sms = 1;
+	if (!configured[dev & 63]) {
+		e = cudaFuncSetAttribute(acm_lift_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_LIFT_SMEM);
+		if (e == cudaSuccess)
+			e = cudaFuncSetAttribute(acm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemScan));
+		if (e != cudaSuccess)
+			return e;
+		configured[dev & 63] = true;
+	}
+	{
+		/* the walk is latency bound: few streams are spread thin, many fill 16 warps per SM */
+		unsigned scan_grid = (a.count + 32 * G2_SCAN_WARPS - 1) / (32 * G2_SCAN_WARPS);
+		if (scan_grid > (unsigned)sms * 2u)
+			scan_grid = (unsigned)sms * 2u; /* two CTAs' rings fit an SM */
+		acm_scan_kernel<<<scan_grid, 32 * G2_SCAN_WARPS, sizeof(SmemScan), st>>>(a, g);
+	}
+	if (g.n_tiles) {
+		const unsigned ugrid = g.n_items < (unsigned)sms * 8u ? g.n_items : (unsigned)sms * 8u;
+		acm_unpack_any_kernel<<<ugrid, G3_THREADS, 0, st>>>(a, g);
+		const unsigned lgrid = g.n_tiles < (unsigned)sms * 4u ? g.n_tiles : (unsigned)sms * 4u;
+		acm_lift_tile_kernel<<<lgrid, G3_THREADS, G3_LIFT_SMEM, st>>>(a, g);
+	}
+	if (g.n_items && g.n_deep)
 		acm_blocks_kernel<<<n_ctas, G2_THREADS, 0, st>>>(a, g, s);
 	return launch_gen2_finish(a, g, st);
 }

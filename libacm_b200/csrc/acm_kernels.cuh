@@ -73,6 +73,8 @@ struct Gen2Stream {
 	uint64_t coff_base;  /* index of its first column offset: block b's are at coff_base + b * cols */
 	uint32_t max_blocks; /* records reserved: min(n_attempt, what the image can hold) */
 	uint32_t pad;
+	uint64_t word_base;  /* level <= 10: index of the stream's first word in the int16 intermediate */
+	uint64_t pad2;
 };
 
 struct Gen2Item {
@@ -91,7 +93,15 @@ struct Gen2Args {
 	const Gen2Item *items;
 	uint32_t n_items;
 	uint32_t *item_counter;      /* zeroed before launch */
+	/* streams of level <= 10: unpack -> int16 intermediate -> tile lift (acm_gen2.cu) */
+	int16_t *inter16;            /* quantiser indices in stream order */
+	const Gen2Item *tiles;       /* lift work items: stream, b0 = tile number (4096 words each) */
+	uint32_t n_tiles;
+	uint32_t n_deep;             /* streams of level > 10: acm_blocks_kernel's */
+	uint32_t *g3_counters;       /* [0] unpack queue, [1] tile queue, [2] scan queue (zeroed before launch) */
 };
+constexpr uint32_t GEN3_TILE_WORDS = 4096;
+constexpr uint32_t GEN3_MAX_LEVEL = 10;
 
 cudaError_t launch_gen2(const KernelArgs &a, const Gen2Args &g, const GenericScratch &s, int n_ctas, cudaStream_t st);
 /* the finalise kernel alone (also the last stage of the split path) */

@@ -345,3 +345,48 @@ def test_out_buffer_of_exactly_the_layout_size():
     assert np.all(s["status"] == 0) and np.all(guard[nbytes:] == 0x77)
     with pytest.raises(Exception):
         api.decode_batch(blob, s, guard[:nbytes - 1], opts)
+
+
+def test_routes_stress_corpus_takes_the_throughput_paths(checker):
+    """BASELINE configs[2]: every stream of the filler-stress corpus (levels 0-10, any rows) is decoded by a
+    throughput path -- the fused level-7 / 16-row kernel or the general scan -> unpack -> tile-lift path --
+    and none by the block-at-a-time backstop, which is only for levels 11-15."""
+    import torch
+    imgs = corpus.images(corpus.stress_params(max_values=20_000))
+    blob, offs, lens = gu.pack(imgs)
+    opts = api.make_opts()
+    d_blob = torch.from_numpy(blob).cuda()
+    s = api.new_streams(offs, lens)
+    api.probe(d_blob, s, opts)
+    plan = api.Plan(s, opts)
+    fused, split, general, backstop = plan.routes()
+    plan.close()
+    assert fused + split + general + backstop == len(imgs)
+    assert backstop == 0 and split == 0
+    # the handful of level-7 / 16-row streams of this corpus go with the majority (a fused-kernel launch
+    # for four streams would last as long as the walk of the longest of them)
+    assert fused == 0 and general == len(imgs)
+    # ... while a batch of that shape alone is the fused kernel's
+    imgs = corpus.images(corpus.fallout_params(40, seed=2, hi=30_000))
+    blob, offs, lens = gu.pack(imgs)
+    s = api.new_streams(offs, lens)
+    api.probe(blob, s, opts)
+    plan = api.Plan(s, opts)
+    assert plan.routes() == (40, 0, 0, 0)
+    plan.close()
+
+
+def test_levels_11_and_12_take_the_backstop(checker):
+    """acm_level up to 15 is accepted by the reference (decode.c:747); levels above 10 (cols > 1024) are decoded
+    block by block through global scratch.  Mixed with tile-path streams in one batch."""
+    from libacm_b200 import gen
+    plist = []
+    for k, (level, rows) in enumerate([(11, 1), (11, 3), (12, 1), (12, 2), (10, 3), (9, 5), (6, 16)]):
+        blen = rows << level
+        plist.append(gen.params(level=level, rows=rows, channels=1 + k % 2, total_values=blen * 3 + blen // 3 + 1,
+                                dist=gen.DIST_STRESS, seed=7000 + k))
+    imgs = corpus.images(plist)
+    s, out = gu.decode_host(imgs, want_checksums=1)
+    assert gu.compare(imgs, s, out, checker, checksums=True) == []
+    s, out = gu.decode_device(imgs, bigendianp=1, sgned=0)
+    assert gu.compare(imgs, s, out, checker, be=1, sgned=0) == []
