@@ -366,19 +366,33 @@ constexpr uint32_t G3_TILE = GEN3_TILE_WORDS; /* output words per lift work item
 constexpr uint32_t G3_BUF = G3_TILE + 2048;
 constexpr size_t G3_LIFT_SMEM = 2 * (size_t)G3_BUF * 4;
 
+constexpr uint32_t G3_CHUNK = 2048;                 /* columns sorted together */
+constexpr int G3_PER = G3_CHUNK / G3_THREADS;       /* ... per thread */
+constexpr int G3_NCLS = 4;                          /* zero, linear, prefix-coded, radix-coded */
+constexpr uint32_t G3_LIST = G3_CHUNK + 32 * G3_NCLS; /* every class padded to whole warps */
+
+struct SmemUnpackAny {
+	TablesSmem tab;
+	uint32_t list[G3_LIST];   /* the chunk's columns sorted by filler class: Pc of the selector; 0xFFFFFFFF = nothing */
+	uint16_t col[G3_LIST];    /* ... and the column's number within the run */
+	uint32_t cnt[G3_NCLS], base[G3_NCLS + 1];
+	uint32_t next;
+	uint32_t item;
+};
+
 __global__ void __launch_bounds__(G3_THREADS) acm_unpack_any_kernel(KernelArgs a, Gen2Args g)
 {
 	int16_t *const inter16 = g.inter16;
-	__shared__ TablesSmem tab;
-	__shared__ uint32_t s_item;
-	const int tid = threadIdx.x;
+	__shared__ SmemUnpackAny sm;
+	TablesSmem &tab = sm.tab;
+	const int tid = threadIdx.x, lane = tid & 31;
 	load_tables(tab, a.tables, tid, G3_THREADS);
 	__syncthreads();
 	for (;;) {
 		if (tid == 0)
-			s_item = atomicAdd(g.g3_counters, 1u);
+			sm.item = atomicAdd(g.g3_counters, 1u);
 		__syncthreads();
-		const uint32_t it = s_item;
+		const uint32_t it = sm.item;
 		__syncthreads();
 		if (it >= g.n_items)
 			break;
@@ -396,23 +410,90 @@ __global__ void __launch_bounds__(G3_THREADS) acm_unpack_any_kernel(KernelArgs a
 			continue;
 		BitReader br;
 		br.init((const uint32_t *)(a.blob + d.base_off), d.file_end);
-		int16_t *dst0 = inter16 + gs.word_base;
+		int16_t *dst0 = inter16 + gs.word_base + (size_t)item.b0 * blen;
 		const uint32_t ncol_run = (bend - item.b0) << level;
-		for (uint32_t idx = tid; idx < ncol_run; idx += G3_THREADS) {
-			const uint32_t b = item.b0 + (idx >> level), c = idx & (cols - 1u);
-			const BlockRec *rp = g.rec + gs.rec_base + b;
-			const int status = __ldg(&rp->status);
-			/* column ncols is included when its payload ran past the limit: a radix code that still
-			 * fits may be out of range first (decode.c:412/:438/:464) */
-			const uint32_t ncheck = __ldg(&rp->ncols) + (status == -7 ? 1u : 0u);
-			if (c >= ncheck)
-				continue;
-			const uint32_t Pc = __ldg(g.coff + gs.coff_base + (size_t)b * cols + c);
-			const uint32_t ind = br.peek(Pc) & 31u;
-			const int r = decode_column(br, Pc + 5u, limit, ind, tab.kind[ind], rows, 1, dst0 + (size_t)b * blen + c, cols,
-						    tab.k8, tab.t);
-			if (r < 0)
-				atomicMin(g.first_bad + si, b);
+		/* The run's columns in chunks of 2048, each chunk sorted by filler class (counting sort in
+		 * shared memory) so that a warp decodes 32 columns of ONE class: neighbouring columns are of
+		 * unrelated types, and a warp that takes them as they come runs every filler's loop in turn
+		 * (measured on the stress corpus: 7.9 of 32 lanes per instruction). */
+		for (uint32_t c0 = 0; c0 < ncol_run; c0 += G3_CHUNK) {
+			if (tid < G3_NCLS)
+				sm.cnt[tid] = 0u;
+			if (tid == 0)
+				sm.next = 0u;
+			__syncthreads();
+			uint32_t mine[G3_PER], pcs[G3_PER]; /* class << 16 | rank; selector position */
+#pragma unroll
+			for (int k = 0; k < G3_PER; k++) {
+				const uint32_t idx = c0 + (uint32_t)tid + (uint32_t)k * G3_THREADS;
+				uint32_t cls = 7u, Pc = 0u;
+				if (idx < ncol_run) {
+					const uint32_t b = item.b0 + (idx >> level), c = idx & (cols - 1u);
+					const BlockRec *rp = g.rec + gs.rec_base + b;
+					const int status = __ldg(&rp->status);
+					/* column ncols is included when its payload ran past the limit: a radix code that still
+					 * fits may be out of range first (decode.c:412/:438/:464) */
+					const uint32_t ncheck = __ldg(&rp->ncols) + (status == -7 ? 1u : 0u);
+					if (c < ncheck) {
+						Pc = __ldg(g.coff + gs.coff_base + (size_t)b * cols + c);
+						const uint32_t kc = tab.kind[br.peek(Pc) & 31u] & 7u;
+						cls = kc == ACM_CLS_ZERO ? 0u : kc == ACM_CLS_LINEAR ? 1u : kc == ACM_CLS_K ? 2u : kc == ACM_CLS_T ? 3u : 7u;
+					}
+				}
+				/* rank within the class: one shared-memory atomic per class and warp */
+				const unsigned peers = __match_any_sync(0xFFFFFFFFu, cls);
+				const int leader = __ffs((int)peers) - 1;
+				uint32_t base = 0;
+				if (lane == leader && cls != 7u)
+					base = atomicAdd(&sm.cnt[cls], (uint32_t)__popc(peers));
+				base = __shfl_sync(0xFFFFFFFFu, base, leader);
+				mine[k] = (cls << 16) | (base + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+				pcs[k] = Pc;
+			}
+			__syncthreads();
+			if (tid == 0) {
+				uint32_t acc = 0;
+				for (int c = 0; c < G3_NCLS; c++) {
+					sm.base[c] = acc;
+					acc += (sm.cnt[c] + 31u) & ~31u;
+				}
+				sm.base[G3_NCLS] = acc;
+			}
+			__syncthreads();
+#pragma unroll
+			for (int k = 0; k < G3_PER; k++) {
+				const uint32_t cls = mine[k] >> 16, rank = mine[k] & 0xFFFFu;
+				if (cls != 7u) {
+					const uint32_t at = sm.base[cls] + rank;
+					sm.list[at] = pcs[k];
+					sm.col[at] = (uint16_t)(tid + k * G3_THREADS);
+				}
+			}
+			if (tid < G3_NCLS) /* the holes at the end of every class */
+				for (uint32_t i = sm.base[tid] + sm.cnt[tid]; i < sm.base[tid + 1]; i++)
+					sm.list[i] = 0xFFFFFFFFu;
+			__syncthreads();
+			/* ---- a warp takes the next 32 columns of the sorted list */
+			const uint32_t nwork = sm.base[G3_NCLS] >> 5;
+			for (;;) {
+				uint32_t w = 0;
+				if (lane == 0)
+					w = atomicAdd(&sm.next, 1u);
+				w = __shfl_sync(0xFFFFFFFFu, w, 0);
+				if (w >= nwork)
+					break;
+				const uint32_t Pc = sm.list[32u * w + (uint32_t)lane];
+				if (Pc != 0xFFFFFFFFu) {
+					const uint32_t idx = c0 + sm.col[32u * w + (uint32_t)lane];
+					const uint32_t b = idx >> level, c = idx & (cols - 1u); /* b relative to the run */
+					const uint32_t ind = br.peek(Pc) & 31u;
+					const int r = decode_column(br, Pc + 5u, limit, ind, tab.kind[ind], rows, 1, dst0 + (size_t)b * blen + c, cols,
+								    tab.k8, tab.t);
+					if (r < 0)
+						atomicMin(g.first_bad + si, item.b0 + b);
+				}
+			}
+			__syncthreads(); /* the lists are free */
 		}
 	}
 }

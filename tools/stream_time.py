@@ -37,7 +37,7 @@ def run(reps=4, seek=True):
         out[name] = {"read_loop_msamples_s": round(n / 2 / best / 1e6, 1), "read_loop_ms": round(best * 1e3, 2)}
         if seek:
             sbest, pos = None, 0
-            for _ in range(2):
+            for _ in range(3):
                 h = ad.Handle(lib, long_img)
                 t0 = time.perf_counter()
                 pos = h.seek(26_460_000 // 4)  # pcm frames: the middle of the stream
