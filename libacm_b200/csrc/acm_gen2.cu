@@ -85,6 +85,10 @@ __device__ __forceinline__ void load_tables(TablesSmem &s, const acm_tables *g, 
  */
 struct SmemScan {
 	TablesSmem tab;
+	/* the first table step of a prefix-coded column, indexed by the 13 stream bits selector + first
+	 * payload byte (the k8 entry of the selector's type; 0 for the other selectors): the step at a
+	 * selector takes the column's first symbols along, without a second dependent lookup */
+	uint32_t sel13[8192];
 	uint32_t ring[walk::RW + 1 + 4][walk::RROW]; /* acm_walk.cuh: [word][warp][lane] */
 };
 constexpr int G2_SCAN_PERIOD = 16; /* steps between two top-ups of the rings */
@@ -98,6 +102,11 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 	load_tables(tab, a.tables, tid, 32 * G2_SCAN_WARPS);
 	for (int i = tid; i < (walk::RW + 5) * walk::RROW; i += 32 * G2_SCAN_WARPS)
 		(&sm.ring[0][0])[i] = 0u;
+	__syncthreads();
+	for (int i = tid; i < 8192; i += 32 * G2_SCAN_WARPS) {
+		const uint32_t kind = tab.kind[i & 31];
+		sm.sel13[i] = (kind & 7u) == ACM_CLS_K ? (uint32_t)tab.k8[(kind >> 3) * 256u + ((uint32_t)i >> 5)] : 0u;
+	}
 	__syncthreads();
 	/* the lane's stream bits come from its shared-memory ring, topped up for all lanes together with
 	 * 16-byte loads well ahead of the position (acm_walk.cuh): a warp-wide load straight from global
@@ -160,7 +169,8 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			const bool act = have && mode >= M_SEL;
 			const bool in_k = mode == M_K;
 			const uint32_t ind = w & 31u, kind = tab.kind[ind], cls = kind & 7u, sub = kind >> 3;
-			const uint32_t e = reinterpret_cast<const uint32_t *>(tab.k8)[2u * (ktab + (w & 255u))];
+			const uint32_t e_k = reinterpret_cast<const uint32_t *>(tab.k8)[2u * (ktab + (w & 255u))];
+			const uint32_t e_s = sm.sel13[w & 0x1FFFu];
 			{
 				/* column c's selector position (fill_block's "ind = get_bits(5)", decode.c:496); the
 				 * offsets of a stream's blocks are one array: a running pointer */
@@ -172,19 +182,23 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			tb = sub == 1u ? t27_bits : tb;
 			tb = sub == 2u ? t37_bits : tb;
 			const uint32_t adv_sel = 5u + (cls == ACM_CLS_LINEAR ? rows * ind : 0u) + (cls == ACM_CLS_T ? tb : 0u);
-			/* prefix codes: whole symbols of the next 8 bits, up to the rows that remain */
-			const uint32_t k = umin32(e & 15u, rem);
+			/* prefix codes: whole symbols of the next 8 bits, up to the rows that remain -- inside a column
+			 * from its type's table, at a selector (the column's first step) from the 13-bit table */
+			const uint32_t e = in_k ? e_k : e_s;
+			const uint32_t rem_in = in_k ? rem : rows;
+			const uint32_t k = umin32(e & 15u, rem_in);
 			const uint32_t adv_k = (e >> (4u * k)) & 15u;
-			const bool enter_k = !in_k && cls == ACM_CLS_K;
-			const uint32_t nrem = in_k ? rem - k : rows;
-			const bool col_done = in_k ? nrem == 0u : !enter_k;
+			const bool is_k = in_k || cls == ACM_CLS_K;
+			const uint32_t nrem = rem_in - k;
+			const bool enter_k = !in_k && cls == ACM_CLS_K && nrem != 0u;
+			const bool col_done = is_k ? nrem == 0u : true;
 			const bool bad = act && !in_k && cls == ACM_CLS_BAD;
-			P += act ? (in_k ? adv_k : adv_sel) : 0u;
+			P += act ? (in_k ? adv_k : adv_sel + (is_k ? adv_k : 0u)) : 0u;
 			c += (act && col_done) ? 1u : 0u;
 			cp += (act && col_done) ? 1 : 0;
 			mode = act ? ((enter_k || (in_k && nrem != 0u)) ? M_K : M_SEL) : mode;
 			ktab = (act && enter_k) ? sub * 256u : ktab;
-			rem = act ? nrem : rem;
+			rem = (act && is_k) ? nrem : rem;
 			const bool endblk = act && mode == M_SEL && c == cols;
 			/* ---- the rare step: block header, end of a block, bad selector */
 			if (hdr || endblk || bad) {
