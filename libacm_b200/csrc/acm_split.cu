@@ -304,13 +304,27 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr)
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
+/* the hand-over words between the walker and the stagers (wpos, fill, quit): shared-memory atomics,
+ * ordered by __threadfence_block() on both sides (racecheck understands atomics, not flag words) */
 __device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr)
+{
+	uint32_t v;
+	asm volatile("atom.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
+{
+	uint32_t old;
+	asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+}
+/* plain volatile accesses: the stagers' own broadcast words, ordered by their barrier */
+__device__ __forceinline__ uint32_t lds32_plain(uint32_t addr)
 {
 	uint32_t v;
 	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
 	return v;
 }
-__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v)
+__device__ __forceinline__ void sts32_plain(uint32_t addr, uint32_t v)
 {
 	asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -385,12 +399,12 @@ __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, 
 		uint32_t fill = (P0 >> 5) & ~3u;
 		for (;;) {
 			if (st == 0) {
-				sts32_volatile(A_TARGET, (lds32_volatile(A_WPOS) & ~3u) + W1_RING);
-				sts32_volatile(A_SQUIT, lds32_volatile(A_QUIT));
+				sts32_plain(A_TARGET, (lds32_volatile(A_WPOS) & ~3u) + W1_RING);
+				sts32_plain(A_SQUIT, lds32_volatile(A_QUIT));
 			}
 			asm volatile("bar.sync 1, %0;" ::"n"(W1_STAGERS) : "memory");
-			const uint32_t target = lds32_volatile(A_TARGET);
-			if (lds32_volatile(A_SQUIT))
+			const uint32_t target = lds32_plain(A_TARGET);
+			if (lds32_plain(A_SQUIT))
 				break;
 			uint32_t n = (target - fill) >> 2;
 			n = n < (uint32_t)W1_STAGERS ? n : (uint32_t)W1_STAGERS;
@@ -423,7 +437,7 @@ __global__ void __launch_bounds__(W1_THREADS, 1) acm_walk1_kernel(KernelArgs a, 
 				sts32_volatile(A_FILL, fill);
 			}
 			if (n == 0u)
-				__nanosleep(400);
+				__nanosleep(2000);
 		}
 		return;
 	}
