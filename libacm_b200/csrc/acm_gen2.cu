@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 	uint32_t t15_bits = 0, t27_bits = 0, t37_bits = 0;
 	uint64_t rec_base = 0, coff_base = 0;
 	uint32_t *cp = g.coff;
+	BlockRec *recp = g.rec;
 	BitReader br;
 	br.init(nullptr, 0);
 	for (;;) {
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 				rec_base = gs.rec_base;
 				coff_base = gs.coff_base;
 				cp = g.coff + coff_base;
+				recp = g.rec + rec_base;
 				br.init((const uint32_t *)(a.blob + d.base_off), d.file_end);
 				P = d.bit0;
 				b = 0;
@@ -165,7 +167,11 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			 * instruction stream for both states (two table loads side by side, selects, a predicated
 			 * store) -- with one warp per sub-partition every branch costs as much as four dependent
 			 * ALU instructions, and lanes in different states would take turns */
-			const bool hdr = have && mode == M_HDR;
+			/* a block header that can be read (pwr 4 bits, val 16: decode.c:588-589) is part of the common
+			 * step too; the one that cannot -- the stream is over -- is the rare step's */
+			const bool at_hdr = have && mode == M_HDR;
+			const bool hdr_ok = at_hdr && b < nmax && P + 20u <= limit;
+			const bool hdr = at_hdr && !hdr_ok;
 			const bool act = have && mode >= M_SEL;
 			const bool in_k = mode == M_K;
 			const uint32_t ind = w & 31u, kind = tab.kind[ind], cls = kind & 7u, sub = kind >> 3;
@@ -193,44 +199,44 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			const bool enter_k = !in_k && cls == ACM_CLS_K && nrem != 0u;
 			const bool col_done = is_k ? nrem == 0u : true;
 			const bool bad = act && !in_k && cls == ACM_CLS_BAD;
-			P += act ? (in_k ? adv_k : adv_sel + (is_k ? adv_k : 0u)) : 0u;
+			val = hdr_ok ? (w >> 4) & 0xFFFFu : val;
+			Pblk = hdr_ok ? P : Pblk;
+			c = hdr_ok ? 0u : c;
+			P += act ? (in_k ? adv_k : adv_sel + (is_k ? adv_k : 0u)) : hdr_ok ? 20u : 0u;
 			c += (act && col_done) ? 1u : 0u;
 			cp += (act && col_done) ? 1 : 0;
-			mode = act ? ((enter_k || (in_k && nrem != 0u)) ? M_K : M_SEL) : mode;
+			mode = act ? ((enter_k || (in_k && nrem != 0u)) ? M_K : M_SEL) : hdr_ok ? M_SEL : mode;
 			ktab = (act && enter_k) ? sub * 256u : ktab;
 			rem = (act && is_k) ? nrem : rem;
+			/* the end of a block that ends inside the stream: its record (two predicated 16-byte stores) */
 			const bool endblk = act && mode == M_SEL && c == cols;
-			/* ---- the rare step: block header, end of a block, bad selector */
-			if (hdr || endblk || bad) {
-				bool rewalk = bad;
+			const bool end_ok = endblk && !bad && P <= limit;
+			{
+				const uint32_t on = end_ok ? 1u : 0u;
+				asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %9, 0;\n\t"
+					     "@p st.global.v4.u32 [%0], {%1,%2,%3,%4};\n\t"
+					     "@p st.global.v4.u32 [%0+16], {%5,%6,%7,%8};\n\t}"
+					     ::"l"(recp), "r"(Pblk), "r"(P), "r"(val), "r"((uint32_t)SCAN_OK), "r"(cols), "r"(0u), "r"(0u), "r"(0u), "r"(on)
+					     : "memory");
+			}
+			b += end_ok ? 1u : 0u;
+			recp += end_ok ? 1 : 0;
+			mode = end_ok ? M_HDR : mode;
+			/* ---- the rare step: the stream is over (all blocks walked, or no header left to read), a bad
+			 * selector, a block that ends past the end of the stream */
+			if (hdr || bad || (endblk && !end_ok)) {
+				bool rewalk = !hdr;
 				if (hdr) {
 					if (b >= nmax) {
 						g.nscan[si] = b;
-						mode = M_NONE;
-					} else if (P + 20u > limit) {
+					} else {
 						/* pwr / val cannot be read: GET_BITS_EXPECT_EOF, decode.c:588-589 */
 						BlockRec r;
 						r.P = P; r.end = P; r.val = 0; r.status = SCAN_EOF; r.ncols = 0; r.pad0 = r.pad1 = r.pad2 = 0u;
 						g.rec[rec_base + b] = r;
 						g.nscan[si] = b + 1u;
-						mode = M_NONE;
-					} else {
-						val = (w >> 4) & 0xFFFFu;
-						Pblk = P;
-						P += 20u;
-						c = 0;
-						mode = M_SEL;
 					}
-				} else if (!bad) {
-					if (P <= limit) {
-						BlockRec r;
-						r.P = Pblk; r.end = P; r.val = (int32_t)val; r.status = SCAN_OK; r.ncols = cols; r.pad0 = r.pad1 = r.pad2 = 0u;
-						g.rec[rec_base + b] = r;
-						b++;
-						mode = M_HDR;
-					} else {
-						rewalk = true;
-					}
+					mode = M_NONE;
 				}
 				if (rewalk) {
 					/* the stream's last block: the reference's verdict */
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 						b++;
 						P = sc.end;
 						cp = g.coff + coff_base + (size_t)b * cols;
+						recp = g.rec + rec_base + b;
 						mode = M_HDR;
 					} else {
 						g.nscan[si] = b + 1u;
