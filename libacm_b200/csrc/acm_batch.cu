@@ -8,6 +8,7 @@
  * reference does per block runs on the device.
  */
 #include <algorithm>
+#include <chrono>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -1028,6 +1029,7 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 	const uint8_t *blob_dev = (const uint8_t *)b->blob;
 	uint8_t *out_dev = (uint8_t *)b->out;
 	const size_t ns = plan->seg.size();
+	const auto t_enter = std::chrono::steady_clock::now();
 	if (ws_reserve(w, b->blob_on_device ? 0 : ((b->blob_len + 15u) & ~(uint64_t)15u) + 64,
 		       b->out_on_device ? 0 : b->out_len + 64) < 0)
 		return ACM_ERR_OTHER;
@@ -1084,11 +1086,24 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 					    cudaMemcpyDeviceToHost, w.s_out));
 		}
 	}
-	for (size_t g = 0; g < ns; g++)
+	const bool trace = getenv("ACM_B200_TRACE") != nullptr;
+	if (trace)
+		fprintf(stderr, "[acm trace] queued %.2f ms after run_segments was entered\n",
+			std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
+	const auto t_q = std::chrono::steady_clock::now();
+	auto since = [&t_q]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_q).count(); };
+	for (size_t g = 0; g < ns; g++) {
 		CUR(cudaEventSynchronize(ev_k[g]));
+		if (trace)
+			fprintf(stderr, "[acm trace] segment %zu decoded %.2f ms after the last launch was queued\n", g, since());
+	}
 	if (acm_gpu_plan_fetch(plan, b->streams, w.s_in) < 0)
 		return ACM_ERR_OTHER;
+	if (trace)
+		fprintf(stderr, "[acm trace] results fetched %.2f ms\n", since());
 	CUR(cudaStreamSynchronize(w.s_out));
+	if (trace)
+		fprintf(stderr, "[acm trace] last copy-out done %.2f ms\n", since());
 	CUR(cudaGetLastError());
 	return ACM_OK;
 }
@@ -1100,6 +1115,7 @@ static int decode_batch_one_device(const acm_gpu_batch *b, const acm_gpu_opts *o
 	int err = ACM_ERR_OTHER, perr = 0, dev = 0;
 	bool need_probe = false, host_io, monotonic = true;
 	unsigned nseg = 1;
+	const auto t_call = std::chrono::steady_clock::now();
 
 	if (use_device(opts) < 0)
 		return ACM_ERR_OTHER;
@@ -1133,9 +1149,13 @@ static int decode_batch_one_device(const acm_gpu_batch *b, const acm_gpu_opts *o
 	{
 		std::lock_guard<std::mutex> lock(g_ws_mutex[dev]);
 		Workspace &w = g_ws[dev];
+		const auto t0 = std::chrono::steady_clock::now();
 		plan = plan_create(b->streams, b->n, opts, nseg, &w.arena, &perr);
 		if (!plan)
 			return perr ? perr : ACM_ERR_OTHER;
+		if (getenv("ACM_B200_TRACE"))
+			fprintf(stderr, "[acm trace] plan for %llu streams in %u segments built in %.2f ms\n", (unsigned long long)b->n, nseg,
+				std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 		err = run_segments(plan, b, w, ev_in, ev_k);
 		if (w.s_in) {
 			cudaStreamSynchronize(w.s_in);
@@ -1151,6 +1171,9 @@ static int decode_batch_one_device(const acm_gpu_batch *b, const acm_gpu_opts *o
 		if (e)
 			cudaEventDestroy(e);
 	acm_gpu_plan_destroy(plan);
+	if (getenv("ACM_B200_TRACE"))
+		fprintf(stderr, "[acm trace] call done %.2f ms after it was entered\n",
+			std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
 	return err;
 }
 
