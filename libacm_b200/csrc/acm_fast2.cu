@@ -81,7 +81,9 @@ constexpr int BLEN = COLS * ROWS;        /* 2048 */
 #define F2_RW 64
 #endif
 #ifndef F2_PERIOD
-#define F2_PERIOD 16
+#define F2_PERIOD 12   /* walk steps between two top-ups of the scan rings (measured, 1 B200, config 2 / config-4 shape:
+			* 8: 4.45 / 18.2 ms, 10: 4.49 / 18.2, 12: 4.22 / 18.15, 14: 4.49 / 19.4, 16: 4.33 / 19.4, 24: 4.46 / 19.7,
+			* 32: 4.64 / 20.2 -- lanes that outrun their ring wait for the next top-up) */
 #endif
 #ifndef F2_HYST
 #define F2_HYST 1      /* scan warp sleeps while every lane is at least RING_D/2 records ahead */
