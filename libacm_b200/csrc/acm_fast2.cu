@@ -85,6 +85,9 @@ constexpr int BLEN = COLS * ROWS;        /* 2048 */
 			* 8: 4.45 / 18.2 ms, 10: 4.49 / 18.2, 12: 4.22 / 18.15, 14: 4.49 / 19.4, 16: 4.33 / 19.4, 24: 4.46 / 19.7,
 			* 32: 4.64 / 20.2 -- lanes that outrun their ring wait for the next top-up) */
 #endif
+#ifndef F2_STEP_UNROLL
+#define F2_STEP_UNROLL 4
+#endif
 #ifndef F2_HYST
 #define F2_HYST 1      /* scan warp sleeps while every lane is at least RING_D/2 records ahead */
 #endif
@@ -118,6 +121,7 @@ constexpr int RROW = 32 * SW;            /* words per ring row: one word of ever
 constexpr int NHOLD = F2_NHOLD;          /* 16-byte chunks per lane and period that travel through registers */
 constexpr int LEAD = RW / 4 - 2;               /* 16-byte chunks requested ahead of the read position */
 constexpr int SCAN_PERIOD = F2_PERIOD;         /* walk steps between two top-ups */
+constexpr int STEP_UNROLL = F2_STEP_UNROLL;    /* ... unrolled by */
 constexpr int XPRE = 68;                 /* chunk -1: the previous block's last 64 X2 words (+4 pad) */
 constexpr int XWORDS = XPRE + BLEN + 4 * 32; /* transpose layout: 4 pad words per 64 */
 constexpr int STAGE_W = 1088;            /* 4352 bytes: a whole block (<= 4179 B) + alignment + read-ahead */
@@ -1347,7 +1351,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 				}
 			}
 			PROF_MARK(5); /* 5: top-up + header */
-#pragma unroll 4
+#pragma unroll STEP_UNROLL
 			for (int k = 0; k < SCAN_PERIOD; k++)
 				fast_step(s, cp, cpend, P - 1u, &sm.ring[0][0], lane4, ring.ready_p,
 					  reinterpret_cast<const unsigned char *>(sm.uni16));
