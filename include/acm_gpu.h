@@ -127,6 +127,12 @@ void acm_gpu_plan_split(const acm_gpu_plan *plan, uint64_t *n_fast, uint64_t *n_
  * the general throughput path (any rows, level <= 10: scan -> unpack -> tile lift), the block-at-a-time
  * backstop (level 11..15) } */
 void acm_gpu_plan_routes(const acm_gpu_plan *plan, uint64_t *out4);
+/* general path of a resident plan: its streams are sorted by expected walk time and cut into this many
+ * groups, each scanned / unpacked / transformed on a CUDA stream of its own, so that the short groups are
+ * decoded while the long ones are still being walked (1 = one group: small batches, levels above 10;
+ * the ACM_B200_GEN_GROUPS environment variable overrides the default of 8, ACM_B200_GEN_GROUP_MIN the
+ * batch size of 1024 streams from which a plan is grouped) */
+int acm_gpu_plan_gen_groups(const acm_gpu_plan *plan);
 /* average device time of the kernels of the last run on that plan, ms (CUDA events on cuda_stream) */
 float acm_gpu_plan_last_ms(acm_gpu_plan *plan);
 void acm_gpu_plan_destroy(acm_gpu_plan *plan);

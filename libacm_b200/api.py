@@ -75,6 +75,8 @@ def lib():
         L.acm_gpu_plan_split.restype = None
         L.acm_gpu_plan_routes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.acm_gpu_plan_routes.restype = None
+        L.acm_gpu_plan_gen_groups.argtypes = [C.c_void_p]
+        L.acm_gpu_plan_gen_groups.restype = C.c_int
         L.acm_gpu_plan_last_ms.argtypes = [C.c_void_p]
         L.acm_gpu_plan_last_ms.restype = C.c_float
         L.acm_gpu_plan_destroy.argtypes = [C.c_void_p]
@@ -184,6 +186,10 @@ class Plan:
         out = (C.c_uint64 * 4)()
         lib().acm_gpu_plan_routes(self._h, out)
         return tuple(int(v) for v in out)
+
+    def gen_groups(self) -> int:
+        """Stream groups of the general path, each on its own CUDA stream (acm_gpu_plan_gen_groups)."""
+        return int(lib().acm_gpu_plan_gen_groups(self._h))
 
     def last_ms(self) -> float:
         return lib().acm_gpu_plan_last_ms(self._h)

@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -190,6 +191,25 @@ struct Segment {
 	uint64_t sp_block0, sp_blocks;    /* and of the per-block arrays */
 };
 
+/*
+ * Groups of the general path (single-segment plans: the resident path).  The scan is one serial walk
+ * per stream, so a launch over the whole batch lasts as long as its longest walk while most lanes
+ * have long since finished; unpack and lift are throughput kernels that only need the records of their
+ * own streams.  The streams are therefore sorted by expected walk time and cut into groups, each on a
+ * CUDA stream of its own: the short groups are unpacked and transformed while the long ones are still
+ * being walked.  A group is a contiguous slice of the segment's streams, work items and tiles; its
+ * items number streams from the group's first.
+ */
+struct GenGroup {
+	uint64_t k0, n;                  /* streams [k0, k0 + n) of the segment's general streams */
+	uint64_t item_first, n_items;
+	uint64_t tile_first, n_tiles;
+};
+constexpr unsigned GEN_GROUPS_MAX = 8;
+/* counters: per segment 4 queue words + 4 general-path words, 4 shared words, and the general-path words
+ * of the groups after the first */
+static inline size_t counter_words(size_t nseg) { return 8 * nseg + 4 + 4 * (GEN_GROUPS_MAX - 1); }
+
 struct acm_gpu_plan {
 	int device;
 	uint64_t n;          /* caller's stream count */
@@ -224,6 +244,9 @@ struct acm_gpu_plan {
 	int sm_count;
 	cudaEvent_t ev0, ev1;
 	bool timed;
+	std::vector<GenGroup> grp;                 /* more than one entry: see GenGroup */
+	cudaStream_t grp_st[GEN_GROUPS_MAX] = {};  /* group j > 0 runs on grp_st[j] */
+	cudaEvent_t grp_ev[GEN_GROUPS_MAX] = {};   /* [0]: fork, [j]: group j done */
 };
 
 static void plan_free(acm_gpu_plan *p)
@@ -231,6 +254,12 @@ static void plan_free(acm_gpu_plan *p)
 	if (!p)
 		return;
 	cudaFree(p->d_pool); /* null when the plan lives in a caller's arena */
+	for (unsigned j = 0; j < GEN_GROUPS_MAX; j++) {
+		if (p->grp_st[j])
+			cudaStreamDestroy(p->grp_st[j]);
+		if (p->grp_ev[j])
+			cudaEventDestroy(p->grp_ev[j]);
+	}
 	if (p->ev0)
 		cudaEventDestroy(p->ev0);
 	if (p->ev1)
@@ -449,14 +478,18 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 				std::copy(dealt.begin(), dealt.end(), fast.begin());
 			}
 		}
-		auto by_work = [](const DevStream &a, const DevStream &b) {
-			uint64_t wa = (uint64_t)a.n_attempt * (a.rows << a.level);
-			uint64_t wb = (uint64_t)b.n_attempt * (b.rows << b.level);
+		/* general path: longest WALK first.  Expected walk steps of a block: one selector step per
+		 * column plus, for a prefix-coded column (8 of the 28 valid selectors), a table step per ~4 rows:
+		 * cols * (1 + rows / 14) */
+		auto walk_cost = [](const DevStream &d) { return (uint64_t)d.n_attempt * ((uint64_t)(14u + d.rows) << d.level); };
+		auto by_walk = [&walk_cost](const DevStream &a, const DevStream &b) {
+			const uint64_t wa = walk_cost(a), wb = walk_cost(b);
 			if (wa != wb)
 				return wa > wb;
 			return a.index < b.index;
 		};
-		std::sort(gen.begin(), gen.end(), by_work);
+		std::sort(gen.begin(), gen.end(), by_walk);
+		std::vector<uint64_t> item_at, tile_at; /* first work item / tile of every general stream */
 		std::sort(spl.begin(), spl.end(), by_len);
 		sg.fast_first = all.size();
 		sg.n_fast = fast.size();
@@ -515,6 +548,8 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			Gen2Stream gs;
 			memset(&gs, 0, sizeof(gs));
 			const uint32_t cols = 1u << d.level, blen = d.rows << d.level;
+			item_at.push_back(g2_items.size());
+			tile_at.push_back(g3_tiles.size());
 			gs.rec_base = g2_blocks;
 			gs.coff_base = g2_coffs;
 			gs.max_blocks = (uint32_t)gen2_max_blocks(d.n_attempt, d.file_end > d.bit0 ? d.file_end - d.bit0 : 0, d.level);
@@ -550,6 +585,41 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		}
 		sg.n_items = g2_items.size() - sg.item_first;
 		sg.n_tiles = g3_tiles.size() - sg.tile_first;
+		item_at.push_back(g2_items.size());
+		tile_at.push_back(g3_tiles.size());
+		size_t group_min = 1024;
+		if (const char *e = getenv("ACM_B200_GEN_GROUP_MIN"))
+			group_min = (size_t)atol(e);
+		if (nseg == 1 && sg.n_deep == 0 && !gen.empty() && gen.size() >= group_min) {
+			/* groups (GenGroup): equal slices of the longest stream's expected walk time */
+			unsigned ng = 8;
+			if (const char *e = getenv("ACM_B200_GEN_GROUPS"))
+				ng = (unsigned)atoi(e);
+			ng = ng < 1 ? 1 : ng > GEN_GROUPS_MAX ? GEN_GROUPS_MAX : ng;
+			const uint64_t c0 = walk_cost(gen[0]);
+			size_t k = 0;
+			for (unsigned j = 0; j < ng && k < gen.size(); j++) {
+				const uint64_t lo = j + 1 == ng ? 0 : c0 / ng * (ng - 1 - j);
+				GenGroup gg;
+				gg.k0 = k;
+				while (k < gen.size() && (walk_cost(gen[k]) > lo || j + 1 == ng))
+					k++;
+				gg.n = k - gg.k0;
+				if (!gg.n)
+					continue;
+				gg.item_first = item_at[gg.k0];
+				gg.n_items = item_at[k] - gg.item_first;
+				gg.tile_first = tile_at[gg.k0];
+				gg.n_tiles = tile_at[k] - gg.tile_first;
+				for (uint64_t i = gg.item_first; i < gg.item_first + gg.n_items; i++)
+					g2_items[i].stream -= (uint32_t)gg.k0;
+				for (uint64_t i = gg.tile_first; i < gg.tile_first + gg.n_tiles; i++)
+					g3_tiles[i].stream -= (uint32_t)gg.k0;
+				p->grp.push_back(gg);
+			}
+			if (p->grp.size() < 2)
+				p->grp.clear(); /* one group: numbering unchanged (k0 = 0) */
+		}
 		p->n_fast += sg.n_fast;
 		p->n_generic += sg.n_gen;
 		max_fast = std::max(max_fast, sg.n_fast);
@@ -559,6 +629,11 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 
 	CU(cudaEventCreate(&p->ev0));
 	CU(cudaEventCreate(&p->ev1));
+	for (size_t j = 0; j < p->grp.size(); j++) {
+		CU(cudaEventCreateWithFlags(&p->grp_ev[j], cudaEventDisableTiming));
+		if (j)
+			CU(cudaStreamCreateWithFlags(&p->grp_st[j], cudaStreamNonBlocking));
+	}
 	{
 		/* ---- geometry of every segment, then ONE device allocation for the whole plan (or a
 		 * slice of the caller's arena: the host path of acm_gpu_decode_batch keeps one
@@ -602,7 +677,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		const size_t o_streams = carve((p->n_dev + 1) * sizeof(DevStream));
 		const size_t o_results = carve((n + 1) * 16); /* status (4) | words (4) | checksums (8) */
 		const size_t o_tables = carve(sizeof(acm_tables));
-		const size_t o_counters = carve((8 * p->seg.size() + 4) * sizeof(uint32_t));
+		const size_t o_counters = carve(counter_words(p->seg.size()) * sizeof(uint32_t));
 		const size_t o_prof = carve(64 * sizeof(unsigned long long));
 		const size_t o_ctl = carve(ctl_bytes);
 		const size_t o_hist = carve(hist_words * 4 + 16);
@@ -800,7 +875,36 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 		g2.n_tiles = (uint32_t)sg.n_tiles;
 		g2.n_deep = sg.n_deep;
 		g2.g3_counters = p->d_counters + 4 * p->seg.size() + 4 + 4 * g;
-		CU(launch_gen2(a, g2, sc, sg.gen_ctas, st));
+		if (p->grp.size() > 1) {
+			/* one CUDA stream per group, forked from and joined to st (GenGroup) */
+			const Gen2Args all = g2;
+			const DevStream *const streams = a.streams;
+			CU(cudaEventRecord(p->grp_ev[0], st));
+			for (size_t j = 0; j < p->grp.size(); j++) {
+				const GenGroup &gg = p->grp[j];
+				cudaStream_t gst = j ? p->grp_st[j] : st;
+				if (j)
+					CU(cudaStreamWaitEvent(gst, p->grp_ev[0], 0));
+				a.streams = streams + gg.k0;
+				a.count = (uint32_t)gg.n;
+				g2 = all;
+				g2.gs += gg.k0;
+				g2.nscan += gg.k0;
+				g2.first_bad += gg.k0;
+				g2.items = all.items + gg.item_first;
+				g2.n_items = (uint32_t)gg.n_items;
+				g2.tiles = all.tiles + gg.tile_first;
+				g2.n_tiles = (uint32_t)gg.n_tiles;
+				g2.g3_counters = all.g3_counters + 4 * j;
+				CU(launch_gen2(a, g2, sc, sg.gen_ctas, gst));
+				if (j)
+					CU(cudaEventRecord(p->grp_ev[j], gst));
+			}
+			for (size_t j = 1; j < p->grp.size(); j++)
+				CU(cudaStreamWaitEvent(st, p->grp_ev[j], 0));
+		} else {
+			CU(launch_gen2(a, g2, sc, sg.gen_ctas, st));
+		}
 	}
 	return ACM_OK;
 fail:
@@ -816,7 +920,7 @@ extern "C" int acm_gpu_plan_run(acm_gpu_plan *p, const void *d_blob, void *d_out
 		return ACM_ERR_OTHER;
 	}
 	CU(cudaSetDevice(p->device));
-	CU(cudaMemsetAsync(p->d_counters, 0, (8 * p->seg.size() + 4) * sizeof(uint32_t), st));
+	CU(cudaMemsetAsync(p->d_counters, 0, counter_words(p->seg.size()) * sizeof(uint32_t), st));
 	if (p->d_ctl)
 		CU(cudaMemsetAsync(p->d_ctl, 0, p->ctl_bytes, st));
 	if (p->n_generic) {
@@ -894,6 +998,11 @@ extern "C" void acm_gpu_plan_routes(const acm_gpu_plan *p, uint64_t *out4)
 	out4[1] = p->n_split;
 	out4[2] = p->n_generic - deep;
 	out4[3] = deep;
+}
+
+extern "C" int acm_gpu_plan_gen_groups(const acm_gpu_plan *p)
+{
+	return p->grp.empty() ? 1 : (int)p->grp.size();
 }
 
 extern "C" void acm_gpu_plan_split(const acm_gpu_plan *p, uint64_t *n_fast, uint64_t *n_generic)
@@ -1048,7 +1157,7 @@ static int run_segments(acm_gpu_plan *plan, const acm_gpu_batch *b, Workspace &w
 		CUR(cudaEventCreateWithFlags(&ev_k[g], cudaEventDisableTiming));
 	}
 	/* the cursors are zeroed before anything else is queued: the copy-in stream waits for it */
-	CUR(cudaMemsetAsync(plan->d_counters, 0, (8 * ns + 4) * sizeof(uint32_t), w.s_in));
+	CUR(cudaMemsetAsync(plan->d_counters, 0, counter_words(ns) * sizeof(uint32_t), w.s_in));
 	if (plan->d_ctl)
 		CUR(cudaMemsetAsync(plan->d_ctl, 0, plan->ctl_bytes, w.s_in));
 	if (plan->n_generic) {

@@ -390,3 +390,43 @@ def test_levels_11_and_12_take_the_backstop(checker):
     assert gu.compare(imgs, s, out, checker, checksums=True) == []
     s, out = gu.decode_device(imgs, bigendianp=1, sgned=0)
     assert gu.compare(imgs, s, out, checker, be=1, sgned=0) == []
+
+
+def test_general_path_stream_groups(checker, monkeypatch):
+    """A resident plan over many general-path streams walks them in groups on CUDA streams of their own
+    (acm_gpu_plan_gen_groups): same PCM, statuses, word counts and checksums as the reference, with healthy,
+    truncated and corrupt streams of every shape spread over the groups, run twice on the same plan."""
+    import torch
+    monkeypatch.setenv("ACM_B200_GEN_GROUP_MIN", "64")
+    rng = np.random.default_rng(77)
+    plist = []
+    for k in range(420):
+        level, rows = int(rng.integers(0, 10)), int(rng.choice([1, 2, 3, 4, 7, 8, 16, 32]))
+        blen = rows << level
+        tv = int(rng.integers(blen + 1, max(blen * 2, 24_000)))
+        plist.append(gen.params(level=level, rows=rows, channels=1 + k % 2, total_values=tv, wavc=k % 3 == 0,
+                                dist=gen.DIST_STRESS, seed=31_000 + k))
+    imgs = corpus.images(plist + corpus.negative_params())
+    imgs += [img[:len(img) * (3 + k % 5) // 9] for k, img in enumerate(imgs[:60])]   # truncated copies
+    order = rng.permutation(len(imgs))
+    imgs = [imgs[i] for i in order]
+    blob, offs, lens = gu.pack(imgs, align=1, lead=3)
+    for groups in ("8", "3", "1"):
+        monkeypatch.setenv("ACM_B200_GEN_GROUPS", groups)
+        opts = api.make_opts(want_checksums=1)
+        d_blob = torch.from_numpy(blob).cuda()
+        s = api.new_streams(offs, lens)
+        api.probe(d_blob, s, opts)
+        nbytes = api.layout(s, opts.wordlen)
+        plan = api.Plan(s, opts)
+        fused, split, general, backstop = plan.routes()
+        assert fused == 0 and split == 0 and backstop == 0 and general > 400
+        assert (plan.gen_groups() == 1) if groups == "1" else (2 <= plan.gen_groups() <= int(groups))
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):
+            d_out = torch.full((nbytes + 16,), 0xAA, dtype=torch.uint8, device="cuda")
+            plan.run(d_blob, d_out, st)
+            plan.fetch(s, st)
+            assert gu.compare(imgs, s, d_out.cpu().numpy(), checker, checksums=True) == []
+        plan.close()
+    assert {0, -6} <= set(s["status"].tolist())

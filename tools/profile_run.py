@@ -54,3 +54,6 @@ if os.environ.get("F2_PROF"):
     print("work  phases Mcycles/run: record %.1f stage-wait %.1f unpack %.1f copy+dequant %.1f transform %.1f rest %.1f" % tuple(v[24:30]))
 plan.fetch(s, cs)
 assert np.all(s["status"] == 0)
+# digest of the PCM (int64 wrap-around sum of the output's 8-byte words) and of the word counts: equal across variants
+n8 = nbytes // 8
+print("groups", plan.gen_groups(), "words", int(s["words"].sum()), "digest", int(d_out[:n8 * 8].view(torch.int64).sum().item()))
