@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 	ring.safe = a.blob;
 	ring.hold_c0 = 0u;
 	ring.idle();
-	enum { M_NONE = 0, M_HDR = 1, M_SEL = 2, M_K = 3 };
+	/* M_OVER / M_REWALK: the lane has reached the rare end of its walk and waits (at most a period) for the
+	 * one place that deals with it, outside the unrolled steps */
+	enum { M_NONE = 0, M_HDR = 1, M_SEL = 2, M_K = 3, M_OVER = 4, M_REWALK = 5 };
 	int mode = M_NONE;
 	bool exhausted = false;
 	uint32_t si = 0, cols = 0, rows = 0, limit = 0, nmax = 0, P = 0, Pblk = 0, b = 0, c = 0, rem = 0, ktab = 0, val = 0;
@@ -129,6 +131,42 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 	BitReader br;
 	br.init(nullptr, 0);
 	for (;;) {
+		/* ---- the rare end of a walk: the stream is over (all blocks walked, or no header left to read), a
+		 * bad selector, a block that ends past the end of the stream.  Kept out of the steps below: four
+		 * inlined copies of scan_block between them cost a branch per step and most of the instruction cache */
+		if (mode >= M_OVER) {
+			if (mode == M_OVER) {
+				if (b >= nmax) {
+					g.nscan[si] = b;
+				} else {
+					/* pwr / val cannot be read: GET_BITS_EXPECT_EOF, decode.c:588-589 */
+					BlockRec r;
+					r.P = P; r.end = P; r.val = 0; r.status = SCAN_EOF; r.ncols = 0; r.pad0 = r.pad1 = r.pad2 = 0u;
+					g.rec[rec_base + b] = r;
+					g.nscan[si] = b + 1u;
+				}
+				mode = M_NONE;
+			} else {
+				/* the stream's last block: the reference's verdict */
+				const ScanResult sc = scan_block(br, Pblk, limit, cols, rows, g.coff + coff_base + (size_t)b * cols, 0u, tab.kind, tab.k8);
+				BlockRec r;
+				r.P = Pblk; r.end = sc.end; r.val = sc.val; r.status = sc.status; r.ncols = sc.ncols; r.pad0 = r.pad1 = r.pad2 = 0u;
+				g.rec[rec_base + b] = r;
+				if (sc.status == SCAN_OK) {
+					/* cannot happen (the walk found the block's end past the limit, or a bad selector) */
+					b++;
+					P = sc.end;
+					cp = g.coff + coff_base + (size_t)b * cols;
+					recp = g.rec + rec_base + b;
+					mode = M_HDR;
+				} else {
+					g.nscan[si] = b + 1u;
+					mode = M_NONE;
+				}
+			}
+			if (mode == M_NONE)
+				ring.idle();
+		}
 		if (mode == M_NONE && !exhausted) {
 			const uint32_t idx = atomicAdd(g.g3_counters + 2, 1u);
 			if (idx < a.count) {
@@ -159,21 +197,26 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			break;
 #pragma unroll 4
 		for (int step = 0; step < G2_SCAN_PERIOD; step++) {
-			/* a lane whose bits have not landed yet does nothing this step */
-			const bool have = mode != M_NONE && P <= ring.ready_p;
+			/* a lane whose bits have not landed yet does nothing this step, nor does one that waits for
+			 * the rare path */
+			const bool have = (uint32_t)(mode - M_HDR) <= (uint32_t)(M_K - M_HDR) && P <= ring.ready_p;
 			const uint32_t *rp = walk::ring_word(&sm.ring[0][0], lane4, P << 5);
 			const uint32_t w = walk::fsr(rp[0], rp[walk::RROW], P);
 			/* ---- the common step, at a selector or inside a prefix-coded column: ONE straight-line
 			 * instruction stream for both states (two table loads side by side, selects, a predicated
 			 * store) -- with one warp per sub-partition every branch costs as much as four dependent
-			 * ALU instructions, and lanes in different states would take turns */
+			 * ALU instructions, and lanes in different states would take turns.  What depends on "this
+			 * lane takes part" is applied through masks the compiler cannot see through (it otherwise
+			 * wraps the advance's arithmetic -- the head of the dependent chain -- in a branch) */
 			/* a block header that can be read (pwr 4 bits, val 16: decode.c:588-589) is part of the common
-			 * step too; the one that cannot -- the stream is over -- is the rare step's */
+			 * step too; the one that cannot -- the stream is over -- is the rare path's */
 			const bool at_hdr = have && mode == M_HDR;
 			const bool hdr_ok = at_hdr && b < nmax && P + 20u <= limit;
 			const bool hdr = at_hdr && !hdr_ok;
 			const bool act = have && mode >= M_SEL;
 			const bool in_k = mode == M_K;
+			uint32_t am = 0u - (uint32_t)act, hm = 0u - (uint32_t)hdr_ok;
+			asm volatile("" : "+r"(am), "+r"(hm));
 			const uint32_t ind = w & 31u, kind = tab.kind[ind], cls = kind & 7u, sub = kind >> 3;
 			const uint32_t e_k = reinterpret_cast<const uint32_t *>(tab.k8)[2u * (ktab + (w & 255u))];
 			const uint32_t e_s = sm.sel13[w & 0x1FFFu];
@@ -199,13 +242,16 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			const bool enter_k = !in_k && cls == ACM_CLS_K && nrem != 0u;
 			const bool col_done = is_k ? nrem == 0u : true;
 			const bool bad = act && !in_k && cls == ACM_CLS_BAD;
+			const uint32_t adv_col = in_k ? adv_k : adv_sel + (is_k ? adv_k : 0u);
+			const uint32_t next_mode = (enter_k || (in_k && nrem != 0u)) ? (uint32_t)M_K : (uint32_t)M_SEL;
+			const uint32_t cd = (uint32_t)col_done & am;
 			val = hdr_ok ? (w >> 4) & 0xFFFFu : val;
 			Pblk = hdr_ok ? P : Pblk;
 			c = hdr_ok ? 0u : c;
-			P += act ? (in_k ? adv_k : adv_sel + (is_k ? adv_k : 0u)) : hdr_ok ? 20u : 0u;
-			c += (act && col_done) ? 1u : 0u;
-			cp += (act && col_done) ? 1 : 0;
-			mode = act ? ((enter_k || (in_k && nrem != 0u)) ? M_K : M_SEL) : hdr_ok ? M_SEL : mode;
+			P += (adv_col & am) | (20u & hm);
+			c += cd;
+			cp += cd;
+			mode = (int)((next_mode & am) | ((uint32_t)M_SEL & hm) | ((uint32_t)mode & ~(am | hm)));
 			ktab = (act && enter_k) ? sub * 256u : ktab;
 			rem = (act && is_k) ? nrem : rem;
 			/* the end of a block that ends inside the stream: its record (two predicated 16-byte stores) */
@@ -222,43 +268,8 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			b += end_ok ? 1u : 0u;
 			recp += end_ok ? 1 : 0;
 			mode = end_ok ? M_HDR : mode;
-			/* ---- the rare step: the stream is over (all blocks walked, or no header left to read), a bad
-			 * selector, a block that ends past the end of the stream */
-			if (hdr || bad || (endblk && !end_ok)) {
-				bool rewalk = !hdr;
-				if (hdr) {
-					if (b >= nmax) {
-						g.nscan[si] = b;
-					} else {
-						/* pwr / val cannot be read: GET_BITS_EXPECT_EOF, decode.c:588-589 */
-						BlockRec r;
-						r.P = P; r.end = P; r.val = 0; r.status = SCAN_EOF; r.ncols = 0; r.pad0 = r.pad1 = r.pad2 = 0u;
-						g.rec[rec_base + b] = r;
-						g.nscan[si] = b + 1u;
-					}
-					mode = M_NONE;
-				}
-				if (rewalk) {
-					/* the stream's last block: the reference's verdict */
-					const ScanResult sc = scan_block(br, Pblk, limit, cols, rows, g.coff + coff_base + (size_t)b * cols, 0u, tab.kind, tab.k8);
-					BlockRec r;
-					r.P = Pblk; r.end = sc.end; r.val = sc.val; r.status = sc.status; r.ncols = sc.ncols; r.pad0 = r.pad1 = r.pad2 = 0u;
-					g.rec[rec_base + b] = r;
-					if (sc.status == SCAN_OK) {
-						/* cannot happen (the walk above found the block's end past the limit, or a bad selector) */
-						b++;
-						P = sc.end;
-						cp = g.coff + coff_base + (size_t)b * cols;
-						recp = g.rec + rec_base + b;
-						mode = M_HDR;
-					} else {
-						g.nscan[si] = b + 1u;
-						mode = M_NONE;
-					}
-				}
-				if (mode == M_NONE)
-					ring.idle();
-			}
+			/* the rare end of the walk: the lane stops here and is dealt with at the top of the loop */
+			mode = hdr ? M_OVER : (bad || (endblk && !end_ok)) ? M_REWALK : mode;
 		}
 		ring.topup(P);
 	}
