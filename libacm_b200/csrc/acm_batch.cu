@@ -12,6 +12,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -471,7 +472,32 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			sg.walk_bound = fast2_walk_bound(fast[0].n_attempt, blocks, sm_count, max_ctas);
 			fast2_geometry(fast.size(), sm_count, max_ctas, &n_scan, &n_work, &n_slots, sg.walk_bound);
 			const size_t head = std::min<size_t>(n_slots, fast.size()) / 32 * 32, warps = head / 32;
-			if (warps > 1) {
+			int deal = sg.walk_bound ? 1 : 0;
+			if (const char *e = getenv("ACM_B200_DEAL"))
+				deal = atoi(e);
+			if (warps > 1 && deal == 1) {
+				/* A walk-bound launch (few, long streams): what counts is when the longest walks end, and
+				 * a scan warp that has its SM sub-partition to itself steps about a third faster than one
+				 * that shares it (the scan SMs are bound by instruction issue).  Slot g is lane g % 32 of
+				 * warp (g / 32) % SW of scan CTA g / SLOTS, and warps w and w + SW / 2 of a CTA share a
+				 * sub-partition: the lower warp of every pair gets 32 of the longest streams, its partner 32
+				 * of the shortest -- the longest of all are paired with the shortest of all -- so that the
+				 * partner is done, and gone, when the long walks have most of their way still to go. */
+				const size_t sw = (size_t)fast2_scan_warps(), half = sw / 2;
+				std::vector<size_t> wa, wb; /* warp numbers of the lower / upper halves, in pair order */
+				for (size_t w = 0; w < warps; w++)
+					((w % sw) < half ? wa : wb).push_back(w);
+				std::vector<DevStream> dealt(head);
+				size_t r = 0;
+				for (size_t j = 0; j < wa.size(); j++, r += 32)
+					std::copy(fast.begin() + r, fast.begin() + r + 32, dealt.begin() + wa[j] * 32);
+				/* what is left, shortest first, to the partners in the same pair order */
+				for (size_t j = 0; j < wb.size(); j++) {
+					const size_t from = head - 32 * (j + 1);
+					std::copy(fast.begin() + from, fast.begin() + from + 32, dealt.begin() + wb[j] * 32);
+				}
+				std::copy(dealt.begin(), dealt.end(), fast.begin());
+			} else if (warps > 1) {
 				std::vector<DevStream> dealt(head);
 				for (size_t r = 0; r < head; r++)
 					dealt[(r % warps) * 32 + r / warps] = fast[r];
@@ -480,8 +506,14 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 		}
 		/* general path: longest WALK first.  Expected walk steps of a block: one selector step per
 		 * column plus, for a prefix-coded column (8 of the 28 valid selectors), a table step per ~4 rows:
-		 * cols * (1 + rows / 14) */
-		auto walk_cost = [](const DevStream &d) { return (uint64_t)d.n_attempt * ((uint64_t)(14u + d.rows) << d.level); };
+		 * cols * (1 + rows / 14)
+		 * -- or, for a stream of long columns (f_linear of many rows), what its ring can take in: 1024 bits
+		 * per top-up period of 16 steps (acm_walk.cuh).  In units of 1 / (14 * 64) step */
+		auto walk_cost = [](const DevStream &d) {
+			const uint64_t steps = (uint64_t)d.n_attempt * ((uint64_t)(14u + d.rows) << d.level) * 64u;
+			const uint64_t bits = d.file_end > d.bit0 ? (uint64_t)(d.file_end - d.bit0) * 14u : 0u;
+			return steps > bits ? steps : bits;
+		};
 		auto by_walk = [&walk_cost](const DevStream &a, const DevStream &b) {
 			const uint64_t wa = walk_cost(a), wb = walk_cost(b);
 			if (wa != wb)
@@ -599,7 +631,9 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			const uint64_t c0 = walk_cost(gen[0]);
 			size_t k = 0;
 			for (unsigned j = 0; j < ng && k < gen.size(); j++) {
-				const uint64_t lo = j + 1 == ng ? 0 : c0 / ng * (ng - 1 - j);
+				/* group j ends at (1 - (j + 1) / ng) ^ 0.8 of the longest walk: the first group, whose
+				 * unpack and lift nothing overlaps, is the thinnest slice */
+				const uint64_t lo = j + 1 == ng ? 0 : (uint64_t)((double)c0 * pow(1.0 - (double)(j + 1) / ng, 0.8) * (1.0 - 0.4 / ng));
 				GenGroup gg;
 				gg.k0 = k;
 				while (k < gen.size() && (walk_cost(gen[k]) > lo || j + 1 == ng))

@@ -58,6 +58,7 @@
  * Bit-exactness: same arithmetic as the generic kernel (uint32 wrap-around, arithmetic shift,
  * truncation), same table-driven symbol decode, same status rules.
  */
+#include <cstdlib>
 #include "acm_fast2_core.cuh"
 #include "acm_kernels.cuh"
 
@@ -1223,7 +1224,7 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 	ring.saddr = (uint32_t)__cvta_generic_to_shared(ring.rw);
 	ring.pol = l2_keep_policy();
 	ring.idle();
-	bool active = false, exhausted = !enabled;
+	bool active = false, exhausted = !enabled, first = true;
 	uint32_t cur = 0, P = 0, blk = 0, limit = 0, n_attempt = 0, prodn = 0;
 	unsigned long long waiting_since = 0ull;
 	uint32_t seen_hb = 0, wait_ns = 250u;
@@ -1249,7 +1250,11 @@ __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int 
 			P = 0;
 		}
 		if (!active && !exhausted) {
-			const uint32_t idx = atomicAdd(a.counter, 1u);
+			/* a slot's first stream is queue entry g (the host decides which streams share a warp and
+			 * which warps share a sub-partition: plan_create); the rest of the queue goes to whoever is
+			 * free first */
+			const uint32_t idx = first ? g : a.n_slots + atomicAdd(a.counter, 1u);
+			first = false;
 			if (idx < a.count) {
 				const DevStream d = a.streams[idx];
 				cur = idx;
@@ -1615,7 +1620,10 @@ void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uin
 #ifndef F2_SCAN_PCT_WALK
 #define F2_SCAN_PCT_WALK 28
 #endif
-	uint32_t cap_scan = (uint32_t)((total * (walk_bound ? F2_SCAN_PCT_WALK : F2_SCAN_PCT) + 50) / 100);
+	int pct_walk = F2_SCAN_PCT_WALK;
+	if (const char *e = getenv("ACM_B200_SCAN_PCT_WALK")) /* tuning */
+		pct_walk = atoi(e);
+	uint32_t cap_scan = (uint32_t)((total * (walk_bound ? pct_walk : F2_SCAN_PCT) + 50) / 100);
 	if (cap_scan < 1)
 		cap_scan = 1;
 	uint32_t ns = want_scan < cap_scan ? (uint32_t)want_scan : cap_scan;
@@ -1654,6 +1662,8 @@ int fast2_walk_bound(uint64_t longest_blocks, uint64_t total_blocks, int sms, in
 }
 
 size_t fast2_hist_words_per_slot() { return fast2::HIST_WORDS; }
+
+int fast2_scan_warps() { return fast2::SW; }
 
 size_t fast2_ring_bytes_per_slot() { return (size_t)fast2::RING_D * fast2::REC_BYTES; }
 

@@ -143,6 +143,7 @@ void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uin
 		    int walk_bound);
 int fast2_walk_bound(uint64_t longest_blocks, uint64_t total_blocks, int sms, int max_ctas);
 size_t fast2_hist_words_per_slot();
+int fast2_scan_warps(); /* scan warps per scan CTA: warps w and w + half of them share an SM sub-partition */
 size_t fast2_ring_bytes_per_slot();
 size_t fast2_ctl_bytes_per_slot();
 cudaError_t launch_fast2(const KernelArgs &a, int n_ctas, cudaStream_t st);

@@ -1,4 +1,12 @@
-set -x
-timeout 900 python -m pytest tests/test_gpu_batch.py -x -q -m gpu -k "2 or kernel" 2>&1 | tail -5
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:"acm_walk|acm_unpack|acm_lift" python tools/profile_run.py --streams 10000 --runs 1 --kernel 2 2>&1 | grep -E "gpu__time|inst_exec" | head -12
-ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -k regex:"acm_walk|acm_unpack|acm_lift" python tools/profile_run.py --streams 125000 --runs 1 --workload config4 --kernel 2 2>&1 | grep -E "gpu__time|inst_exec" | head -12
+# scan-warp pairing (ACM_B200_DEAL): parity of the fused kernel, config 2 and config-4 shape with both deals; config 3 with the refined walk proxy
+timeout 900 python -m pytest tests/test_gpu_batch.py -x -q -m gpu -k "fallout or config2_full or more_streams or truncations or fast_shape or unaligned or healthy" 2>&1 | tail -3
+for d in 0 1 0 1; do
+echo "== deal $d"
+ACM_B200_DEAL=$d timeout 300 python tools/profile_run.py --streams 10000 --runs 4 2>&1 | tail -3
+done
+for d in 0 1; do
+echo "== config-4 shape, deal $d"
+ACM_B200_DEAL=$d timeout 300 python tools/profile_run.py --streams 125000 --runs 3 --workload config4 2>&1 | tail -2
+done
+echo "== config 3"
+timeout 300 python tools/profile_run.py --streams 10000 --runs 3 --workload config3 2>&1 | tail -2

@@ -1,2 +1,4 @@
-set -x
-ncu --set full --clock-control none --import-source on -k regex:acm_walk -c 1 -o gpurun_out/prof_r02_split_walk_c2 -f python tools/profile_run.py --streams 10000 --runs 1 --kernel 2 2>&1 | tail -1
+for pct in 18 20 22 24 26 28; do
+echo "== pct $pct"
+ACM_B200_SCAN_PCT_WALK=$pct timeout 300 python tools/profile_run.py --streams 10000 --runs 4 2>&1 | tail -2 | head -1
+done
