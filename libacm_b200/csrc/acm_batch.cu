@@ -631,9 +631,12 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			const uint64_t c0 = walk_cost(gen[0]);
 			size_t k = 0;
 			for (unsigned j = 0; j < ng && k < gen.size(); j++) {
-				/* group j ends at (1 - (j + 1) / ng) ^ 0.8 of the longest walk: the first group, whose
-				 * unpack and lift nothing overlaps, is the thinnest slice */
-				const uint64_t lo = j + 1 == ng ? 0 : (uint64_t)((double)c0 * pow(1.0 - (double)(j + 1) / ng, 0.8) * (1.0 - 0.4 / ng));
+				/* group j ends at (1 - (j + 1) / ng) ^ 1.5 of the longest walk (measured on the filler-stress
+				 * corpus, 8 groups: exponent 0.6 27.0 ms, 0.8 24.8, 1.0 24.3, 1.3 - 2.0 24.0, 2.6 24.3; 5 groups
+				 * 25.0 - 25.9): the groups of short streams, whose unpack and lift run beside everybody
+				 * else's walk, are the thin ones */
+				static const double gpow = getenv("ACM_B200_GEN_GROUP_POW") ? atof(getenv("ACM_B200_GEN_GROUP_POW")) : 1.5; /* tuning */
+				const uint64_t lo = j + 1 == ng ? 0 : (uint64_t)((double)c0 * pow(1.0 - (double)(j + 1) / ng, gpow) * (1.0 - 0.4 / ng));
 				GenGroup gg;
 				gg.k0 = k;
 				while (k < gen.size() && (walk_cost(gen[k]) > lo || j + 1 == ng))
