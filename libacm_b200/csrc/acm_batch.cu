@@ -1020,9 +1020,17 @@ fail:
 extern "C" int acm_gpu_plan_launches(const acm_gpu_plan *p)
 {
 	int k = 0;
-	for (const Segment &sg : p->seg)
-		k += (sg.n_fast ? 1 : 0) + (sg.n_gen ? 2 + (sg.n_items ? 1 : 0) : 0) /* general path: scan, blocks, finish */
-		     + (sg.n_split ? 3 + (sg.sp_n_items ? 1 : 0) : 0);                /* split path: walk, unpack, lift, finish */
+	for (const Segment &sg : p->seg) {
+		k += (sg.n_fast ? 1 : 0) + (sg.n_split ? 3 + (sg.sp_n_items ? 1 : 0) : 0); /* split path: walk, unpack, lift, finish */
+		if (!sg.n_gen)
+			continue;
+		/* general path (launch_gen2): scan, unpack + tile lift (levels <= 10), blocks (levels > 10), finish -- per group */
+		if (p->grp.size() > 1)
+			for (const GenGroup &gg : p->grp)
+				k += 2 + (gg.n_tiles ? 2 : 0);
+		else
+			k += 2 + (sg.n_tiles ? 2 : 0) + (sg.n_items && sg.n_deep ? 1 : 0);
+	}
 	return k;
 }
 

@@ -429,4 +429,11 @@ def test_general_path_stream_groups(checker, monkeypatch):
             plan.fetch(s, st)
             assert gu.compare(imgs, s, d_out.cpu().numpy(), checker, checksums=True) == []
         plan.close()
+        # the one-shot entry point with device-resident buffers builds the same kind of plan
+        s2 = api.new_streams(offs, lens)
+        api.probe(d_blob, s2, opts)
+        assert api.layout(s2, opts.wordlen) == nbytes
+        d_out = torch.full((nbytes + 16,), 0x55, dtype=torch.uint8, device="cuda")
+        api.decode_batch(d_blob, s2, d_out, opts)
+        assert gu.compare(imgs, s2, d_out.cpu().numpy(), checker, checksums=True) == []
     assert {0, -6} <= set(s["status"].tolist())
