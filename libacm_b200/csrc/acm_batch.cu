@@ -362,15 +362,25 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 	 * and up to four of them are resident together */
 	max_ctas = nseg > 1 ? sm_count / (int)(nseg < 4 ? nseg : 4) : sm_count;
 	{
-		/* segment boundaries: equal shares of the output words */
+		/* segment boundaries by output words.  The pipeline's step is the first segment's latency
+		 * (copy-in + a decode that lasts as long as the walk of its longest stream, whatever its size)
+		 * plus the PCM's trip to the host, during which the copy engine should never wait for a decode:
+		 * the first segments are small (the copy-out starts early, and their copies are short enough for
+		 * the next decode to be done in time), the later ones make up for it: shares 1 : 2 : 3 : 4 : 5 : 6 : 6 ... */
 		uint64_t total = 0, acc = 0, first = 0;
+		double wsum = 0.0, wacc = 0.0;
+		static const bool ramp = !(getenv("ACM_B200_SEG_RAMP") && atoi(getenv("ACM_B200_SEG_RAMP")) == 0);
+		auto seg_weight = [nseg](unsigned g) { return ramp && nseg >= 4 ? (g < 5 ? 1.0 + g : 6.0) : 1.0; };
 		for (uint64_t i = 0; i < n; i++)
 			total += s[i].total_values;
+		for (unsigned g = 0; g < nseg; g++)
+			wsum += seg_weight(g);
 		for (unsigned g = 0; g < nseg; g++) {
 			Segment sg;
 			memset(&sg, 0, sizeof(sg));
 			sg.s_first = first;
-			uint64_t target = total / nseg * (g + 1);
+			wacc += seg_weight(g);
+			uint64_t target = (uint64_t)((double)total * (wacc / wsum));
 			uint64_t i = first;
 			if (g + 1 == nseg) {
 				i = n;
