@@ -180,6 +180,7 @@ struct Segment {
 	size_t ring_off;                  /* block-record rings of the fast kernel (offset in bytes) */
 	size_t ctl_off;                   /* slot control words (offset in bytes) */
 	uint32_t n_scan, n_slots;         /* fast kernel geometry: scan CTAs, slots in use */
+	uint32_t scan_warps;              /* ... scan warps in use per scan CTA */
 	bool sparse;                      /* the kernels do not write every byte of [out_lo, out_hi) */
 	int walk_bound;                   /* fast kernel: the longest stream's walk bounds the launch (more scan CTAs) */
 	uint64_t item_first, n_items;     /* general path: this segment's decode work items */
@@ -480,9 +481,10 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			for (const DevStream &d : fast)
 				blocks += d.n_attempt;
 			sg.walk_bound = fast2_walk_bound(fast[0].n_attempt, blocks, sm_count, max_ctas);
-			fast2_geometry(fast.size(), sm_count, max_ctas, &n_scan, &n_work, &n_slots, sg.walk_bound);
+			uint32_t scan_warps = 0;
+			fast2_geometry(fast.size(), sm_count, max_ctas, &n_scan, &n_work, &n_slots, sg.walk_bound, &scan_warps);
 			const size_t head = std::min<size_t>(n_slots, fast.size()) / 32 * 32, warps = head / 32;
-			int deal = sg.walk_bound ? 1 : 0;
+			int deal = sg.walk_bound && scan_warps == (uint32_t)fast2_scan_warps() ? 1 : 0; /* no partners in a sparse launch */
 			if (const char *e = getenv("ACM_B200_DEAL"))
 				deal = atoi(e);
 			if (warps > 1 && deal == 1) {
@@ -696,7 +698,7 @@ static acm_gpu_plan *plan_create(const acm_gpu_stream *s, uint64_t n, const acm_
 			sg.fast_ctas = 0;
 			if (sg.n_fast) {
 				uint32_t n_work = 0;
-				fast2_geometry(sg.n_fast, p->sm_count, max_ctas, &sg.n_scan, &n_work, &sg.n_slots, sg.walk_bound);
+				fast2_geometry(sg.n_fast, p->sm_count, max_ctas, &sg.n_scan, &n_work, &sg.n_slots, sg.walk_bound, &sg.scan_warps);
 				sg.fast_ctas = (int)(sg.n_scan + n_work);
 			}
 			hist_words += (size_t)sg.n_slots * fast2_hist_words_per_slot();
@@ -872,6 +874,7 @@ static int plan_run_segment(acm_gpu_plan *p, size_t g, const void *d_blob, void 
 	a.slotctl = p->d_ctl ? p->d_ctl + sg.ctl_off : nullptr;
 	a.scan_done = p->d_counters + 4 * g + 2;
 	a.n_scan = sg.n_scan;
+	a.scan_warps = sg.scan_warps;
 	a.n_slots = sg.n_slots;
 	a.resume_hist = nullptr;
 	a.resume_stride = 0;

@@ -1214,7 +1214,7 @@ __device__ __forceinline__ void decode_visit(SmemWork &sm, const KernelArgs &a, 
  */
 __device__ __forceinline__ void scan_cta(const KernelArgs &a, SmemScan &sm, int warp, int lane)
 {
-	const uint32_t g = (uint32_t)blockIdx.x * SLOTS + 32u * (uint32_t)warp + (uint32_t)lane;
+	const uint32_t g = (uint32_t)blockIdx.x * 32u * a.scan_warps + 32u * (uint32_t)warp + (uint32_t)lane;
 	const bool enabled = g < a.n_slots;
 	SlotCtl *const ctl = reinterpret_cast<SlotCtl *>(a.slotctl) + g;
 	uint8_t *const slot_ring = a.ring + (size_t)g * RING_D * REC_BYTES;
@@ -1469,7 +1469,7 @@ __device__ __forceinline__ void work_cta(const KernelArgs &a, SmemWork &sm, int 
 		return;
 	for (;;) {
 		PROF_MARK(0); /* 8+0: decode */
-		const bool done = *reinterpret_cast<volatile uint32_t *>(a.scan_done) == a.n_scan * (uint32_t)SW;
+		const bool done = *reinterpret_cast<volatile uint32_t *>(a.scan_done) == a.n_scan * a.scan_warps;
 		/* the free owned slot with the largest backlog: best = backlog << 8 | local index (0: none).
 		 * Largest first: the slots of the longest streams are the ones that fall behind while
 		 * decoding is the bottleneck, and whatever backlog they have when the scan ends is the
@@ -1566,7 +1566,7 @@ __global__ void __launch_bounds__(THREADS, 1) acm_decode_fast2_kernel(KernelArgs
 		for (int i = tid; i < SW * (RW + 1) * 32; i += THREADS)
 			(&sm.ring[0][0])[i] = 0u;
 		__syncthreads();
-		if (warp < SW)
+		if (warp < (int)a.scan_warps)
 			scan_cta(a, sm, warp, lane);
 	} else {
 		SmemWork &sm = *reinterpret_cast<SmemWork *>(smem_raw);
@@ -1602,7 +1602,7 @@ size_t fast2_smem_bytes() { return fast2::SMEM_BYTES; }
  * have the lowest block indices, so they are placed first).  n_slots = slots in use.
  */
 void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots,
-		    int walk_bound)
+		    int walk_bound, uint32_t *scan_warps)
 {
 #ifndef F2_SCAN_PCT
 #define F2_SCAN_PCT 22
@@ -1610,7 +1610,8 @@ void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uin
 	int total = max_ctas < sms ? max_ctas : sms;
 	if (total < 2)
 		total = 2;
-	const uint64_t want_scan = (count + fast2::SLOTS - 1) / fast2::SLOTS;
+	uint64_t want_scan = (count + fast2::SLOTS - 1) / fast2::SLOTS;
+	uint32_t sw = (uint32_t)fast2::SW;
 	/* A batch whose longest stream takes as long to WALK as the whole batch takes to decode (few, long
 	 * streams: BASELINE configs[1]) gets more scan CTAs: with a lane for every stream from the start no
 	 * lane is refilled, the scan warps thin out as their shorter streams end, and a round of a warp with
@@ -1626,10 +1627,23 @@ void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uin
 	uint32_t cap_scan = (uint32_t)((total * (walk_bound ? pct_walk : F2_SCAN_PCT) + 50) / 100);
 	if (cap_scan < 1)
 		cap_scan = 1;
+	/* A walk-bound batch small enough for it gets its lanes on ONE scan warp per SM sub-partition (the lower
+	 * half of twice as many scan CTAs): a scan warp that shares its sub-partition steps a third slower, and
+	 * here the SMs are there for the taking (a segment of the host path, a small resident batch). */
+	static const bool sparse_ok = !(getenv("ACM_B200_SCAN_SPARSE") && atoi(getenv("ACM_B200_SCAN_SPARSE")) == 0);
+	if (walk_bound && sparse_ok && scan_warps) {
+		const uint64_t want_half = (count + fast2::SLOTS / 2 - 1) / (fast2::SLOTS / 2);
+		if (want_half <= cap_scan) {
+			sw = (uint32_t)fast2::SW / 2u;
+			want_scan = want_half;
+		}
+	}
+	if (scan_warps)
+		*scan_warps = sw;
 	uint32_t ns = want_scan < cap_scan ? (uint32_t)want_scan : cap_scan;
 	if (ns < 1)
 		ns = 1;
-	uint64_t slots = (uint64_t)ns * fast2::SLOTS;
+	uint64_t slots = (uint64_t)ns * 32u * sw;
 	if (slots > count)
 		slots = (count + 31) / 32 * 32; /* whole warps */
 	/* one decode CTA per ~16 slots, at least one, at most what is left of the budget */

@@ -29,6 +29,7 @@ struct KernelArgs {
 	uint32_t *scan_done;      /* fast kernel: [0] scan warps that have finished, [1] heartbeat (zeroed before launch) */
 	uint32_t n_scan;          /* fast kernel: scan CTAs (the first n_scan of the grid) */
 	uint32_t n_slots;         /* fast kernel: stream slots in use */
+	uint32_t scan_warps;      /* fast kernel: scan warps in use per scan CTA (all of them, or one per SM sub-partition) */
 	unsigned long long *prof; /* 64 counters, only written by -DF2_PROF tuning builds */
 	/* generic kernel, resumable decode (acm_stream.cu): when resume_hist != NULL stream i of the
 	 * slice starts from / leaves its per-stage history at resume_hist + i * resume_stride (2*cols
@@ -140,7 +141,7 @@ bool fast_shape(uint32_t level, uint32_t rows);
 size_t fast2_smem_bytes();
 /* walk_bound: the batch's longest stream takes about as long to walk as the batch to decode (see fast2_walk_bound) */
 void fast2_geometry(uint64_t count, int sms, int max_ctas, uint32_t *n_scan, uint32_t *n_work, uint32_t *n_slots,
-		    int walk_bound);
+		    int walk_bound, uint32_t *scan_warps = nullptr);
 int fast2_walk_bound(uint64_t longest_blocks, uint64_t total_blocks, int sms, int max_ctas);
 size_t fast2_hist_words_per_slot();
 int fast2_scan_warps(); /* scan warps per scan CTA: warps w and w + half of them share an SM sub-partition */
