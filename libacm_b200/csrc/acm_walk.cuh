@@ -42,6 +42,8 @@ constexpr int RROW = 32 * SW;       /* words per ring row: one word of every lan
 #define WALK_PERIOD 32
 #endif
 constexpr int NHOLD = WALK_NHOLD;   /* 16-byte chunks a lane can take in per period */
+constexpr int NSMALL = 2;           /* ... and how many of them a top-up handles without asking whether any lane wants more */
+static_assert(NSMALL <= NHOLD, "top-up tiers");
 constexpr int NSTART = 4;           /* chunks a lane loads synchronously when it takes a new stream */
 constexpr int LEAD = RW / 4 - 2;    /* 16-byte chunks requested ahead of the read position */
 constexpr int PERIOD = WALK_PERIOD; /* walk steps between two top-ups */
@@ -149,8 +151,15 @@ struct Ring {
 				if ((uint32_t)k < hold_n)
 					hold[k] = trim(hold_c0 + k, hold[k]);
 		}
+		/* Most periods no lane of the warp moves more than NSMALL chunks (a lane that walks short columns
+		 * reads a few hundred bits per period): the chunks beyond them are skipped for the whole warp, one
+		 * vote and one uniform branch instead of the stores and loads of NHOLD - NSMALL chunks nobody wants
+		 * (the top-up was an eighth of the instructions of a warp whose walk bounds a launch) */
+		const bool many_st = __any_sync(0xFFFFFFFFu, hold_n > (uint32_t)NSMALL);
 #pragma unroll
 		for (int k = 0; k < NHOLD; k++) {
+			if (k >= NSMALL && !many_st)
+				break;
 			const uint32_t c = hold_c0 + k;
 			const bool on = (uint32_t)k < hold_n;
 			uint32_t *row = const_cast<uint32_t *>(rw) + (on ? (c & (RW / 4 - 1)) * (4u * RROW) : (RW + 1u) * RROW);
@@ -168,9 +177,13 @@ struct Ring {
 		int n = (int)(c0 + LEAD) - (int)f0;
 		n = n < NHOLD ? n : NHOLD;
 		n = base && n > 0 ? n : 0;
+		const bool many_ld = __any_sync(0xFFFFFFFFu, n > NSMALL);
 #pragma unroll
-		for (int k = 0; k < NHOLD; k++)
+		for (int k = 0; k < NHOLD; k++) {
+			if (k >= NSMALL && !many_ld)
+				break;
 			hold[k] = ldg_keep_v4(k < n && f0 + (uint32_t)k < room16 ? base + (size_t)(f0 + k) * 16u : safe, pol);
+		}
 		prefetch_l2(base && f0 + 64u < room16 ? base + (size_t)(f0 + 64u) * 16u : safe);
 		hold_c0 = f0;
 		hold_n = (uint32_t)n;
