@@ -121,6 +121,11 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 	/* M_OVER / M_REWALK: the lane has reached the rare end of its walk and waits (at most a period) for the
 	 * one place that deals with it, outside the unrolled steps */
 	enum { M_NONE = 0, M_HDR = 1, M_SEL = 2, M_K = 3, M_OVER = 4, M_REWALK = 5 };
+	/* A ring row has room for the lanes of eight warps (acm_walk.cuh), a scan CTA has four: the upper half of
+	 * rows 0..31 is the lanes' selector tables, entry i of a lane in row i at the lane's own bank */
+	static_assert(G2_SCAN_WARPS * 32 * 2 <= walk::RROW && walk::RW >= 32, "selector tables in the ring's unused half");
+	uint32_t *const seltab = &sm.ring[0][0] + walk::RROW / 2 + warp * 32 + lane;
+	constexpr uint32_t SELTAB_BYTE0 = (uint32_t)(walk::RROW / 2) * 4u; /* byte offset of that half within a row */
 	int mode = M_NONE;
 	bool exhausted = false;
 	uint32_t si = 0, cols = 0, rows = 0, limit = 0, nmax = 0, P = 0, Pblk = 0, b = 0, c = 0, rem = 0, ktab = 0, val = 0;
@@ -188,6 +193,19 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 				P = d.bit0;
 				b = 0;
 				ring.start(a.blob + d.base_off, a.blob_room > d.base_off ? a.blob_room - d.base_off : 0, d.file_end, P);
+				/* the lane's selector table (see the step): what a selector advances the position by for THIS
+				 * stream's row count -- f_zero 5 bits, f_linear 5 + rows * ind (decode.c:196-206), radix codes
+				 * whole (3 rows per 5- or 7-bit code, 2 for f_t37: decode.c:405-476), prefix codes and bad
+				 * selectors the 5 selector bits -- with the filler's class and sub-type above it */
+				for (uint32_t i = 0; i < 32u; i++) {
+					const uint32_t kind = tab.kind[i], cls = kind & 7u, sub = kind >> 3;
+					uint32_t adv = 5u;
+					if (cls == ACM_CLS_LINEAR)
+						adv += rows * i;
+					if (cls == ACM_CLS_T)
+						adv += sub == 0u ? t15_bits : sub == 1u ? t27_bits : t37_bits;
+					seltab[i * walk::RROW] = adv | (sub << 20) | (cls << 24);
+				}
 				mode = M_HDR;
 			} else {
 				exhausted = true;
@@ -217,7 +235,9 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			const bool in_k = mode == M_K;
 			uint32_t am = 0u - (uint32_t)act, hm = 0u - (uint32_t)hdr_ok;
 			asm volatile("" : "+r"(am), "+r"(hm));
-			const uint32_t ind = w & 31u, kind = tab.kind[ind], cls = kind & 7u, sub = kind >> 3;
+			const uint32_t e2 = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(&sm.ring[0][0]) +
+									      (((w & 31u) * (4u * walk::RROW)) | (SELTAB_BYTE0 + lane4)));
+			const uint32_t cls = e2 >> 24;
 			const uint32_t e_k = reinterpret_cast<const uint32_t *>(tab.k8)[2u * (ktab + (w & 255u))];
 			const uint32_t e_s = sm.sel13[w & 0x1FFFu];
 			{
@@ -226,11 +246,8 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 				asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.global.u32 [%0], %1;\n\t}"
 					     ::"l"(cp), "r"(P), "r"((uint32_t)(act && !in_k)) : "memory");
 			}
-			/* selector: f_zero 5 bits, f_linear 5 + rows * ind (decode.c:196-206), radix codes whole */
-			uint32_t tb = t15_bits;
-			tb = sub == 1u ? t27_bits : tb;
-			tb = sub == 2u ? t37_bits : tb;
-			const uint32_t adv_sel = 5u + (cls == ACM_CLS_LINEAR ? rows * ind : 0u) + (cls == ACM_CLS_T ? tb : 0u);
+			/* selector: the advance over the selector and a fixed-size payload, from the lane's table */
+			const uint32_t adv_sel = e2 & 0xFFFFFu;
 			/* prefix codes: whole symbols of the next 8 bits, up to the rows that remain -- inside a column
 			 * from its type's table, at a selector (the column's first step) from the 13-bit table */
 			const uint32_t e = in_k ? e_k : e_s;
@@ -252,7 +269,7 @@ __global__ void __launch_bounds__(32 * G2_SCAN_WARPS) acm_scan_kernel(KernelArgs
 			c += cd;
 			cp += cd;
 			mode = (int)((next_mode & am) | ((uint32_t)M_SEL & hm) | ((uint32_t)mode & ~(am | hm)));
-			ktab = (act && enter_k) ? sub * 256u : ktab;
+			ktab = (act && enter_k) ? (e2 >> 12) & 0x700u : ktab; /* sub-type * 256 */
 			rem = (act && is_k) ? nrem : rem;
 			/* the end of a block that ends inside the stream: its record (two predicated 16-byte stores) */
 			const bool endblk = act && mode == M_SEL && c == cols;
