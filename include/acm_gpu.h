@@ -144,6 +144,10 @@ int acm_gpu_plan_debug_counters(acm_gpu_plan *plan, unsigned long long *out64);
 /* grid geometry of the level-7 / 16-row kernel for n streams: out3 = { scan CTAs, decode CTAs, stream
  * slots }; host logic only (tests) */
 void acm_gpu_debug_geometry(uint64_t n, int sms, int max_ctas, uint32_t *out3);
+/* the same for a launch that is bound by the walk of its longest stream (few, long streams): out4 =
+ * { scan CTAs, decode CTAs, stream slots, scan warps in use per scan CTA (all 8, or one per SM
+ * sub-partition when the batch is small enough for twice as many scan CTAs) } */
+void acm_gpu_debug_geometry_walk(uint64_t n, int sms, int max_ctas, uint32_t *out4);
 
 /*
  * On-GPU corpus generation (test / benchmark input side, not part

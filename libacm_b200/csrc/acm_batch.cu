@@ -1093,6 +1093,11 @@ extern "C" void acm_gpu_debug_geometry(uint64_t n, int sms, int max_ctas, uint32
 	fast2_geometry(n, sms, max_ctas, &out3[0], &out3[1], &out3[2], 0);
 }
 
+extern "C" void acm_gpu_debug_geometry_walk(uint64_t n, int sms, int max_ctas, uint32_t *out4)
+{
+	fast2_geometry(n, sms, max_ctas, &out4[0], &out4[1], &out4[2], 1, &out4[3]);
+}
+
 /* the plan's 64 in-kernel counters, accumulated over its runs ([32]: blocks re-walked by the generic scan,
  * always counted; the cycle counters of -DF2_PROF tuning builds are zero otherwise) */
 extern "C" int acm_gpu_plan_debug_counters(acm_gpu_plan *p, unsigned long long *out64)

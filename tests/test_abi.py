@@ -59,4 +59,24 @@ def test_fast_kernel_geometry_rules():
                 assert n_slots <= (n + 31) // 32 * 32      # never more slots than streams (whole warps)
                 assert n_work == 1 or n_work % 2 == 1      # slots 0, 32, 64, .. (the longest streams) spread over all owners
     lib.acm_gpu_debug_geometry(10_000, 148, 148, out)
-    assert tuple(out) == (33, 115, 8448)                  # the bench's full-batch launch
+    assert tuple(out) == (33, 115, 8448)                  # a decode-bound launch of that size
+    # walk-bound launches (few, long streams): a lane for every stream if the scan share allows it, and ONE
+    # scan warp per sub-partition (4 of a scan CTA's 8) when that still fits
+    lib.acm_gpu_debug_geometry_walk.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint32)]
+    lib.acm_gpu_debug_geometry_walk.restype = None
+    out4 = (C.c_uint32 * 4)()
+    for sms in (8, 37, 132, 148):
+        for budget in sorted({sms // 4 or 2, sms}):
+            for n in (1, 31, 33, 300, 1250, 2500, 10_000, 125_000):
+                lib.acm_gpu_debug_geometry_walk(n, sms, budget, out4)
+                n_scan, n_work, n_slots, sw = tuple(out4)
+                assert sw in (4, 8) and n_scan >= 1 and n_work >= 1
+                assert n_scan + n_work <= max(2, min(budget, sms))
+                assert 32 <= n_slots <= n_scan * 32 * sw and n_slots % 32 == 0
+                assert n_slots <= n_work * 128 and n_slots <= (n + 31) // 32 * 32
+    lib.acm_gpu_debug_geometry_walk(10_000, 148, 148, out4)
+    assert tuple(out4) == (40, 107, 10016, 8)             # the bench's full-batch launch: every clip has a lane
+    lib.acm_gpu_debug_geometry_walk(1250, 148, 37, out4)
+    assert tuple(out4) == (10, 27, 1280, 4)               # a segment of the host path: sparse scan CTAs
+    lib.acm_gpu_debug_geometry_walk(300, 148, 148, out4)
+    assert tuple(out4)[0] == 3 and tuple(out4)[3] == 4    # a small resident batch
